@@ -1,0 +1,150 @@
+/*
+ * wun.h - C ABI of the B200 Wave-U-Net forward/backward engine (libwun.so).
+ *
+ * The reference has no FFI layer; its boundary for this path is the Python duck type
+ *     UnetAudioSeparator(model_config).get_padding(shape) / .get_output(mix, training, ...)
+ * (/root/reference/Models/UnetAudioSeparator.py:15-144) plus the loss / Adam lines of
+ * /root/reference/Training.py:50-77.  Each entry point below names the reference lines it replaces.
+ * The Python facade in wave-u-net_b200/Models/UnetAudioSeparator.py binds these with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (cudaStream_t travels as void*).
+ *   - every device pointer is CALLER-OWNED (the facade hands in torch CUDA tensors' data_ptr()).
+ *   - all tensors float32, channels-last [B, T, C] contiguous, like the reference (:88).
+ *   - parameters / gradients / Adam slots are ONE contiguous float32 buffer each, laid out by
+ *     wun_param_table() in TF variable-creation order (kernel [k, C_in, C_out], then bias, ...).
+ *   - return value: 0 = ok, negative = error; wun_last_error() gives the message (thread-local).
+ *     WUN_E_NOTIMPL mirrors the reference's NotImplementedError (:136, :144), WUN_E_SHAPE its
+ *     AssertionError (:55, :121, Utils.py:114-117).
+ *   - no hidden synchronisation, allocation or host<->device copy inside forward / backward / adam:
+ *     everything is enqueued on `stream`, so a whole step can be captured in a CUDA graph.
+ */
+#ifndef WUN_H
+#define WUN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WUN_OK           0
+#define WUN_E_INVALID   -1   /* bad argument / null pointer */
+#define WUN_E_NOTIMPL   -2   /* unknown upsampling / output_type / output_activation  */
+#define WUN_E_SHAPE     -3   /* infeasible shape (reference AssertionError)            */
+#define WUN_E_CUDA      -4   /* CUDA runtime error (message has the cudaError string)  */
+#define WUN_E_NOGPU     -5   /* compute entry point called without a usable CUDA device */
+
+#define WUN_MAX_SOURCES 8
+
+/* model_config keys read by UnetAudioSeparator.__init__ (:20-32) + num_sources (Config.py:49).
+ * upsampling: 0 = "linear", 1 = "learned".  output_type: 0 = "direct", 1 = "difference".
+ * output_activation: 0 = "tanh", 1 = "linear".  Any other value -> WUN_E_NOTIMPL at create. */
+typedef struct WunConfig {
+    int32_t num_layers;
+    int32_t num_initial_filters;
+    int32_t filter_size;
+    int32_t merge_filter_size;
+    int32_t input_filter_size;
+    int32_t output_filter_size;
+    int32_t upsampling;
+    int32_t output_type;
+    int32_t context;          /* 0 = "same" padding, 1 = "valid" (context) */
+    int32_t num_channels;     /* 1 if mono_downmix else 2 */
+    int32_t num_sources;      /* len(source_names) */
+    int32_t output_activation;
+} WunConfig;
+
+typedef struct WunParamInfo {
+    char     name[64];        /* TF variable name, e.g. "separator/conv1d_3/kernel" */
+    int32_t  ndim;
+    int32_t  shape[3];        /* kernel: [k, C_in, C_out]; bias: [C_out]; interp: [F] */
+    int64_t  offset;          /* element offset into the flat parameter buffer */
+    int64_t  numel;
+} WunParamInfo;
+
+typedef struct WunHandle WunHandle;
+
+/* --- pure host (usable without a GPU) ------------------------------------------------------- */
+
+/* UnetAudioSeparator.get_padding (:34-83): desired output frames -> (T_in, T_out). */
+int wun_get_padding(const WunConfig* cfg, int64_t num_frames, int64_t* t_in, int64_t* t_out);
+
+/* UnetAudioSeparator.__init__ (:15-32) for a fixed window: validates the config, solves all layer
+ * shapes for `num_frames` desired output frames and builds the launch plan.  No device work. */
+int wun_create(const WunConfig* cfg, int64_t num_frames, WunHandle** out);
+/* Same, but for a given INPUT window length (what get_output sees: mix.shape[1]). */
+int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle** out);
+int wun_destroy(WunHandle* h);
+
+int64_t wun_input_frames(const WunHandle* h);     /* T_in  */
+int64_t wun_output_frames(const WunHandle* h);    /* T_out */
+
+/* Variables under scope "separator" (:92) in creation order; what Utils.getTrainableVariables
+ * ("separator") (Utils.py:5-6) would list. */
+int64_t wun_param_count(const WunHandle* h);                 /* number of tensors  */
+int64_t wun_param_numel(const WunHandle* h);                 /* total float32 elements */
+int wun_param_table(const WunHandle* h, WunParamInfo* out, int64_t capacity);
+
+/* Bytes of scratch the engine needs for batch `batch` (activations kept for backward, gradients of
+ * activations, reduction scratch).  `training` = 0 sizes it for forward only. */
+int64_t wun_workspace_bytes(const WunHandle* h, int64_t batch, int training);
+
+/* Algorithmic work of one forward pass at batch `batch` (live positions only, 2 FLOP per MAC) and
+ * of forward+backward; used by bench.py for the roofline. */
+double wun_forward_flops(const WunHandle* h, int64_t batch);
+double wun_forward_backward_flops(const WunHandle* h, int64_t batch);
+
+/* Number of kernels one call enqueues (for bench.py's gpu_launches claim). */
+int64_t wun_launches_forward(const WunHandle* h);
+int64_t wun_launches_forward_backward(const WunHandle* h);
+
+/* --- device entry points ---------------------------------------------------------------------- */
+
+/* get_output (:85-144): mix [B, T_in, C] -> sources, written to `outputs` as
+ * [num_sources][B, T_out, C] contiguous in source_names order.  `training` = 0 applies AudioClip
+ * (Utils.py:89-92) exactly where the reference does. */
+int wun_forward(WunHandle* h, const float* params, const float* mix, int64_t batch, int training,
+                float* outputs, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One training-graph evaluation (Training.py:47-63 + the tf.gradients half of :77):
+ * forward, MSE loss  sum_k mean((target_k - est_k)^2) / K  -> *loss (device scalar), and the
+ * gradient of that loss wrt every parameter -> `grads` (flat, same layout as params; overwritten).
+ * targets: [num_sources][B, T_out, C].  outputs may be NULL.  grad_scale multiplies the gradient
+ * (1/world_size for data-parallel averaging; 1.0 otherwise). */
+int wun_forward_backward(WunHandle* h, const float* params, const float* mix, const float* targets,
+                         int64_t batch, float* outputs, float* loss, float* grads, float grad_scale,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* tf.train.AdamOptimizer(lr).minimize update (Training.py:77), TF formulation:
+ *   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m,v moments;  p -= lr_t * m / (sqrt(v) + eps).
+ * `step` = t >= 1.  One fused pass over the flat buffers. */
+int wun_adam_step(WunHandle* h, float* params, const float* grads, float* m, float* v, int64_t step,
+                  float lr, float beta1, float beta2, float eps, void* stream);
+
+/* Evaluate.predict_track (Evaluate.py:117-143) device side: cut `n_windows` windows
+ * [T_in, C] starting at frame positions `starts[i]` (DEVICE array, int64) out of the already padded mixture
+ * `padded` [n_padded, C] (device) into `mix_batch` [n_windows, T_in, C]  (gather), and
+ * scatter window outputs [num_sources][n_windows, T_out, C] back into `preds`
+ * [num_sources][n_frames, C] at `starts[i]` (plain overwrite, later windows win). */
+int wun_gather_windows(WunHandle* h, const float* padded, int64_t n_padded, const int64_t* starts,
+                       int64_t n_windows, float* mix_batch, void* stream);
+int wun_scatter_windows(WunHandle* h, const float* outputs, const int64_t* starts, int64_t n_windows,
+                        float* preds, int64_t n_frames, void* stream);
+
+/* --- diagnostics -------------------------------------------------------------------------------- */
+const char* wun_last_error(void);
+const char* wun_version(void);
+/* Human-readable plan (layer shapes, live windows, kernel choice per layer) into buf; returns the
+ * number of bytes that the full text needs. */
+int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity);
+/* Which kernel family a conv layer uses: "simt" or "umma".  layer: 0..L-1 down, L bottleneck,
+ * L+1..2L up.  pass: 0 fwd, 1 dgrad, 2 wgrad. */
+const char* wun_layer_kernel(const WunHandle* h, int layer, int pass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WUN_H */

@@ -1,0 +1,132 @@
+"""CPU tests of the host side: Config shim, C-ABI symbols, shape solver, parameter table, plan FLOPs.
+No compute entry point is exercised (no GPU needed); they must fail loudly without one."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import Config
+import wun
+from Models.UnetAudioSeparator import UnetAudioSeparator
+from oracle import wave_unet_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def mc(named=(), **kw):
+    return Config.build_config(list(named), kw, experiment_id=0)["model_config"]
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "wun.h")).read()
+    declared = set(re.findall(r"\b(wun_[a-z_]+)\s*\(", header))
+    assert declared == set(wun.SYMBOLS), declared ^ set(wun.SYMBOLS)
+    lib = ctypes.CDLL(wun.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in wun.lib.wun_version()
+
+
+def test_config_presets_and_cli():
+    c = mc(["baseline_stereo"])
+    assert (c["output_type"], c["context"], c["mono_downmix"], c["num_channels"]) == ("difference", True, False, 2)
+    assert c["source_names"] == ["accompaniment", "vocals"] and c["num_sources"] == 2
+    c = mc(["full_multi_instrument"])
+    assert c["source_names"] == ["bass", "drums", "other", "vocals"] and c["num_sources"] == 4
+    cfg, extras = Config.parse_command_line(
+        ["with", "cfg.full_44KHz", "cfg.model_config.batch_size=8", "input_path=a.mp3", "model_config.task=voice"])
+    assert cfg["model_config"]["expected_sr"] == 44100 and cfg["model_config"]["batch_size"] == 8
+    assert cfg["model_config"]["upsampling"] == "learned" and extras == {"input_path": "a.mp3"}
+    with pytest.raises(NotImplementedError):
+        mc([], task="speech")
+    with pytest.raises(KeyError):
+        mc(["nonexistent"])
+    # defaults == reference base dict values (Config.py:9-39)
+    d = mc([])
+    assert (d["num_layers"], d["filter_size"], d["merge_filter_size"], d["num_initial_filters"],
+            d["num_frames"], d["batch_size"], d["init_sup_sep_lr"]) == (12, 15, 5, 24, 16384, 16, 1e-4)
+
+
+def test_get_padding_facade_matches_reference_rows():
+    rows = json.load(open(os.path.join(GOLDEN, "padding.json")))
+    for r in rows:
+        cfg = mc([r["preset"]]) if "preset" in r else mc(["baseline_context"], **r["overrides"])
+        if cfg["network"] != "unet":
+            continue
+        sep = UnetAudioSeparator(cfg)
+        shape = np.array([cfg["batch_size"] if "preset" in r else 3, r["num_frames"], 0])
+        if "error" in r:
+            with pytest.raises(AssertionError):
+                sep.get_padding(shape)
+            continue
+        i, o = sep.get_padding(shape)
+        assert [int(v) for v in i] == r["in_shape"], r
+        assert [int(v) for v in o] == r["out_shape"], r
+        if cfg["context"]:
+            assert isinstance(i, np.ndarray) and i.dtype == np.int64
+        else:
+            assert isinstance(i, list)
+
+
+@pytest.mark.parametrize("preset", ["baseline", "baseline_stereo", "full", "full_multi_instrument",
+                                    "baseline_context", "baseline_diff"])
+def test_param_table_matches_oracle(preset):
+    cfg = mc([preset])
+    sep = UnetAudioSeparator(cfg)
+    eng = sep.engine(num_frames=cfg["num_frames"])
+    want = O.param_table(cfg)
+    assert [(n, tuple(s)) for n, s, _, _ in eng.param_table] == [(n, tuple(s)) for n, s in want]
+    off = 0
+    for n, s, o, c in eng.param_table:
+        assert o == off and c == int(np.prod(s))
+        off += c
+    assert off == eng.param_numel
+    assert (eng.T_in, eng.T_out) == O.get_padding(cfg, cfg["num_frames"])
+
+
+def test_live_flops_match_survey():
+    """live forward GFLOP at B=16: M4 222.65, M6(B=32) 445.41, M1 78.20; fwd+bwd 666.1."""
+    e = UnetAudioSeparator(mc(["baseline_stereo"])).engine(num_frames=16384)
+    assert abs(e.forward_flops(16) * 1e-9 - 222.65) < 0.05
+    assert abs(e.forward_backward_flops(16) * 1e-9 - 666.1) < 0.2
+    e = UnetAudioSeparator(mc(["full_multi_instrument"])).engine(num_frames=16384)
+    assert abs(e.forward_flops(32) * 1e-9 - 445.41) < 0.1
+    e = UnetAudioSeparator(mc(["baseline"])).engine(num_frames=16384)
+    assert abs(e.forward_flops(16) * 1e-9 - 78.20) < 0.05
+
+
+def test_errors_mirror_reference():
+    with pytest.raises(NotImplementedError):
+        wun.Engine(wun.config_from_model_config(dict(mc(["baseline"]), output_type="foo")), num_frames=64)
+    with pytest.raises(NotImplementedError):
+        wun.Engine(wun.config_from_model_config(dict(mc(["baseline"]), output_activation="relu")), num_frames=64)
+    with pytest.raises(AssertionError):      # :121 - lengths must match without context
+        wun.Engine(wun.config_from_model_config(mc(["baseline"])), num_frames=1000)
+    with pytest.raises(AssertionError):      # :55
+        wun.Engine(wun.config_from_model_config(mc(["baseline_context"], num_layers=1, filter_size=3,
+                                                   merge_filter_size=3, input_filter_size=3)), num_frames=-10)
+
+
+def test_workspace_and_describe():
+    e = UnetAudioSeparator(mc(["baseline_stereo"])).engine(num_frames=16384)
+    inf, tr = e.workspace_bytes(16, False), e.workspace_bytes(16, True)
+    assert 0 < inf < tr < 4e9          # ~0.6 GB saved activations + gradients at B=16
+    d = e.describe()
+    assert "down0" in d and "up11" in d and "T_in=147443" in d
+    assert e.launches(False) > 20 and e.launches(True) > e.launches(False)
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has GPU")
+    e = UnetAudioSeparator(mc(["baseline"], num_layers=2)).engine(num_frames=64)
+    buf = (ctypes.c_float * 16)()
+    rc = wun.lib.wun_forward(e._h, ctypes.addressof(buf), ctypes.addressof(buf), 1, 0, ctypes.addressof(buf),
+                             ctypes.addressof(buf), 1 << 40, None)
+    assert rc == wun.WUN_E_NOGPU
+    assert b"no CPU fallback" in wun.lib.wun_last_error()

@@ -1,0 +1,8 @@
+#!/bin/bash
+# Builds libwun.so (the C-ABI engine) in-tree for sm_100a.  Cross-compiles without a GPU.
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared \
+      -o libwun.so csrc/plan.cpp csrc/kernels_simt.cu csrc/engine.cu csrc/umma.cu -lcuda "$@"
+echo "built $(pwd)/libwun.so"

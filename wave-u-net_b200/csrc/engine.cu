@@ -1,0 +1,601 @@
+// engine.cu - C ABI (include/wun.h) of the B200 Wave-U-Net engine: turns the host plan into kernel launches.
+//
+// Forward  = get_output             /root/reference/Models/UnetAudioSeparator.py:85-144
+// Backward = what tf.gradients builds for AdamOptimizer.minimize, /root/reference/Training.py:77
+// (the reference has no backward source; the derivation is in DESIGN.md "Backward").
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wun.h"
+#include "kernels.h"
+#include "launch.h"
+#include "plan.h"
+#include "umma.h"
+
+using namespace wun;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& m) { g_err = m; return code; }
+
+#define WUN_CUDA_OK(expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return set_err(WUN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+namespace {
+
+struct DgradClass {
+    int plane;            // forward plane whose gradient this class produces
+    int r_lo, r_hi;       // rows written
+    int acc_lo, acc_hi;   // rows accumulated into an earlier write
+};
+
+struct OpBackward {
+    std::vector<DgradClass> dgrad;   // empty: no input gradient needed (down0)
+};
+
+struct Layout {
+    std::vector<int64_t> off;   // float offsets per tensor; -1 = not allocated
+    int64_t total = 0;
+};
+
+}  // namespace
+
+struct WunHandle {
+    Plan plan;
+    std::vector<OpBackward> bwd_down, bwd_up;
+    OpBackward bwd_bottleneck;
+    UmmaState umma;                      // tensor-core path state (weight packs, eligibility)
+    // per-call state
+    bool dry = false;
+    int64_t launches = 0;
+    cudaStream_t stream = nullptr;
+    const float* params = nullptr;
+    const float* mix = nullptr;
+    float* ws = nullptr;
+    Layout lay;
+    int batch = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// planning helpers
+// ------------------------------------------------------------------------------------------------
+static void touched_range(const ConvOp& op, int plane, int* lo, int* hi) {
+    int l = 1 << 30, h = -(1 << 30);
+    for (const auto& c : op.classes) {
+        if (c.m_hi <= c.m_lo) continue;
+        for (const auto& t : c.terms)
+            if (t.plane == plane) {
+                l = std::min(l, c.m_lo + t.d);
+                h = std::max(h, c.m_hi - 1 + t.d + 1);
+            }
+    }
+    const ViewSpec& v = op.planes[plane];
+    l = std::max(l, v.r_lo);
+    h = std::min(h, v.r_hi);
+    if (h < l) h = l;
+    *lo = l; *hi = h;
+}
+
+static inline int ceil_div_floor(int a, int s) {   // ceil(a / s) for s > 0, any sign of a
+    return (a >= 0) ? (a + s - 1) / s : -((-a) / s);
+}
+
+static void plan_backward(WunHandle* h) {
+    Plan& P = h->plan;
+    const int L = P.cfg.num_layers;
+    std::map<int, std::pair<int, int>> written;   // grad tensor -> tensor-row range written so far
+    auto plan_op = [&](const ConvOp& op, OpBackward* ob, bool is_up) {
+        for (size_t p = 0; p < op.planes.size(); ++p) {
+            const int gt = op.plane_grad_tensor[p];
+            if (gt == -2) continue;
+            const ViewSpec& v = op.planes[p];
+            DgradClass dc;
+            dc.plane = (int)p;
+            if (is_up && p == 0) touched_range(op, 0, &dc.r_lo, &dc.r_hi);
+            else { dc.r_lo = v.r_lo; dc.r_hi = v.r_hi; }
+            dc.acc_lo = dc.acc_hi = 0;
+            auto it = written.find(gt);
+            if (it != written.end() && gt != P.t_gue && gt != P.t_gmid) {
+                const int wlo = it->second.first, whi = it->second.second;
+                dc.acc_lo = ceil_div_floor(wlo - v.row_offset, v.row_step);
+                dc.acc_hi = ceil_div_floor(whi - v.row_offset, v.row_step);
+            }
+            ob->dgrad.push_back(dc);
+        }
+        // record writes after the whole op (both parities of one tensor belong to the same op)
+        for (const auto& dc : ob->dgrad) {
+            const ViewSpec& v = op.planes[dc.plane];
+            const int gt = op.plane_grad_tensor[dc.plane];
+            if (dc.r_hi <= dc.r_lo) continue;
+            int lo = v.row_offset + dc.r_lo * v.row_step;
+            int hi = v.row_offset + (dc.r_hi - 1) * v.row_step + 1;
+            auto it = written.find(gt);
+            if (it == written.end()) written[gt] = {lo, hi};
+            else it->second = {std::min(it->second.first, lo), std::max(it->second.second, hi)};
+        }
+    };
+    h->bwd_up.assign(L, OpBackward());
+    h->bwd_down.assign(L, OpBackward());
+    for (int i = L - 1; i >= 0; --i) plan_op(P.up[i], &h->bwd_up[i], true);
+    plan_op(P.bottleneck, &h->bwd_bottleneck, false);
+    for (int i = L - 1; i >= 0; --i) plan_op(P.down[i], &h->bwd_down[i], false);
+}
+
+static Layout make_layout(const Plan& P, int64_t B, bool training) {
+    Layout l;
+    l.off.assign(P.tensors.size(), -1);
+    int64_t cur = 0;
+    for (size_t i = 0; i < P.tensors.size(); ++i) {
+        const TensorSpec& t = P.tensors[i];
+        if (t.training_only && !training) continue;
+        int64_t n = t.rows * t.C * (t.per_batch ? B : 1);
+        l.off[i] = cur;
+        cur += (n + 63) / 64 * 64;
+    }
+    l.total = cur + 64;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// materialisation of launch blocks
+// ------------------------------------------------------------------------------------------------
+static const float* tensor_ptr(const WunHandle* h, int tensor) {
+    if (tensor == TENSOR_MIX) return h->mix;
+    return h->ws + h->lay.off[tensor];
+}
+
+static void tensor_geom(const WunHandle* h, int tensor, int64_t* rows, int* C, bool* per_batch) {
+    if (tensor == TENSOR_MIX) { *rows = h->plan.T_in; *C = h->plan.cfg.num_channels; *per_batch = true; return; }
+    const TensorSpec& t = h->plan.tensors[tensor];
+    *rows = t.rows; *C = t.C; *per_batch = t.per_batch;
+}
+
+static PlaneView make_plane(const WunHandle* h, const ViewSpec& v) {
+    PlaneView p;
+    memset(&p, 0, sizeof(p));
+    int64_t rows; int C; bool pb;
+    tensor_geom(h, v.tensor, &rows, &C, &pb);
+    p.base = tensor_ptr(h, v.tensor) + (long long)v.row_offset * C;
+    p.bstride = pb ? rows * C : 0;
+    p.rstride = v.row_step * C;
+    p.r_lo = v.r_lo; p.r_hi = v.r_hi; p.C = v.C;
+    p.kind = v.kind; p.mid_mode = v.mid_mode; p.xrows = v.xrows;
+    p.blend = (v.blend_tensor >= 0) ? tensor_ptr(h, v.blend_tensor) : nullptr;
+    return p;
+}
+
+// the same geometry as `v`, but on another tensor (gradient twin / scratch) with explicit batch stride
+static PlaneView make_plane_on(const WunHandle* h, const ViewSpec& v, int tensor, long long bstride, int r_lo, int r_hi) {
+    PlaneView p;
+    memset(&p, 0, sizeof(p));
+    p.base = tensor_ptr(h, tensor) + (long long)v.row_offset * v.C;
+    p.bstride = bstride;
+    p.rstride = v.row_step * v.C;
+    p.r_lo = r_lo; p.r_hi = r_hi; p.C = v.C;
+    p.kind = PLANE_DIRECT;
+    return p;
+}
+
+static long long view_bstride(const WunHandle* h, const ViewSpec& v) {
+    int64_t rows; int C; bool pb;
+    tensor_geom(h, v.tensor, &rows, &C, &pb);
+    return rows * C;
+}
+
+static void launch_conv(WunHandle* h, const ConvLaunch& L) {
+    ++h->launches;
+    if (!h->dry) launch_plane_conv_simt(L, h->stream);
+}
+
+static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
+    if (umma_try_forward(h->umma, h->plan, op, layer_index, h->params, h->mix, h->ws, h->lay.off.data(), h->batch,
+                         h->stream, h->dry, &h->launches))
+        return WUN_OK;
+    ConvLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.nplanes = (int)op.planes.size();
+    for (int p = 0; p < L.nplanes; ++p) L.planes[p] = make_plane(h, op.planes[p]);
+    L.ncls = (int)op.classes.size();
+    int nt = 0, max_rows = 0;
+    for (int q = 0; q < L.ncls; ++q) {
+        const ClassSpec& c = op.classes[q];
+        OutView& o = L.cls[q];
+        PlaneView ov = make_plane(h, c.out);
+        o.base = const_cast<float*>(ov.base); o.bstride = ov.bstride; o.rstride = ov.rstride;
+        o.m_lo = c.m_lo; o.m_hi = c.m_hi; o.saved = nullptr; o.acc_lo = o.acc_hi = 0;
+        o.term_begin = nt;
+        for (const auto& t : c.terms) {
+            if (nt >= kMaxTerms) return set_err(WUN_E_INVALID, "too many conv terms");
+            L.terms[nt++] = {t.plane, t.d, (t.tap * op.cin_tot + t.coff) * op.cout};
+        }
+        o.term_end = nt;
+        max_rows = std::max(max_rows, c.m_hi - c.m_lo);
+    }
+    L.N = op.cout; L.w_sk = op.cout; L.w_sn = 1;
+    L.W = h->params + h->plan.params[op.w_param].offset;
+    L.bias = h->params + h->plan.params[op.b_param].offset;
+    L.epilogue = EPI_BIAS_LRELU; L.batch = h->batch; L.max_rows = max_rows;
+    launch_conv(h, L);
+    return WUN_OK;
+}
+
+// dgrad: one class per forward input plane that needs a gradient; the forward classes' gradient
+// tensors become the input planes.
+static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob) {
+    if (ob.dgrad.empty()) return WUN_OK;
+    const Plan& P = h->plan;
+    ConvLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.nplanes = (int)op.classes.size();
+    for (int q = 0; q < L.nplanes; ++q) {
+        const ClassSpec& c = op.classes[q];
+        L.planes[q] = make_plane_on(h, c.out, P.grad_twin[c.out.tensor], view_bstride(h, c.out), c.m_lo, c.m_hi);
+    }
+    L.ncls = (int)ob.dgrad.size();
+    int nt = 0, max_rows = 0;
+    for (int k = 0; k < L.ncls; ++k) {
+        const DgradClass& dc = ob.dgrad[k];
+        const ViewSpec& v = op.planes[dc.plane];
+        const int gt = op.plane_grad_tensor[dc.plane];
+        long long bs = view_bstride(h, v);
+        if (gt == P.t_gmid) bs = (long long)(v.r_hi - v.r_lo) * v.C;   // [B, nmid, C]
+        PlaneView ov = make_plane_on(h, v, gt, bs, dc.r_lo, dc.r_hi);
+        OutView& o = L.cls[k];
+        o.base = const_cast<float*>(ov.base); o.bstride = ov.bstride; o.rstride = ov.rstride;
+        o.m_lo = dc.r_lo; o.m_hi = dc.r_hi;
+        o.saved = op.plane_slope[dc.plane] ? make_plane(h, v).base : nullptr;
+        o.acc_lo = dc.acc_lo; o.acc_hi = dc.acc_hi;
+        o.term_begin = nt;
+        for (int q = 0; q < (int)op.classes.size(); ++q)
+            for (const auto& t : op.classes[q].terms)
+                if (t.plane == dc.plane) {
+                    if (nt >= kMaxTerms) return set_err(WUN_E_INVALID, "too many dgrad terms");
+                    L.terms[nt++] = {q, -t.d, (t.tap * op.cin_tot + t.coff) * op.cout};
+                }
+        // sort by (plane, d)
+        std::stable_sort(L.terms + o.term_begin, L.terms + nt, [](const Term& a, const Term& b) {
+            if (a.plane != b.plane) return a.plane < b.plane;
+            return a.d < b.d;
+        });
+        o.term_end = nt;
+        max_rows = std::max(max_rows, dc.r_hi - dc.r_lo);
+        L.N = v.C;   // all classes of one op's dgrad have... (checked below)
+    }
+    // classes may differ in channel count (skip vs upsampled planes): launch per distinct N
+    std::vector<int> done(L.ncls, 0);
+    for (int k = 0; k < L.ncls; ++k) {
+        if (done[k]) continue;
+        const int N = op.planes[ob.dgrad[k].plane].C;
+        ConvLaunch S = L;
+        S.ncls = 0; S.max_rows = 0;
+        for (int k2 = k; k2 < L.ncls; ++k2)
+            if (!done[k2] && op.planes[ob.dgrad[k2].plane].C == N) {
+                S.cls[S.ncls++] = L.cls[k2];
+                S.max_rows = std::max(S.max_rows, L.cls[k2].m_hi - L.cls[k2].m_lo);
+                done[k2] = 1;
+            }
+        S.N = N; S.w_sk = 1; S.w_sn = op.cout;
+        S.W = h->params + P.params[op.w_param].offset;
+        S.bias = nullptr;
+        // slope is per class (saved != null); classes without saved use EPI_PLAIN semantics via null check
+        S.epilogue = EPI_SLOPE;
+        S.batch = h->batch;
+        if (S.max_rows > 0) launch_conv(h, S);
+    }
+    return WUN_OK;
+}
+
+static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale) {
+    const Plan& P = h->plan;
+    for (const auto& c : op.classes) {
+        if (c.m_hi <= c.m_lo) continue;
+        PlaneView dpre = make_plane_on(h, c.out, P.grad_twin[c.out.tensor], view_bstride(h, c.out), c.m_lo, c.m_hi);
+        // bias gradient
+        ++h->launches;
+        if (!h->dry) launch_colsum(dpre, h->batch, scale, grads + P.params[op.b_param].offset, h->stream);
+        size_t i = 0;
+        while (i < c.terms.size()) {
+            WgradLaunch W;
+            memset(&W, 0, sizeof(W));
+            const int p = c.terms[i].plane;
+            int dmin = c.terms[i].d;
+            while (i < c.terms.size() && c.terms[i].plane == p && W.nterms < 8 && c.terms[i].d - dmin <= 15) {
+                W.d[W.nterms] = c.terms[i].d;
+                W.woff[W.nterms] = (c.terms[i].tap * op.cin_tot + c.terms[i].coff) * op.cout;
+                ++W.nterms; ++i;
+            }
+            W.plane = make_plane(h, op.planes[p]);
+            W.dpre = dpre;
+            W.m_lo = c.m_lo; W.m_hi = c.m_hi;
+            W.N = op.cout; W.w_sk = op.cout; W.w_sn = 1;
+            W.dW = grads + P.params[op.w_param].offset;
+            W.scale = scale; W.batch = h->batch;
+            ++h->launches;
+            if (!h->dry) launch_plane_wgrad_simt(W, h->stream);
+        }
+    }
+    return WUN_OK;
+}
+
+static void fill_output_launch(const WunHandle* h, OutputLaunch* O, const float* targets, float* outputs, float* loss,
+                               int training) {
+    const Plan& P = h->plan;
+    memset(O, 0, sizeof(*O));
+    O->params = h->params;
+    for (int s = 0; s < P.nconv; ++s) {
+        O->w_off[s] = P.params[P.out_w_param[s]].offset;
+        O->b_off[s] = P.params[P.out_b_param[s]].offset;
+    }
+    O->mix = h->mix;
+    O->feat = tensor_ptr(h, P.t_feat);
+    O->targets = targets;
+    O->outputs = outputs;
+    O->dpre = (h->lay.off[P.t_dpre_out] >= 0) ? const_cast<float*>(tensor_ptr(h, P.t_dpre_out)) : nullptr;
+    O->loss = loss;
+    O->batch = h->batch; O->T_in = (int)P.T_in; O->Tf = (int)P.Tf; O->T_out = (int)P.T_out;
+    O->C = P.cfg.num_channels; O->F = P.cfg.num_initial_filters;
+    O->nconv = P.nconv; O->K = P.cfg.num_sources;
+    O->ofs = P.cfg.output_filter_size; O->pad_left = P.out_pad_left;
+    O->crop_feat = P.crop_feat; O->crop_out = P.crop_out;
+    O->output_type = P.cfg.output_type; O->activation = P.cfg.output_activation; O->training = training;
+    O->inv_count = 1.0f / (float)((double)h->batch * P.T_out * P.cfg.num_channels * P.cfg.num_sources);
+}
+
+static int run_forward(WunHandle* h, const float* targets, float* outputs, float* loss, int training) {
+    const Plan& P = h->plan;
+    const int L = P.cfg.num_layers;
+    for (int i = 0; i < L; ++i) {
+        const UpsampleSpec& us = P.ups[i];
+        if (us.interp_param >= 0) {
+            ++h->launches;
+            if (!h->dry)
+                launch_sigmoid(h->params + P.params[us.interp_param].offset,
+                               const_cast<float*>(tensor_ptr(h, us.wsig_tensor)), us.C, h->stream);
+        }
+    }
+    int rc;
+    for (int i = 0; i < L; ++i)
+        if ((rc = conv_forward(h, P.down[i], i)) != WUN_OK) return rc;
+    if ((rc = conv_forward(h, P.bottleneck, L)) != WUN_OK) return rc;
+    for (int i = 0; i < L; ++i)
+        if ((rc = conv_forward(h, P.up[i], L + 1 + i)) != WUN_OK) return rc;
+    OutputLaunch O;
+    fill_output_launch(h, &O, targets, outputs, loss, training);
+    ++h->launches;
+    if (!h->dry) launch_output_fwd(O, h->stream);
+    return WUN_OK;
+}
+
+static int run_backward(WunHandle* h, const float* targets, float* grads, float scale) {
+    const Plan& P = h->plan;
+    const int L = P.cfg.num_layers;
+    int rc;
+    OutputLaunch O;
+    fill_output_launch(h, &O, targets, nullptr, nullptr, 1);
+    h->launches += 2;
+    if (!h->dry) {
+        launch_output_wgrad(O, grads, scale, h->stream);
+        launch_output_dgrad(O, const_cast<float*>(tensor_ptr(h, P.grad_twin[P.t_feat])), h->stream);
+    }
+    for (int i = L - 1; i >= 0; --i) {
+        const ConvOp& op = P.up[i];
+        if ((rc = conv_wgrad(h, op, grads, scale)) != WUN_OK) return rc;
+        if ((rc = conv_dgrad(h, op, h->bwd_up[i])) != WUN_OK) return rc;
+        const UpsampleSpec& us = P.ups[i];
+        UpsampleBwdLaunch U;
+        memset(&U, 0, sizeof(U));
+        U.due = tensor_ptr(h, P.t_gue);
+        U.dmid = tensor_ptr(h, P.t_gmid);
+        U.x = tensor_ptr(h, us.src_tensor);
+        U.gx = const_cast<float*>(tensor_ptr(h, P.grad_twin[us.src_tensor]));
+        U.blend = (us.wsig_tensor >= 0) ? tensor_ptr(h, us.wsig_tensor) : nullptr;
+        U.dvar = (us.interp_param >= 0) ? grads + P.params[us.interp_param].offset : nullptr;
+        U.batch = h->batch; U.N = us.N; U.nmid = us.nmid; U.C = us.C; U.mid_mode = us.mid_mode; U.scale = scale;
+        ++h->launches;
+        if (!h->dry) launch_upsample_bwd(U, h->stream);
+    }
+    if ((rc = conv_wgrad(h, P.bottleneck, grads, scale)) != WUN_OK) return rc;
+    if ((rc = conv_dgrad(h, P.bottleneck, h->bwd_bottleneck)) != WUN_OK) return rc;
+    for (int i = L - 1; i >= 0; --i) {
+        if ((rc = conv_wgrad(h, P.down[i], grads, scale)) != WUN_OK) return rc;
+        if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i])) != WUN_OK) return rc;
+    }
+    return WUN_OK;
+}
+
+static int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_err(WUN_E_NOGPU, "no CUDA device: the engine has no CPU fallback");
+    }
+    return WUN_OK;
+}
+
+static int begin_call(WunHandle* h, const float* params, const float* mix, int64_t batch, bool training, void* ws,
+                      int64_t ws_bytes, void* stream, bool dry) {
+    if (!h) return set_err(WUN_E_INVALID, "null handle");
+    if (batch < 1 || batch > (1 << 20)) return set_err(WUN_E_INVALID, "batch out of range");
+    h->lay = make_layout(h->plan, batch, training);
+    h->dry = dry;
+    h->launches = 0;
+    h->batch = (int)batch;
+    if (dry) return WUN_OK;
+    if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
+    if (ws_bytes < h->lay.total * (int64_t)sizeof(float)) return set_err(WUN_E_INVALID, "workspace too small");
+    int rc = check_device();
+    if (rc != WUN_OK) return rc;
+    h->params = params; h->mix = mix; h->ws = (float*)ws; h->stream = (cudaStream_t)stream;
+    return WUN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* wun_last_error(void) { return g_err.c_str(); }
+const char* wun_version(void) { return "wun-b200 0.1 (sm_100a)"; }
+
+int wun_get_padding(const WunConfig* cfg, int64_t num_frames, int64_t* t_in, int64_t* t_out) {
+    if (!cfg || !t_in || !t_out) return set_err(WUN_E_INVALID, "null argument");
+    std::string msg;
+    int rc = solve_padding(*cfg, num_frames, t_in, t_out, &msg);
+    if (rc != WUN_OK) return set_err(rc, msg);
+    return WUN_OK;
+}
+
+int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle** out) {
+    if (!cfg || !out) return set_err(WUN_E_INVALID, "null argument");
+    WunHandle* h = new WunHandle();
+    std::string msg;
+    int rc = build_plan(*cfg, input_frames, &h->plan, &msg);
+    if (rc != WUN_OK) { delete h; return set_err(rc, msg); }
+    plan_backward(h);
+    umma_init(&h->umma, h->plan);
+    *out = h;
+    return WUN_OK;
+}
+
+int wun_create(const WunConfig* cfg, int64_t num_frames, WunHandle** out) {
+    if (!cfg || !out) return set_err(WUN_E_INVALID, "null argument");
+    int64_t t_in = 0, t_out = 0;
+    std::string msg;
+    int rc = solve_padding(*cfg, num_frames, &t_in, &t_out, &msg);
+    if (rc != WUN_OK) return set_err(rc, msg);
+    return wun_create_for_input(cfg, t_in, out);
+}
+
+int wun_destroy(WunHandle* h) {
+    if (h) { umma_destroy(&h->umma); delete h; }
+    return WUN_OK;
+}
+
+int64_t wun_input_frames(const WunHandle* h) { return h ? h->plan.T_in : -1; }
+int64_t wun_output_frames(const WunHandle* h) { return h ? h->plan.T_out : -1; }
+int64_t wun_param_count(const WunHandle* h) { return h ? (int64_t)h->plan.params.size() : -1; }
+int64_t wun_param_numel(const WunHandle* h) { return h ? h->plan.param_numel : -1; }
+
+int wun_param_table(const WunHandle* h, WunParamInfo* out, int64_t capacity) {
+    if (!h || !out) return set_err(WUN_E_INVALID, "null argument");
+    if (capacity < (int64_t)h->plan.params.size()) return set_err(WUN_E_INVALID, "param table capacity too small");
+    for (size_t i = 0; i < h->plan.params.size(); ++i) out[i] = h->plan.params[i];
+    return WUN_OK;
+}
+
+int64_t wun_workspace_bytes(const WunHandle* h, int64_t batch, int training) {
+    if (!h || batch < 1) return -1;
+    Layout l = make_layout(h->plan, batch, training != 0);
+    return (l.total + umma_workspace_floats(h->umma, h->plan, batch, training != 0)) * (int64_t)sizeof(float);
+}
+
+double wun_forward_flops(const WunHandle* h, int64_t batch) { return h ? h->plan.fwd_flops_per_item * batch : 0; }
+double wun_forward_backward_flops(const WunHandle* h, int64_t batch) {
+    return h ? (3.0 * h->plan.fwd_flops_per_item - h->plan.dgrad0_flops_per_item) * batch : 0;
+}
+
+int64_t wun_launches_forward(const WunHandle* hc) {
+    WunHandle* h = const_cast<WunHandle*>(hc);
+    if (begin_call(h, nullptr, nullptr, 1, false, nullptr, 0, nullptr, true) != WUN_OK) return -1;
+    run_forward(h, nullptr, nullptr, nullptr, 0);
+    return h->launches;
+}
+
+int64_t wun_launches_forward_backward(const WunHandle* hc) {
+    WunHandle* h = const_cast<WunHandle*>(hc);
+    if (begin_call(h, nullptr, nullptr, 1, true, nullptr, 0, nullptr, true) != WUN_OK) return -1;
+    run_forward(h, nullptr, nullptr, nullptr, 1);
+    run_backward(h, nullptr, nullptr, 1.f);
+    return h->launches;
+}
+
+int wun_forward(WunHandle* h, const float* params, const float* mix, int64_t batch, int training, float* outputs,
+                void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = begin_call(h, params, mix, batch, false, workspace, workspace_bytes, stream, false);
+    if (rc != WUN_OK) return rc;
+    if (!outputs) return set_err(WUN_E_INVALID, "outputs is null");
+    rc = run_forward(h, nullptr, outputs, nullptr, training);
+    if (rc != WUN_OK) return rc;
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_forward_backward(WunHandle* h, const float* params, const float* mix, const float* targets, int64_t batch,
+                         float* outputs, float* loss, float* grads, float grad_scale, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+    int rc = begin_call(h, params, mix, batch, true, workspace, workspace_bytes, stream, false);
+    if (rc != WUN_OK) return rc;
+    if (!targets || !loss || !grads) return set_err(WUN_E_INVALID, "targets/loss/grads must not be null");
+    WUN_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), h->stream));
+    WUN_CUDA_OK(cudaMemsetAsync(grads, 0, sizeof(float) * h->plan.param_numel, h->stream));
+    rc = run_forward(h, targets, outputs, loss, 1);
+    if (rc != WUN_OK) return rc;
+    rc = run_backward(h, targets, grads, grad_scale);
+    if (rc != WUN_OK) return rc;
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_adam_step(WunHandle* h, float* params, const float* grads, float* m, float* v, int64_t step, float lr,
+                  float beta1, float beta2, float eps, void* stream) {
+    if (!h || !params || !grads || !m || !v) return set_err(WUN_E_INVALID, "null argument");
+    if (step < 1) return set_err(WUN_E_INVALID, "step must be >= 1");
+    int rc = check_device();
+    if (rc != WUN_OK) return rc;
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    launch_adam(params, grads, m, v, h->plan.param_numel, (float)lr_t, beta1, beta2, eps, (cudaStream_t)stream);
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_gather_windows(WunHandle* h, const float* padded, int64_t n_padded, const int64_t* starts, int64_t n_windows,
+                       float* mix_batch, void* stream) {
+    if (!h || !padded || !starts || !mix_batch) return set_err(WUN_E_INVALID, "null argument");
+    int rc = check_device();
+    if (rc != WUN_OK) return rc;
+    launch_gather_windows(padded, n_padded, (const long long*)starts, (int)n_windows, (int)h->plan.T_in,
+                          h->plan.cfg.num_channels, mix_batch, (cudaStream_t)stream);
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_scatter_windows(WunHandle* h, const float* outputs, const int64_t* starts, int64_t n_windows, float* preds,
+                        int64_t n_frames, void* stream) {
+    if (!h || !outputs || !starts || !preds) return set_err(WUN_E_INVALID, "null argument");
+    int rc = check_device();
+    if (rc != WUN_OK) return rc;
+    launch_scatter_windows(outputs, (const long long*)starts, (int)n_windows, h->plan.cfg.num_sources,
+                           (int)h->plan.T_out, h->plan.cfg.num_channels, preds, n_frames, (cudaStream_t)stream);
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
+    if (!h) return -1;
+    std::string s = h->plan.describe();
+    s += umma_describe(h->umma, h->plan);
+    if (buf && capacity > 0) {
+        int64_t n = std::min<int64_t>(capacity - 1, (int64_t)s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+const char* wun_layer_kernel(const WunHandle* h, int layer, int pass) {
+    if (!h) return "";
+    return umma_layer_kernel(h->umma, layer, pass);
+}
+
+}  // extern "C"

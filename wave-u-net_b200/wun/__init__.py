@@ -1,0 +1,219 @@
+"""ctypes binding of libwun.so (include/wun.h) - the only way Python reaches the CUDA engine.
+
+No fallback of any kind lives here: if the shared library is missing the import fails loudly, and the
+compute entry points fail with WUN_E_NOGPU when there is no CUDA device.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libwun.so")
+
+WUN_OK, WUN_E_INVALID, WUN_E_NOTIMPL, WUN_E_SHAPE, WUN_E_CUDA, WUN_E_NOGPU = 0, -1, -2, -3, -4, -5
+
+# every symbol include/wun.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "wun_get_padding", "wun_create", "wun_create_for_input", "wun_destroy", "wun_input_frames",
+    "wun_output_frames", "wun_param_count", "wun_param_numel", "wun_param_table", "wun_workspace_bytes",
+    "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
+    "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step",
+    "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
+    "wun_layer_kernel",
+]
+
+
+class WunConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "num_layers", "num_initial_filters", "filter_size", "merge_filter_size", "input_filter_size",
+        "output_filter_size", "upsampling", "output_type", "context", "num_channels", "num_sources",
+        "output_activation")]
+
+
+class WunParamInfo(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 64), ("ndim", ctypes.c_int32), ("shape", ctypes.c_int32 * 3),
+                ("offset", ctypes.c_int64), ("numel", ctypes.c_int64)]
+
+
+class WunError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libwun error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found. Build it with wave-u-net_b200/build.sh (or __graft_entry__.build()). "
+            "There is no CPU or PyTorch fallback for the Wave-U-Net engine." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    P, I64, F, VP = ctypes.POINTER, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+    H = VP
+    lib.wun_get_padding.argtypes = [P(WunConfig), I64, P(I64), P(I64)]
+    lib.wun_create.argtypes = [P(WunConfig), I64, P(H)]
+    lib.wun_create_for_input.argtypes = [P(WunConfig), I64, P(H)]
+    lib.wun_destroy.argtypes = [H]
+    for n in ("wun_input_frames", "wun_output_frames", "wun_param_count", "wun_param_numel",
+              "wun_launches_forward", "wun_launches_forward_backward"):
+        getattr(lib, n).argtypes = [H]
+        getattr(lib, n).restype = I64
+    lib.wun_param_table.argtypes = [H, P(WunParamInfo), I64]
+    lib.wun_workspace_bytes.argtypes = [H, I64, ctypes.c_int]
+    lib.wun_workspace_bytes.restype = I64
+    for n in ("wun_forward_flops", "wun_forward_backward_flops"):
+        getattr(lib, n).argtypes = [H, I64]
+        getattr(lib, n).restype = ctypes.c_double
+    lib.wun_forward.argtypes = [H, VP, VP, I64, ctypes.c_int, VP, VP, I64, VP]
+    lib.wun_forward_backward.argtypes = [H, VP, VP, VP, I64, VP, VP, VP, F, VP, I64, VP]
+    lib.wun_adam_step.argtypes = [H, VP, VP, VP, VP, I64, F, F, F, F, VP]
+    lib.wun_gather_windows.argtypes = [H, VP, I64, VP, I64, VP, VP]
+    lib.wun_scatter_windows.argtypes = [H, VP, VP, I64, VP, I64, VP]
+    lib.wun_last_error.restype = ctypes.c_char_p
+    lib.wun_version.restype = ctypes.c_char_p
+    lib.wun_describe.argtypes = [H, ctypes.c_char_p, I64]
+    lib.wun_describe.restype = I64
+    lib.wun_layer_kernel.argtypes = [H, ctypes.c_int, ctypes.c_int]
+    lib.wun_layer_kernel.restype = ctypes.c_char_p
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != WUN_OK:
+        msg = lib.wun_last_error().decode("utf-8", "replace")
+        if rc == WUN_E_NOTIMPL:
+            raise NotImplementedError(msg)          # reference: UnetAudioSeparator.py:136,144
+        if rc == WUN_E_SHAPE:
+            raise AssertionError(msg)               # reference: asserts :55, :121, Utils.py:114-117
+        raise WunError(rc, msg)
+
+
+_UPSAMPLING = {"linear": 0, "learned": 1}
+_OUTPUT_TYPE = {"direct": 0, "difference": 1}
+_ACTIVATION = {"tanh": 0, "linear": 1}
+
+
+def config_from_model_config(mc):
+    """model_config dict (Config.py) -> WunConfig; the keys are those UnetAudioSeparator.__init__
+    reads (/root/reference/Models/UnetAudioSeparator.py:20-32)."""
+    c = WunConfig()
+    c.num_layers = int(mc["num_layers"])
+    c.num_initial_filters = int(mc["num_initial_filters"])
+    c.filter_size = int(mc["filter_size"])
+    c.merge_filter_size = int(mc["merge_filter_size"])
+    c.input_filter_size = int(mc["input_filter_size"])
+    c.output_filter_size = int(mc["output_filter_size"])
+    c.upsampling = _UPSAMPLING.get(mc["upsampling"], 0)     # reference: anything but 'learned' is bilinear (:110-117)
+    c.output_type = _OUTPUT_TYPE.get(mc["output_type"], -1)
+    c.context = 1 if mc["context"] else 0
+    c.num_channels = 1 if mc["mono_downmix"] else 2
+    c.num_sources = len(mc["source_names"])
+    c.output_activation = _ACTIVATION.get(mc["output_activation"], -1)
+    return c
+
+
+def get_padding(cfg, num_frames):
+    t_in, t_out = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.wun_get_padding(ctypes.byref(cfg), int(num_frames), ctypes.byref(t_in), ctypes.byref(t_out)))
+    return t_in.value, t_out.value
+
+
+class Engine(object):
+    """One plan (fixed window length) of the CUDA engine."""
+
+    def __init__(self, cfg, num_frames=None, input_frames=None):
+        self._h = ctypes.c_void_p()
+        self.cfg = cfg
+        if input_frames is not None:
+            check(lib.wun_create_for_input(ctypes.byref(cfg), int(input_frames), ctypes.byref(self._h)))
+        else:
+            check(lib.wun_create(ctypes.byref(cfg), int(num_frames), ctypes.byref(self._h)))
+        self.T_in = lib.wun_input_frames(self._h)
+        self.T_out = lib.wun_output_frames(self._h)
+        n = lib.wun_param_count(self._h)
+        arr = (WunParamInfo * n)()
+        check(lib.wun_param_table(self._h, arr, n))
+        self.param_table = [(a.name.decode(), tuple(a.shape[:a.ndim]), int(a.offset), int(a.numel)) for a in arr]
+        self.param_numel = lib.wun_param_numel(self._h)
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.wun_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- host-only queries -------------------------------------------------------------------
+    def workspace_bytes(self, batch, training):
+        return lib.wun_workspace_bytes(self._h, int(batch), 1 if training else 0)
+
+    def forward_flops(self, batch):
+        return lib.wun_forward_flops(self._h, int(batch))
+
+    def forward_backward_flops(self, batch):
+        return lib.wun_forward_backward_flops(self._h, int(batch))
+
+    def launches(self, training):
+        return (lib.wun_launches_forward_backward if training else lib.wun_launches_forward)(self._h)
+
+    def describe(self):
+        n = lib.wun_describe(self._h, None, 0)
+        buf = ctypes.create_string_buffer(int(n))
+        lib.wun_describe(self._h, buf, n)
+        return buf.value.decode()
+
+    def layer_kernel(self, layer, pass_):
+        return lib.wun_layer_kernel(self._h, int(layer), int(pass_)).decode()
+
+    # ---- device calls (torch tensors supply memory and the stream) --------------------------------
+    def _workspace(self, batch, training, device):
+        import torch
+        key = (int(batch), bool(training), str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.workspace_bytes(batch, training)
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+            self._ws = {key: ws}          # keep one workspace alive (the latest shape)
+        return ws
+
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def forward(self, params, mix, training, out=None):
+        import torch
+        B = mix.shape[0]
+        K, C = self.cfg.num_sources, self.cfg.num_channels
+        assert mix.is_cuda and mix.dtype == torch.float32 and mix.is_contiguous()
+        assert tuple(mix.shape[1:]) == (self.T_in, C), (tuple(mix.shape), self.T_in, C)
+        if out is None:
+            out = torch.empty((K, B, self.T_out, C), dtype=torch.float32, device=mix.device)
+        ws = self._workspace(B, False, mix.device)
+        check(lib.wun_forward(self._h, params.data_ptr(), mix.data_ptr(), B, 1 if training else 0, out.data_ptr(),
+                              ws.data_ptr(), ws.numel() * 4, self._stream()))
+        return out
+
+    def forward_backward(self, params, mix, targets, grads, loss, grad_scale=1.0, out=None):
+        B = mix.shape[0]
+        ws = self._workspace(B, True, mix.device)
+        check(lib.wun_forward_backward(self._h, params.data_ptr(), mix.data_ptr(), targets.data_ptr(), B,
+                                       out.data_ptr() if out is not None else None, loss.data_ptr(),
+                                       grads.data_ptr(), float(grad_scale), ws.data_ptr(), ws.numel() * 4,
+                                       self._stream()))
+        return loss
+
+    def adam_step(self, params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        check(lib.wun_adam_step(self._h, params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), int(step),
+                                float(lr), float(beta1), float(beta2), float(eps), self._stream()))
+
+    def gather_windows(self, padded, starts, mix_batch):
+        check(lib.wun_gather_windows(self._h, padded.data_ptr(), padded.shape[0], starts.data_ptr(),
+                                     starts.numel(), mix_batch.data_ptr(), self._stream()))
+
+    def scatter_windows(self, outputs, starts, preds):
+        check(lib.wun_scatter_windows(self._h, outputs.data_ptr(), starts.data_ptr(), starts.numel(),
+                                      preds.data_ptr(), preds.shape[1], self._stream()))
