@@ -5,6 +5,7 @@
 // (the reference has no backward source; the derivation is in DESIGN.md "Backward").
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -17,7 +18,7 @@
 #include "kernels.h"
 #include "launch.h"
 #include "plan.h"
-#include "umma.h"
+#include "kernels_umma.h"
 
 using namespace wun;
 
@@ -54,7 +55,10 @@ struct WunHandle {
     Plan plan;
     std::vector<OpBackward> bwd_down, bwd_up;
     OpBackward bwd_bottleneck;
-    UmmaState umma;                      // tensor-core path state (weight packs, eligibility)
+    bool umma_enabled = true;            // tcgen05 path on (WUN_DISABLE_UMMA=1 turns it off, for A/B tests)
+    size_t arena_bytes = 0;              // scratch for packed bf16 weights (max over launches)
+    std::vector<std::string> kernel_used;   // [layer*3 + pass] -> "simt" | "umma" (filled by dry runs)
+    int cur_layer = 0, cur_pass = 0;
     // per-call state
     bool dry = false;
     int64_t launches = 0;
@@ -192,15 +196,27 @@ static long long view_bstride(const WunHandle* h, const ViewSpec& v) {
     return rows * C;
 }
 
-static void launch_conv(WunHandle* h, const ConvLaunch& L) {
+// Every plane convolution goes through here: tcgen05 when the launch is eligible, CUDA cores otherwise.
+static int launch_conv(WunHandle* h, const ConvLaunch& L) {
+    UmmaChoice ch;
+    const bool use_umma = h->umma_enabled && umma_plan_from_conv(L, &ch);
+    const size_t slot = (size_t)h->cur_layer * 3 + h->cur_pass;
+    if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
+    if (use_umma) {
+        h->launches += 2;                       // weight pack + conv
+        if (h->dry) { h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); return WUN_OK; }
+        uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total);
+        cudaError_t e = umma_run_conv(L, ch, arena, h->stream);
+        if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(e));
+        return WUN_OK;
+    }
     ++h->launches;
     if (!h->dry) launch_plane_conv_simt(L, h->stream);
+    return WUN_OK;
 }
 
 static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
-    if (umma_try_forward(h->umma, h->plan, op, layer_index, h->params, h->mix, h->ws, h->lay.off.data(), h->batch,
-                         h->stream, h->dry, &h->launches))
-        return WUN_OK;
+    h->cur_layer = layer_index; h->cur_pass = 0;
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
     L.nplanes = (int)op.planes.size();
@@ -225,14 +241,14 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
     L.W = h->params + h->plan.params[op.w_param].offset;
     L.bias = h->params + h->plan.params[op.b_param].offset;
     L.epilogue = EPI_BIAS_LRELU; L.batch = h->batch; L.max_rows = max_rows;
-    launch_conv(h, L);
-    return WUN_OK;
+    return launch_conv(h, L);
 }
 
 // dgrad: one class per forward input plane that needs a gradient; the forward classes' gradient
 // tensors become the input planes.
-static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob) {
+static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int layer_index) {
     if (ob.dgrad.empty()) return WUN_OK;
+    h->cur_layer = layer_index; h->cur_pass = 1;
     const Plan& P = h->plan;
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
@@ -290,7 +306,10 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob) {
         // slope is per class (saved != null); classes without saved use EPI_PLAIN semantics via null check
         S.epilogue = EPI_SLOPE;
         S.batch = h->batch;
-        if (S.max_rows > 0) launch_conv(h, S);
+        if (S.max_rows > 0) {
+            int rc = launch_conv(h, S);
+            if (rc != WUN_OK) return rc;
+        }
     }
     return WUN_OK;
 }
@@ -390,7 +409,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     for (int i = L - 1; i >= 0; --i) {
         const ConvOp& op = P.up[i];
         if ((rc = conv_wgrad(h, op, grads, scale)) != WUN_OK) return rc;
-        if ((rc = conv_dgrad(h, op, h->bwd_up[i])) != WUN_OK) return rc;
+        if ((rc = conv_dgrad(h, op, h->bwd_up[i], L + 1 + i)) != WUN_OK) return rc;
         const UpsampleSpec& us = P.ups[i];
         UpsampleBwdLaunch U;
         memset(&U, 0, sizeof(U));
@@ -405,10 +424,10 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         if (!h->dry) launch_upsample_bwd(U, h->stream);
     }
     if ((rc = conv_wgrad(h, P.bottleneck, grads, scale)) != WUN_OK) return rc;
-    if ((rc = conv_dgrad(h, P.bottleneck, h->bwd_bottleneck)) != WUN_OK) return rc;
+    if ((rc = conv_dgrad(h, P.bottleneck, h->bwd_bottleneck, L)) != WUN_OK) return rc;
     for (int i = L - 1; i >= 0; --i) {
         if ((rc = conv_wgrad(h, P.down[i], grads, scale)) != WUN_OK) return rc;
-        if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i])) != WUN_OK) return rc;
+        if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i], i)) != WUN_OK) return rc;
     }
     return WUN_OK;
 }
@@ -432,10 +451,11 @@ static int begin_call(WunHandle* h, const float* params, const float* mix, int64
     h->launches = 0;
     h->batch = (int)batch;
     if (dry) return WUN_OK;
+    { int rc0 = check_device(); if (rc0 != WUN_OK) return rc0; }
     if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
-    if (ws_bytes < h->lay.total * (int64_t)sizeof(float)) return set_err(WUN_E_INVALID, "workspace too small");
-    int rc = check_device();
-    if (rc != WUN_OK) return rc;
+    if (ws_bytes < h->lay.total * (int64_t)sizeof(float) + (int64_t)h->arena_bytes)
+        return set_err(WUN_E_INVALID, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return set_err(WUN_E_INVALID, "workspace must be 256-byte aligned");
     h->params = params; h->mix = mix; h->ws = (float*)ws; h->stream = (cudaStream_t)stream;
     return WUN_OK;
 }
@@ -463,7 +483,11 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     int rc = build_plan(*cfg, input_frames, &h->plan, &msg);
     if (rc != WUN_OK) { delete h; return set_err(rc, msg); }
     plan_backward(h);
-    umma_init(&h->umma, h->plan);
+    const char* dis = getenv("WUN_DISABLE_UMMA");
+    h->umma_enabled = !(dis && dis[0] == '1');
+    h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
+    // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
+    wun_launches_forward_backward(h);
     *out = h;
     return WUN_OK;
 }
@@ -478,7 +502,7 @@ int wun_create(const WunConfig* cfg, int64_t num_frames, WunHandle** out) {
 }
 
 int wun_destroy(WunHandle* h) {
-    if (h) { umma_destroy(&h->umma); delete h; }
+    if (h) delete h;
     return WUN_OK;
 }
 
@@ -497,7 +521,7 @@ int wun_param_table(const WunHandle* h, WunParamInfo* out, int64_t capacity) {
 int64_t wun_workspace_bytes(const WunHandle* h, int64_t batch, int training) {
     if (!h || batch < 1) return -1;
     Layout l = make_layout(h->plan, batch, training != 0);
-    return (l.total + umma_workspace_floats(h->umma, h->plan, batch, training != 0)) * (int64_t)sizeof(float);
+    return l.total * (int64_t)sizeof(float) + (int64_t)h->arena_bytes + 256;
 }
 
 double wun_forward_flops(const WunHandle* h, int64_t batch) { return h ? h->plan.fwd_flops_per_item * batch : 0; }
@@ -584,7 +608,9 @@ int wun_scatter_windows(WunHandle* h, const float* outputs, const int64_t* start
 int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
     if (!h) return -1;
     std::string s = h->plan.describe();
-    s += umma_describe(h->umma, h->plan);
+    s += "  kernels (fwd/dgrad): ";
+    for (size_t i = 0; i + 2 < h->kernel_used.size(); i += 3) s += h->kernel_used[i] + "/" + h->kernel_used[i + 1] + " ";
+    s += "\n";
     if (buf && capacity > 0) {
         int64_t n = std::min<int64_t>(capacity - 1, (int64_t)s.size());
         memcpy(buf, s.data(), n);
@@ -595,7 +621,9 @@ int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
 
 const char* wun_layer_kernel(const WunHandle* h, int layer, int pass) {
     if (!h) return "";
-    return umma_layer_kernel(h->umma, layer, pass);
+    const size_t slot = (size_t)layer * 3 + pass;
+    if (layer < 0 || pass < 0 || pass > 2 || slot >= h->kernel_used.size()) return "";
+    return h->kernel_used[slot].c_str();
 }
 
 }  // extern "C"

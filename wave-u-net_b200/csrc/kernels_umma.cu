@@ -1,0 +1,523 @@
+// kernels_umma.cu - tcgen05 (5th-gen tensor core) plane convolution for sm_100a.
+//
+// One kernel serves the forward conv blocks and their dgrads (both are "plane convolutions", launch.h):
+//     out_cls[b, m, n] = epi( sum_terms  plane[b, m + d, :] . W_term[:, n] )
+// mapped onto tcgen05.mma as a shifted-tap implicit GEMM:
+//   * A operand: the CTA stages a SLAB of input rows once per 16-channel chunk in shared memory, as
+//     bf16 "channel-atom planes"  [hi|lo][atom(8 ch)][row][16 B]  (K-major, SWIZZLE_NONE canonical layout:
+//     8 rows x 16 B core matrices, SBO = 128 B between 8-row groups, LBO = atom-plane stride between the two
+//     K atoms of one MMA).  A conv tap is then just a descriptor START-ADDRESS shift of d*16 B - the slab is
+//     read by up to 8 taps x MT row tiles without ever being re-loaded or re-converted.  Decimation
+//     ([:, ::2, :], UnetAudioSeparator.py:100), the skip crop (:122), zero padding and the linear / learned
+//     upsampling (:109-118, InterpolationLayer.py:19-39) all happen in the fp32 -> bf16 converter warps that
+//     fill the slab, so none of those tensors ever exists in HBM.
+//   * fp32-level accuracy: every fp32 operand x is split x = hi + lo (two bf16), and each K step issues
+//     three MMAs  hi*hi + lo*hi + hi*lo  into the same fp32 TMEM accumulator (error ~2^-17 per operand;
+//     measured 5e-6 end to end vs the 1e-4 parity bar; single-pass bf16/tf32 fail it - BASELINE.md section 6).
+//   * B operand (weights): pre-packed once per optimizer step into the exact K-step streaming order, hi/lo
+//     bf16, core-matrix layout; streamed with cp.async.bulk (UBLKCP) through an mbarrier ring.
+//   * accumulators: MT row tiles x NPAD fp32 columns in TMEM; epilogue tcgen05.ld -> bias/LeakyReLU (fwd)
+//     or LeakyReLU-slope / accumulate (dgrad) -> global.
+// Warp roles: warps 0-3 converter + epilogue (TMEM lane quarter = warp id), warp 4 TMEM alloc + MMA issue
+// (one elected lane), warp 5 weight loader (one elected lane).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "kernels_umma.h"
+
+namespace wun {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must become a trap (reported error), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major / MN-major SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, M = 128, cta_group::1
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo_elem, hi_elem);   // .x = first (low address)
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab fill helpers
+// ------------------------------------------------------------------------------------------------
+// 16 channels [c0, c0+16) of plane row r of batch b, fp32, zero where invalid.
+__device__ __forceinline__ void load_row16(const PlaneView& P, int b, int r, int c0, float* x) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = 0.f;
+    if (r < P.r_lo || r >= P.r_hi) return;
+    const float* p = P.base + (long long)b * P.bstride + (long long)r * P.rstride + c0;
+    const int nv = min(16, P.C - c0);      // multiple of 8 (eligibility)
+    if (nv >= 16) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float4 t = __ldg(q + i); x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w; }
+    } else if (nv >= 8) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { float4 t = __ldg(q + i); x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w; }
+    }
+    if (P.kind == PLANE_MID) {
+        float nx[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nx[i] = 0.f;
+        const bool has_next = (P.mid_mode == MID_VALID) || (r + 1 < P.xrows);
+        if (has_next) {
+            const float4* q = reinterpret_cast<const float4*>(p + P.rstride);
+            const int n4 = (nv >= 16) ? 4 : 2;
+            for (int i = 0; i < n4; ++i) { float4 t = __ldg(q + i); nx[4 * i] = t.x; nx[4 * i + 1] = t.y; nx[4 * i + 2] = t.z; nx[4 * i + 3] = t.w; }
+        } else if (P.mid_mode == MID_CLAMP) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) nx[i] = x[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < nv) {
+                if (P.blend) { const float w = __ldg(P.blend + c0 + i); x[i] = w * x[i] + (1.f - w) * nx[i]; }
+                else x[i] = x[i] + (nx[i] - x[i]) * 0.5f;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlabStages = 3;
+constexpr int kBStages = 6;
+constexpr int kWorkerThreads = 128;
+
+__global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_constant__ UmmaLaunch L) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cls = blockIdx.z % L.ncls, b = blockIdx.z / L.ncls;
+    const UmmaClass& K = L.cls[cls];
+    const int split = blockIdx.y;
+    const int rows_tile = L.MT * 128;
+    const int m_base = K.out.m_lo + blockIdx.x * rows_tile;
+    if (m_base >= K.out.m_hi) return;
+
+    const int NPAD = L.NPAD;
+    const uint32_t slab_bytes = 64u * L.rows_alloc;          // [hi|lo][2 atoms][rows_alloc][16 B]
+    const uint32_t bblk_bytes = 64u * NPAD;                  // [hi|lo][2 atoms][NPAD/8][8][16 B]
+    uint8_t* slab0 = smem;
+    uint8_t* bring0 = smem + kSlabStages * slab_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bring0 + kBStages * bblk_bytes);
+    // bars: slab_full[3], slab_empty[3], b_full[6], b_empty[6], acc_full
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int SLAB_FULL = 0, SLAB_EMPTY = kSlabStages, B_FULL = 2 * kSlabStages, B_EMPTY = 2 * kSlabStages + kBStages,
+              ACC_FULL = 2 * kSlabStages + 2 * kBStages;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
+
+    if (tid == 0) {
+        for (int i = 0; i < kSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
+        for (int i = 0; i < kBStages; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // job = (group, 16-channel chunk); K-step = (job, term)
+    if (warp < 4) {
+        // ===================== converter: fill slabs =====================
+        int ji = 0;
+        for (int g = 0; g < K.ngroups; ++g) {
+            const UmmaGroup& G = K.groups[g];
+            const PlaneView& P = L.planes[G.plane];
+            const int nchunk = (P.C + 15) >> 4;
+            for (int c = 0; c < nchunk; ++c, ++ji) {
+                const int st = ji % kSlabStages;
+                mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
+                uint8_t* S = slab0 + st * slab_bytes;
+                const uint32_t atom_stride = 16u * L.rows_alloc;
+                for (int rr = tid; rr < L.rows_alloc; rr += kWorkerThreads) {
+                    float x[16];
+                    load_row16(P, b, m_base + G.dmin + rr, c * 16, x);
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+                        const float r0 = x[2 * i] - __bfloat162float(h0), r1 = x[2 * i + 1] - __bfloat162float(h1);
+                        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[i] = pack_bf16x2(r0, r1);
+                    }
+                    uint4* d = reinterpret_cast<uint4*>(S + 16u * rr);
+                    *d = make_uint4(hi[0], hi[1], hi[2], hi[3]);                                                  // hi, atom 0
+                    *reinterpret_cast<uint4*>(S + atom_stride + 16u * rr) = make_uint4(hi[4], hi[5], hi[6], hi[7]);   // hi, atom 1
+                    *reinterpret_cast<uint4*>(S + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(S + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                mbar_arrive(BAR(SLAB_FULL + st));
+            }
+        }
+        // ===================== epilogue =====================
+        mbar_wait(BAR(ACC_FULL), 0);
+        tc_fence_after();
+        const int n0 = split * NPAD;
+        for (int mt = 0; mt < L.MT; ++mt) {
+            const int m = m_base + mt * 128 + warp * 32 + lane;
+            const bool row_ok = m < K.out.m_hi;
+            const long long roff = (long long)b * K.out.bstride + (long long)m * K.out.rstride;
+            const bool accum = row_ok && (m >= K.out.acc_lo && m < K.out.acc_hi);
+            for (int cb = 0; cb < NPAD; cb += 16) {
+                if (n0 + cb >= L.N) break;           // warp-uniform
+                __syncwarp();                        // tcgen05.ld is .sync.aligned: reconverge after masked stores
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + cb), v);
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + cb + j;
+                    if (n < L.N) {
+                        float y = v[j];
+                        if (L.epilogue == EPI_BIAS_LRELU) {
+                            if (L.bias) y += __ldg(L.bias + n);
+                            y = fmaxf(0.2f * y, y);
+                        } else if (L.epilogue == EPI_SLOPE && K.out.saved) {
+                            const float s = __ldg(K.out.saved + roff + n);
+                            y *= (s > 0.f) ? 1.f : 0.2f;
+                        }
+                        v[j] = y;
+                    }
+                }
+                float* dst = K.out.base + roff + n0 + cb;
+                if (n0 + cb + 16 <= L.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (accum) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                        d4[q] = o;
+                    }
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + cb + j < L.N) dst[j] = accum ? (dst[j] + v[j]) : v[j];
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t atom_stride = 16u * L.rows_alloc;
+            const uint32_t b_lbo = 16u * NPAD;       // between the two K atoms of a weight block
+            int ji = 0, bi = 0;
+            uint32_t first = 0;                      // accumulate flag: 0 for the very first K step
+            for (int g = 0; g < K.ngroups; ++g) {
+                const UmmaGroup& G = K.groups[g];
+                const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                for (int c = 0; c < nchunk; ++c, ++ji) {
+                    const int st = ji % kSlabStages;
+                    mbar_wait(BAR(SLAB_FULL + st), (ji / kSlabStages) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(slab0 + st * slab_bytes);
+                    for (int t = G.term_begin; t < G.term_end; ++t, ++bi) {
+                        const int bs = bi % kBStages;
+                        mbar_wait(BAR(B_FULL + bs), (bi / kBStages) & 1);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(bring0 + bs * bblk_bytes);
+                        const uint64_t b_hi = umma_desc(sb, b_lbo, 128);
+                        const uint64_t b_lo = umma_desc(sb + 32u * NPAD, b_lbo, 128);
+                        const uint32_t roff = 16u * (uint32_t)(L.d[t] - G.dmin);
+                        for (int mt = 0; mt < L.MT; ++mt) {
+                            const uint32_t a0 = sa + roff + 16u * 128u * mt;
+                            const uint64_t a_hi = umma_desc(a0, atom_stride, 128);
+                            const uint64_t a_lo = umma_desc(a0 + 2 * atom_stride, atom_stride, 128);
+                            const uint32_t td = tmem_base + (uint32_t)(mt * NPAD);
+                            umma_bf16(td, a_lo, b_hi, idesc, first);
+                            umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                            umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                        }
+                        first = 1u;
+                        umma_commit(BAR(B_EMPTY + bs));       // weight stage free once these MMAs retire
+                    }
+                    umma_commit(BAR(SLAB_EMPTY + st));        // slab stage free
+                }
+            }
+            umma_commit(BAR(ACC_FULL));
+        }
+        __syncwarp();
+    } else {
+        // ===================== weight loader =====================
+        if (lane == 0) {
+            const uint8_t* src = K.wpack[split];
+            int bi = 0;
+            for (int g = 0; g < K.ngroups; ++g) {
+                const UmmaGroup& G = K.groups[g];
+                const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                const int nblk = nchunk * (G.term_end - G.term_begin);
+                for (int i = 0; i < nblk; ++i, ++bi) {
+                    const int bs = bi % kBStages;
+                    mbar_wait(BAR(B_EMPTY + bs), ((bi / kBStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes);
+                    bulk_g2s(smem_u32(bring0 + bs * bblk_bytes), src + (size_t)bi * bblk_bytes, bblk_bytes, BAR(B_FULL + bs));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L.tmem_cols);
+    }
+}
+
+size_t umma_smem_bytes(const UmmaLaunch& L) {
+    return (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)kBStages * 64u * L.NPAD + (2 * kSlabStages + 2 * kBStages + 1) * 8 + 16;
+}
+
+cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = umma_smem_bytes(L);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(plane_conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int max_tiles = 0;
+    for (int q = 0; q < L.ncls; ++q) {
+        const int rows = L.cls[q].out.m_hi - L.cls[q].out.m_lo;
+        max_tiles = max(max_tiles, (rows + L.MT * 128 - 1) / (L.MT * 128));
+    }
+    if (max_tiles <= 0) return cudaSuccess;
+    dim3 grid(max_tiles, L.nsplit, L.batch * L.ncls);
+    plane_conv_umma_kernel<<<grid, 192, smem, stream>>>(L);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight pre-pack: fp32 W -> hi/lo bf16 blocks in K-step streaming order.  blockIdx.y = job (class, split);
+// one thread per (block, n, k) element.  Block bi = ((group, chunk), term) in the kernel's loop order; element
+// (a, n, kk) of the hi half sits at byte a*16*NPAD + (n/8)*128 + (n%8)*16 + kk*2, the lo half 32*NPAD bytes later.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) umma_pack_kernel(const __grid_constant__ UmmaPackLaunch PL) {
+    const UmmaPackJob& J = PL.jobs[blockIdx.y];
+    const long long total = (long long)J.nblocks * PL.NPAD * 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk16 = (int)(i % 16);
+        const int n = (int)((i / 16) % PL.NPAD);
+        const int bi = (int)(i / (16LL * PL.NPAD));
+        int g = 0, base = 0;
+        while (g < J.ngroups - 1 && bi >= base + J.g_nchunk[g] * J.g_nterm[g]) { base += J.g_nchunk[g] * J.g_nterm[g]; ++g; }
+        const int rel = bi - base;
+        const int chunk = rel / J.g_nterm[g], term = J.g_term_begin[g] + rel % J.g_nterm[g];
+        const int k = chunk * 16 + kk16;              // channel within the plane
+        const int nn = J.n0 + n;
+        float w = 0.f;
+        if (k < J.g_C[g] && nn < PL.N)
+            w = __ldg(PL.W + (long long)PL.woff[term] + (long long)k * PL.w_sk + (long long)nn * PL.w_sn);
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        const int a = kk16 >> 3, kk = kk16 & 7;
+        uint8_t* blk = J.out + (size_t)bi * 64u * PL.NPAD;
+        const size_t off = (size_t)a * 16u * PL.NPAD + (size_t)(n >> 3) * 128u + (size_t)(n & 7) * 16u + (size_t)kk * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(blk + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(blk + 32u * PL.NPAD + off) = l;
+    }
+}
+
+cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream) {
+    int maxblk = 0;
+    for (int j = 0; j < PL.njobs; ++j) maxblk = max(maxblk, PL.jobs[j].nblocks);
+    const long long total = (long long)maxblk * PL.NPAD * 16;
+    if (total <= 0 || PL.njobs <= 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    dim3 grid((unsigned)blocks, PL.njobs);
+    umma_pack_kernel<<<grid, 256, 0, stream>>>(PL);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: turn a generic plane-convolution launch (launch.h ConvLaunch) into a tcgen05 launch
+// ------------------------------------------------------------------------------------------------
+bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
+    memset(ch, 0, sizeof(*ch));
+    if (L.N < 16 || L.ncls < 1 || L.ncls > kMaxClasses) return false;
+    for (int p = 0; p < L.nplanes; ++p) {
+        const PlaneView& P = L.planes[p];
+        if (P.C % 8 != 0 || P.C < 8) return false;
+        if (P.rstride % 4 != 0 || P.bstride % 4 != 0 || (reinterpret_cast<uintptr_t>(P.base) & 15) != 0) return false;
+    }
+    const int npad_total = (L.N + 15) / 16 * 16;
+    if (npad_total > 512) return false;
+    ch->nsplit = (npad_total <= 256) ? 1 : 2;
+    ch->NPAD = (ch->nsplit == 1) ? npad_total : (((L.N + 1) / 2 + 15) / 16 * 16);
+    int maxspan = 0, max_rows = 0;
+    size_t bytes = 0;
+    for (int q = 0; q < L.ncls; ++q) {
+        const OutView& O = L.cls[q];
+        max_rows = max(max_rows, O.m_hi - O.m_lo);
+        int ngroups = 0, t = O.term_begin;
+        while (t < O.term_end) {
+            const int p = L.terms[t].plane;
+            int t1 = t, dmin = L.terms[t].d, dmax = dmin;
+            while (t1 < O.term_end && L.terms[t1].plane == p) { dmin = min(dmin, L.terms[t1].d); dmax = max(dmax, L.terms[t1].d); ++t1; }
+            if (dmax - dmin > 24) return false;
+            maxspan = max(maxspan, dmax - dmin);
+            bytes += (size_t)((L.planes[p].C + 15) / 16) * (t1 - t) * 64u * ch->NPAD * ch->nsplit;
+            ++ngroups; t = t1;
+        }
+        if (ngroups > kUmmaMaxGroups) return false;
+    }
+    if (max_rows <= 0) return false;
+    // two co-resident CTAs per SM beat one big one (measured): keep TMEM <= 256 columns and smem <= ~110 KB
+    int MT = 256 / ch->NPAD;
+    if (MT > 2) MT = 2;
+    if (MT < 1) MT = 1;
+    if (max_rows <= 128) MT = 1;
+    ch->MT = MT;
+    ch->rows_alloc = MT * 128 + (maxspan + 7) / 8 * 8;
+    int tm = 32;
+    while (tm < MT * ch->NPAD) tm *= 2;
+    ch->tmem_cols = tm;
+    ch->pack_bytes = (bytes + 255) / 256 * 256;
+    return true;
+}
+
+cudaError_t umma_run_conv(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena, cudaStream_t stream) {
+    UmmaLaunch U;
+    UmmaPackLaunch PL;
+    cudaError_t e = umma_build(L, ch, arena, &U, &PL);
+    if (e != cudaSuccess) return e;
+    e = launch_umma_pack(PL, stream);
+    if (e != cudaSuccess) return e;
+    return launch_plane_conv_umma(U, stream);
+}
+
+cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena, UmmaLaunch* Up, UmmaPackLaunch* PLp) {
+    UmmaLaunch& U = *Up;
+    UmmaPackLaunch& PL = *PLp;
+    memset(&U, 0, sizeof(U));
+    memset(&PL, 0, sizeof(PL));
+    for (int p = 0; p < L.nplanes; ++p) U.planes[p] = L.planes[p];
+    U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
+    U.tmem_cols = ch.tmem_cols; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
+    PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
+    int nterm_total = 0;
+    for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);
+    for (int t = 0; t < nterm_total; ++t) { U.d[t] = L.terms[t].d; PL.woff[t] = L.terms[t].woff; }
+    uint8_t* cur = arena;
+    for (int q = 0; q < L.ncls; ++q) {
+        UmmaClass& K = U.cls[q];
+        K.out = L.cls[q];
+        K.ngroups = 0;
+        int t = K.out.term_begin;
+        int nblocks = 0;
+        UmmaPackJob J0;
+        memset(&J0, 0, sizeof(J0));
+        while (t < K.out.term_end) {
+            const int p = L.terms[t].plane;
+            UmmaGroup G;
+            G.plane = p; G.term_begin = t; G.dmin = L.terms[t].d;
+            int t1 = t;
+            while (t1 < K.out.term_end && L.terms[t1].plane == p) { G.dmin = min(G.dmin, L.terms[t1].d); ++t1; }
+            G.term_end = t1;
+            const int g = K.ngroups++;
+            K.groups[g] = G;
+            J0.g_nchunk[g] = (L.planes[p].C + 15) / 16; J0.g_nterm[g] = t1 - t; J0.g_term_begin[g] = t; J0.g_C[g] = L.planes[p].C;
+            nblocks += J0.g_nchunk[g] * J0.g_nterm[g];
+            t = t1;
+        }
+        J0.ngroups = K.ngroups; J0.nblocks = nblocks;
+        for (int sp = 0; sp < ch.nsplit; ++sp) {
+            UmmaPackJob J = J0;
+            J.n0 = sp * ch.NPAD; J.out = cur;
+            K.wpack[sp] = cur;
+            cur += (size_t)nblocks * 64u * ch.NPAD;
+            if (PL.njobs >= kUmmaMaxPackJobs) return cudaErrorInvalidValue;
+            PL.jobs[PL.njobs++] = J;
+        }
+    }
+    return cudaSuccess;
+}
+
+}  // namespace wun

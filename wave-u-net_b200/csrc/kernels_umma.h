@@ -1,0 +1,76 @@
+// kernels_umma.h - parameter blocks and launchers of the tcgen05 plane-convolution kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "launch.h"
+
+namespace wun {
+
+constexpr int kUmmaMaxGroups = 4;
+constexpr int kUmmaMaxSplit = 2;
+
+struct UmmaGroup {          // all terms of one class that read the same plane (consecutive row shifts)
+    int plane;
+    int term_begin, term_end;   // indices into UmmaLaunch::d
+    int dmin;
+};
+
+struct UmmaClass {
+    OutView out;
+    UmmaGroup groups[kUmmaMaxGroups];
+    int ngroups;
+    const uint8_t* wpack[kUmmaMaxSplit];   // packed weights of this class, per output-channel split
+};
+
+struct UmmaLaunch {
+    PlaneView planes[kMaxPlanes];
+    UmmaClass cls[kMaxClasses];
+    int d[kMaxTerms];       // row shift of every term (grouped per class/plane)
+    int ncls;
+    int N;                  // real output channels
+    int NPAD;               // channels handled per split, multiple of 16, <= 256
+    int nsplit;             // 1 or 2 (N > 256)
+    int MT;                 // 128-row tiles per CTA
+    int rows_alloc;         // slab rows per stage  (>= MT*128 + max row-shift span)
+    int tmem_cols;          // power of two >= MT*NPAD
+    const float* bias;
+    int epilogue;
+    int batch;
+};
+
+constexpr int kUmmaMaxPackJobs = kMaxClasses * kUmmaMaxSplit;
+
+struct UmmaPackJob {        // one (class, split) weight pack
+    uint8_t* out;
+    int ngroups;
+    int g_nchunk[kUmmaMaxGroups], g_nterm[kUmmaMaxGroups], g_term_begin[kUmmaMaxGroups], g_C[kUmmaMaxGroups];
+    int n0;
+    int nblocks;
+};
+
+struct UmmaPackLaunch {
+    const float* W;
+    int woff[kMaxTerms];
+    int w_sk, w_sn;
+    int N, NPAD;
+    int njobs;
+    UmmaPackJob jobs[kUmmaMaxPackJobs];
+};
+
+struct UmmaChoice {         // tiling decisions for one ConvLaunch
+    int NPAD, nsplit, MT, rows_alloc, tmem_cols;
+    size_t pack_bytes;      // arena bytes the packed weights of this launch need
+};
+
+size_t umma_smem_bytes(const UmmaLaunch& L);
+cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream);
+cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream);
+// Decide whether / how a generic plane-convolution launch runs on tcgen05; false = not eligible (SIMT).
+bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* choice);
+// Pack the weights into `arena` (choice.pack_bytes, 256-B aligned) and enqueue the tcgen05 kernel.
+cudaError_t umma_run_conv(const ConvLaunch& L, const UmmaChoice& choice, uint8_t* arena, cudaStream_t stream);
+// The two parameter blocks umma_run_conv launches (exposed for the probe / per-kernel timing).
+cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& choice, uint8_t* arena, UmmaLaunch* U, UmmaPackLaunch* PL);
+
+}  // namespace wun
