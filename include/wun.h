@@ -140,6 +140,10 @@ const char* wun_version(void);
 /* Human-readable plan (layer shapes, live windows, kernel choice per layer) into buf; returns the
  * number of bytes that the full text needs. */
 int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity);
+/* Where a saved activation / activation-gradient lives inside the caller's workspace (tests: per-layer parity).
+ * Names: dec<i>, odd<i> (live even / odd rows of down block i), z (bottleneck), up<i>, and g_<name> twins. */
+int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,
+                     int64_t* rows, int32_t* channels);
 /* Which kernel family a conv layer uses: "simt" or "umma".  layer: 0..L-1 down, L bottleneck,
  * L+1..2L up.  pass: 0 fwd, 1 dgrad, 2 wgrad. */
 const char* wun_layer_kernel(const WunHandle* h, int layer, int pass);

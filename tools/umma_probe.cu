@@ -140,10 +140,105 @@ static double run_case(const char* name, Problem p, bool check, int timing_iters
         const double flops = 2.0 * p.B * ((double)Td + n_odd) * p.fs * p.Cin * p.Cout;
         tf = flops / (ms * 1e-3) * 1e-12;
         printf("[%s] time %.1f us  %.1f useful TFLOP/s (x3 MMAs issued, padded K/N not counted)\n", name, ms * 1e3, tf);
+#ifdef WUN_UMMA_TIMING
+        unsigned long long tt[16];
+        CK(cudaMemcpyFromSymbol(tt, g_umma_timing, sizeof(tt)));
+        const double n = (double)tt[0];
+        printf("   per-CTA cycles: total %.0f prologue %.0f | mma loop %.0f (wait slab %.0f, wait B %.0f) | conv wait-empty %.0f fill %.0f | epi wait-acc %.0f epi %.0f | loader wait %.0f  (CTAs %.0f)\n",
+               tt[1] / n, tt[2] / n, tt[3] / n, tt[4] / n, tt[5] / n, tt[6] / n, tt[7] / n, tt[8] / n, tt[9] / n, tt[10] / n, n / (timing_iters + 4));
+        memset(tt, 0, sizeof(tt));
+        CK(cudaMemcpyToSymbol(g_umma_timing, tt, sizeof(tt)));
+#endif
     }
     cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(ddec); cudaFree(dodd);
     for (auto q : packs) cudaFree(q);
     return worst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad check / timing on the same "down block" geometry
+// ------------------------------------------------------------------------------------------------
+static void run_wgrad(const char* name, Problem p, bool check, int timing_iters) {
+    const int To = p.T - p.fs + 1, Td = (To + 1) / 2;
+    const int mo_lo = p.cs / 2, mo_hi = (p.cs + p.U) / 2, n_odd = mo_hi - mo_lo;
+    std::vector<float> x((size_t)p.B * p.T * p.Cin), gdec((size_t)p.B * Td * p.Cout), godd((size_t)p.B * (n_odd + 1) * p.Cout);
+    unsigned s = 777u;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+    for (auto& v : x) v = rnd();
+    for (auto& v : gdec) v = rnd() * 1e-3f;
+    for (auto& v : godd) v = rnd() * 1e-3f;
+    float *dx, *dgd, *dgo, *ddw;
+    const size_t wn = (size_t)p.fs * p.Cin * p.Cout;
+    CK(cudaMalloc(&dx, x.size() * 4)); CK(cudaMalloc(&dgd, gdec.size() * 4)); CK(cudaMalloc(&dgo, godd.size() * 4)); CK(cudaMalloc(&ddw, wn * 4));
+    CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgd, gdec.data(), gdec.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgo, godd.data(), godd.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<UmmaWgradLaunch> launches;
+    for (int q = 0; q < 2; ++q)
+        for (int par = 0; par < 2; ++par) {
+            UmmaWgradLaunch W;
+            memset(&W, 0, sizeof(W));
+            W.P.base = dx + par * p.Cin; W.P.bstride = (long long)p.T * p.Cin; W.P.rstride = 2 * p.Cin;
+            W.P.r_lo = 0; W.P.r_hi = (par == 0) ? (p.T + 1) / 2 : p.T / 2; W.P.C = p.Cin; W.P.kind = PLANE_DIRECT;
+            W.G.base = (q == 0) ? dgd : dgo - (long long)mo_lo * p.Cout;
+            W.G.bstride = (q == 0) ? (long long)Td * p.Cout : (long long)n_odd * p.Cout;
+            W.G.rstride = p.Cout; W.G.C = p.Cout; W.G.kind = PLANE_DIRECT;
+            W.m_lo = (q == 0) ? 0 : mo_lo; W.m_hi = (q == 0) ? Td : mo_hi;
+            W.G.r_lo = W.m_lo; W.G.r_hi = W.m_hi;
+            W.batch = p.B; W.dW = ddw; W.w_sp = p.Cout; W.w_sg = 1; W.scale = 1.f;
+            for (int j = 0; j < p.fs; ++j) {
+                int e = q + j;
+                if ((e & 1) != par) continue;
+                W.d[W.ntaps] = e >> 1; W.woff[W.ntaps] = j * p.Cin * p.Cout; ++W.ntaps;
+            }
+            if (W.m_hi <= W.m_lo || W.ntaps == 0) continue;
+            if (!umma_plan_wgrad(&W)) { printf("[%s] wgrad not eligible\n", name); exit(4); }
+            launches.push_back(W);
+        }
+    const UmmaWgradLaunch& W0 = launches[0];
+    printf("[%s] wgrad B=%d T=%d Cin=%d Cout=%d swap=%d NT=%d mtiles=%d ntiles=%d taps/cta=%d tapsets=%d rows/cta=%d tmem=%d\n", name, p.B, p.T,
+           p.Cin, p.Cout, W0.swap, W0.NT, W0.n_mtiles, W0.n_ntiles, W0.taps_per_cta, W0.n_tapsets, W0.rows_per_cta, W0.tmem_cols);
+    CK(cudaMemset(ddw, 0, wn * 4));
+    for (auto& W : launches) CK(launch_wgrad_umma(W, 0));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("[%s] WGRAD KERNEL ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); }
+    if (check) {
+        std::vector<float> dw(wn);
+        CK(cudaMemcpy(dw.data(), ddw, wn * 4, cudaMemcpyDeviceToHost));
+        std::vector<double> ref(wn, 0.0);
+        auto split = [](float v, float* h, float* l) { *h = bf16_round(v); *l = bf16_round(v - *h); };
+        for (int b = 0; b < p.B; ++b)
+            for (int a = 0; a < To; ++a) {
+                const bool even = (a & 1) == 0;
+                if (!even && !(a >= p.cs && a < p.cs + p.U)) continue;
+                const float* g = even ? &gdec[((size_t)b * Td + a / 2) * p.Cout] : &godd[((size_t)b * n_odd + ((a - 1) / 2 - mo_lo)) * p.Cout];
+                for (int j = 0; j < p.fs; ++j)
+                    for (int c = 0; c < p.Cin; ++c) {
+                        float xh, xl; split(x[((size_t)b * p.T + a + j) * p.Cin + c], &xh, &xl);
+                        for (int n = 0; n < p.Cout; ++n) {
+                            float gh, gl; split(g[n], &gh, &gl);
+                            ref[((size_t)j * p.Cin + c) * p.Cout + n] += (double)xh * gh + (double)xl * gh + (double)xh * gl;
+                        }
+                    }
+            }
+        double num = 0, den = 0, worst = 0;
+        for (size_t i = 0; i < wn; ++i) { num += (dw[i] - ref[i]) * (dw[i] - ref[i]); den += ref[i] * ref[i]; worst = fmax(worst, fabs(dw[i] - ref[i])); }
+        const double rel = sqrt(num / den);
+        printf("[%s] wgrad %s rel_l2=%.3e max_abs_err=%.3e (|ref| rms %.3e)\n", name, rel < 1e-4 ? "PASS" : "FAIL", rel, worst, sqrt(den / wn));
+    }
+    if (timing_iters > 0) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (auto& W : launches) CK(launch_wgrad_umma(W, 0));
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < timing_iters; ++i) for (auto& W : launches) CK(launch_wgrad_umma(W, 0));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= timing_iters;
+        const double flops = 2.0 * p.B * ((double)Td + n_odd) * p.fs * p.Cin * p.Cout;
+        printf("[%s] wgrad time %.1f us (4 launches)  %.1f useful TFLOP/s\n", name, ms * 1e3, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(dx); cudaFree(dgd); cudaFree(dgo); cudaFree(ddw);
 }
 
 int main(int argc, char** argv) {
@@ -162,7 +257,17 @@ int main(int argc, char** argv) {
     run_case("c72_n96_mt3",{ 2, 3000,  72, 96, 15, 3, 1,  500, 801}, true, 0);
     run_case("n72pad_mt2", { 2, 1000,  48, 72, 15, 2, 1,  100, 301}, true, 0);
     run_case("nsplit",     { 2, 300,   64, 288, 15, 1, 2,  50, 101}, true, 0);
+    run_wgrad("wg_tiny",   { 1, 300,   16, 16,  3, 1, 1,   40, 101}, true, 0);
+    run_wgrad("wg_taps15", { 2, 1500,  32, 48, 15, 1, 1,  200, 401}, true, 0);
+    run_wgrad("wg_c72n96", { 2, 3000,  72, 96, 15, 1, 1,  500, 801}, true, 0);
+    run_wgrad("wg_c24",    { 2, 1500,  24, 48, 15, 1, 1,  200, 401}, true, 0);
+    run_wgrad("wg_wide",   { 2, 300,  264, 288, 15, 1, 1,  50, 101}, true, 0);
     if (argc > 1 && !strcmp(argv[1], "notime")) return 0;
+    run_wgrad("wg_down1",  {16, 73715, 24, 48, 15, 1, 1, 32750, 8201}, false, 10);
+    run_wgrad("wg_down2",  {16, 36851, 48, 72, 15, 1, 1, 16366, 4105}, false, 10);
+    run_wgrad("wg_down3",  {16, 18419, 72, 96, 15, 1, 1, 8174, 2057}, false, 10);
+    run_wgrad("wg_down5",  {16, 4595, 120, 144, 15, 1, 1, 2030, 521}, false, 10);
+    run_wgrad("wg_down8",  {16, 563, 192, 216, 15, 1, 1, 242, 69}, false, 10);
     if (argc > 2 && !strcmp(argv[1], "only")) {      // single timed layer, for ncu
         int mt = atoi(argv[2]);
         run_case("down3_only", {16, 18419, 72, 96, 15, mt, 1, 8174, 2057}, false, 3);

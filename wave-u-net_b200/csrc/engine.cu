@@ -56,6 +56,7 @@ struct WunHandle {
     std::vector<OpBackward> bwd_down, bwd_up;
     OpBackward bwd_bottleneck;
     bool umma_enabled = true;            // tcgen05 path on (WUN_DISABLE_UMMA=1 turns it off, for A/B tests)
+    bool umma_pass[3] = {true, true, true};   // per pass (fwd, dgrad, wgrad): WUN_UMMA_FWD=0 / WUN_UMMA_DGRAD=0 / WUN_UMMA_WGRAD=0
     size_t arena_bytes = 0;              // scratch for packed bf16 weights (max over launches)
     std::vector<std::string> kernel_used;   // [layer*3 + pass] -> "simt" | "umma" (filled by dry runs)
     int cur_layer = 0, cur_pass = 0;
@@ -199,7 +200,7 @@ static long long view_bstride(const WunHandle* h, const ViewSpec& v) {
 // Every plane convolution goes through here: tcgen05 when the launch is eligible, CUDA cores otherwise.
 static int launch_conv(WunHandle* h, const ConvLaunch& L) {
     UmmaChoice ch;
-    const bool use_umma = h->umma_enabled && umma_plan_from_conv(L, &ch);
+    const bool use_umma = h->umma_enabled && h->umma_pass[h->cur_pass] && umma_plan_from_conv(L, &ch);
     const size_t slot = (size_t)h->cur_layer * 3 + h->cur_pass;
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
     if (use_umma) {
@@ -314,8 +315,9 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
     return WUN_OK;
 }
 
-static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale) {
+static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale, int layer_index) {
     const Plan& P = h->plan;
+    h->cur_layer = layer_index;
     for (const auto& c : op.classes) {
         if (c.m_hi <= c.m_lo) continue;
         PlaneView dpre = make_plane_on(h, c.out, P.grad_twin[c.out.tensor], view_bstride(h, c.out), c.m_lo, c.m_hi);
@@ -340,7 +342,22 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale)
             W.dW = grads + P.params[op.w_param].offset;
             W.scale = scale; W.batch = h->batch;
             ++h->launches;
-            if (!h->dry) launch_plane_wgrad_simt(W, h->stream);
+            // tensor-core wgrad when eligible
+            UmmaWgradLaunch U;
+            memset(&U, 0, sizeof(U));
+            U.P = W.plane; U.G = W.dpre; U.m_lo = W.m_lo; U.m_hi = W.m_hi; U.batch = W.batch; U.ntaps = W.nterms;
+            for (int t = 0; t < W.nterms; ++t) { U.d[t] = W.d[t]; U.woff[t] = W.woff[t]; }
+            U.dW = W.dW; U.w_sp = W.w_sk; U.w_sg = W.w_sn; U.scale = W.scale;
+            const bool use_umma = h->umma_enabled && h->umma_pass[2] && umma_plan_wgrad(&U);
+            const size_t slot = (size_t)h->cur_layer * 3 + 2;
+            if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
+            if (h->dry) continue;
+            if (use_umma) {
+                cudaError_t e = launch_wgrad_umma(U, h->stream);
+                if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 wgrad launch: ") + cudaGetErrorString(e));
+            } else {
+                launch_plane_wgrad_simt(W, h->stream);
+            }
         }
     }
     return WUN_OK;
@@ -408,7 +425,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     }
     for (int i = L - 1; i >= 0; --i) {
         const ConvOp& op = P.up[i];
-        if ((rc = conv_wgrad(h, op, grads, scale)) != WUN_OK) return rc;
+        if ((rc = conv_wgrad(h, op, grads, scale, L + 1 + i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, op, h->bwd_up[i], L + 1 + i)) != WUN_OK) return rc;
         const UpsampleSpec& us = P.ups[i];
         UpsampleBwdLaunch U;
@@ -423,10 +440,10 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         ++h->launches;
         if (!h->dry) launch_upsample_bwd(U, h->stream);
     }
-    if ((rc = conv_wgrad(h, P.bottleneck, grads, scale)) != WUN_OK) return rc;
+    if ((rc = conv_wgrad(h, P.bottleneck, grads, scale, L)) != WUN_OK) return rc;
     if ((rc = conv_dgrad(h, P.bottleneck, h->bwd_bottleneck, L)) != WUN_OK) return rc;
     for (int i = L - 1; i >= 0; --i) {
-        if ((rc = conv_wgrad(h, P.down[i], grads, scale)) != WUN_OK) return rc;
+        if ((rc = conv_wgrad(h, P.down[i], grads, scale, i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i], i)) != WUN_OK) return rc;
     }
     return WUN_OK;
@@ -485,6 +502,8 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     plan_backward(h);
     const char* dis = getenv("WUN_DISABLE_UMMA");
     h->umma_enabled = !(dis && dis[0] == '1');
+    { const char* names[3] = {"WUN_UMMA_FWD", "WUN_UMMA_DGRAD", "WUN_UMMA_WGRAD"};
+      for (int i = 0; i < 3; ++i) { const char* v = getenv(names[i]); h->umma_pass[i] = !(v && v[0] == '0'); } }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);
@@ -608,8 +627,9 @@ int wun_scatter_windows(WunHandle* h, const float* outputs, const int64_t* start
 int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
     if (!h) return -1;
     std::string s = h->plan.describe();
-    s += "  kernels (fwd/dgrad): ";
-    for (size_t i = 0; i + 2 < h->kernel_used.size(); i += 3) s += h->kernel_used[i] + "/" + h->kernel_used[i + 1] + " ";
+    s += "  kernels (fwd/dgrad/wgrad): ";
+    for (size_t i = 0; i + 2 < h->kernel_used.size(); i += 3)
+        s += h->kernel_used[i] + "/" + h->kernel_used[i + 1] + "/" + h->kernel_used[i + 2] + " ";
     s += "\n";
     if (buf && capacity > 0) {
         int64_t n = std::min<int64_t>(capacity - 1, (int64_t)s.size());
@@ -617,6 +637,19 @@ int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
         buf[n] = 0;
     }
     return (int64_t)s.size() + 1;
+}
+
+int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,
+                     int64_t* rows, int32_t* channels) {
+    if (!h || !name || !offset_floats || !rows || !channels) return set_err(WUN_E_INVALID, "null argument");
+    Layout l = make_layout(h->plan, batch, training != 0);
+    for (size_t i = 0; i < h->plan.tensors.size(); ++i)
+        if (h->plan.tensors[i].name == name) {
+            if (l.off[i] < 0) return set_err(WUN_E_INVALID, "tensor exists only in training workspaces");
+            *offset_floats = l.off[i]; *rows = h->plan.tensors[i].rows; *channels = h->plan.tensors[i].C;
+            return WUN_OK;
+        }
+    return set_err(WUN_E_INVALID, std::string("no workspace tensor named ") + name);
 }
 
 const char* wun_layer_kernel(const WunHandle* h, int layer, int pass) {

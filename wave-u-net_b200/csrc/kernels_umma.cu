@@ -163,6 +163,17 @@ __device__ __forceinline__ void load_row16(const PlaneView& P, int b, int r, int
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+#ifdef WUN_UMMA_TIMING
+__device__ unsigned long long g_umma_timing[16];
+#define T_NOW() clock64()
+#define T_ADD(i, v) atomicAdd(&g_umma_timing[i], (unsigned long long)(v))
+#define T_WAIT(i, stmt) do { long long t__ = clock64(); stmt; T_ADD(i, clock64() - t__); } while (0)
+#else
+#define T_NOW() 0LL
+#define T_ADD(i, v) do { } while (0)
+#define T_WAIT(i, stmt) stmt
+#endif
+
 constexpr int kSlabStages = 3;
 constexpr int kBStages = 6;
 constexpr int kWorkerThreads = 128;
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
     const int rows_tile = L.MT * 128;
     const int m_base = K.out.m_lo + blockIdx.x * rows_tile;
     if (m_base >= K.out.m_hi) return;
+    const long long t_start = T_NOW();
 
     const int NPAD = L.NPAD;
     const uint32_t slab_bytes = 64u * L.rows_alloc;          // [hi|lo][2 atoms][rows_alloc][16 B]
@@ -201,6 +213,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (tid == 0) { T_ADD(0, 1); T_ADD(2, T_NOW() - t_start); }
 
     // job = (group, 16-channel chunk); K-step = (job, term)
     if (warp < 4) {
@@ -212,7 +225,9 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
             const int nchunk = (P.C + 15) >> 4;
             for (int c = 0; c < nchunk; ++c, ++ji) {
                 const int st = ji % kSlabStages;
-                mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
+                if (tid == 0) { T_WAIT(6, mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1)); }
+                else mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
+                const long long t_fill = T_NOW();
                 uint8_t* S = slab0 + st * slab_bytes;
                 const uint32_t atom_stride = 16u * L.rows_alloc;
                 for (int rr = tid; rr < L.rows_alloc; rr += kWorkerThreads) {
@@ -234,11 +249,14 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                 }
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 mbar_arrive(BAR(SLAB_FULL + st));
+                if (tid == 0) T_ADD(7, T_NOW() - t_fill);
             }
         }
         // ===================== epilogue =====================
-        mbar_wait(BAR(ACC_FULL), 0);
+        if (tid == 0) { T_WAIT(8, mbar_wait(BAR(ACC_FULL), 0)); }
+        else mbar_wait(BAR(ACC_FULL), 0);
         tc_fence_after();
+        const long long t_epi = T_NOW();
         const int n0 = split * NPAD;
         for (int mt = 0; mt < L.MT; ++mt) {
             const int m = m_base + mt * 128 + warp * 32 + lane;
@@ -282,6 +300,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
             }
         }
         tc_fence_before();
+        if (tid == 0) T_ADD(9, T_NOW() - t_epi);
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -289,18 +308,19 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
             const uint32_t atom_stride = 16u * L.rows_alloc;
             const uint32_t b_lbo = 16u * NPAD;       // between the two K atoms of a weight block
             int ji = 0, bi = 0;
+            const long long t_mma = T_NOW();
             uint32_t first = 0;                      // accumulate flag: 0 for the very first K step
             for (int g = 0; g < K.ngroups; ++g) {
                 const UmmaGroup& G = K.groups[g];
                 const int nchunk = (L.planes[G.plane].C + 15) >> 4;
                 for (int c = 0; c < nchunk; ++c, ++ji) {
                     const int st = ji % kSlabStages;
-                    mbar_wait(BAR(SLAB_FULL + st), (ji / kSlabStages) & 1);
+                    T_WAIT(4, mbar_wait(BAR(SLAB_FULL + st), (ji / kSlabStages) & 1));
                     tc_fence_after();
                     const uint32_t sa = smem_u32(slab0 + st * slab_bytes);
                     for (int t = G.term_begin; t < G.term_end; ++t, ++bi) {
                         const int bs = bi % kBStages;
-                        mbar_wait(BAR(B_FULL + bs), (bi / kBStages) & 1);
+                        T_WAIT(5, mbar_wait(BAR(B_FULL + bs), (bi / kBStages) & 1));
                         tc_fence_after();
                         const uint32_t sb = smem_u32(bring0 + bs * bblk_bytes);
                         const uint64_t b_hi = umma_desc(sb, b_lbo, 128);
@@ -322,6 +342,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                 }
             }
             umma_commit(BAR(ACC_FULL));
+            T_ADD(3, T_NOW() - t_mma);
         }
         __syncwarp();
     } else {
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                 const int nblk = nchunk * (G.term_end - G.term_begin);
                 for (int i = 0; i < nblk; ++i, ++bi) {
                     const int bs = bi % kBStages;
-                    mbar_wait(BAR(B_EMPTY + bs), ((bi / kBStages) & 1) ^ 1);
+                    T_WAIT(10, mbar_wait(BAR(B_EMPTY + bs), ((bi / kBStages) & 1) ^ 1));
                     mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes);
                     bulk_g2s(smem_u32(bring0 + bs * bblk_bytes), src + (size_t)bi * bblk_bytes, bblk_bytes, BAR(B_FULL + bs));
                 }
@@ -348,6 +369,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, L.tmem_cols);
     }
+    if (tid == 0) T_ADD(1, T_NOW() - t_start);
 }
 
 size_t umma_smem_bytes(const UmmaLaunch& L) {
@@ -370,6 +392,218 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     if (max_tiles <= 0) return cudaSuccess;
     dim3 grid(max_tiles, L.nsplit, L.batch * L.ncls);
     plane_conv_umma_kernel<<<grid, 192, smem, stream>>>(L);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad kernel (MN-major operands: K = rows).  Slab layout per side: [hi|lo][atom (8 ch)][row][16 B]; for an
+// MN-major SWIZZLE_NONE operand the 8x8 core matrix is 8 rows (K) x 16 B, K groups LBO = 128 B apart, channel
+// atoms SBO = atom-plane stride apart.  A tap is again a start-address shift (d rows * 16 B) of the P side.
+// grid = (batch * chunks_per_batch, n_mtiles * n_ntiles, n_tapsets); 192 threads, roles as in the conv kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgRK = 64;          // rows per pipeline stage
+constexpr int kWgSpan = 16;        // extra P rows per stage (max tap shift span)
+constexpr int kWgStages = 2;
+
+__global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constant__ UmmaWgradLaunch L) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / L.chunks_per_batch;
+    const int r0 = L.m_lo + (blockIdx.x % L.chunks_per_batch) * L.rows_per_cta;
+    const int r1 = min(r0 + L.rows_per_cta, L.m_hi);
+    if (r0 >= r1) return;
+    const int mtile = blockIdx.y / L.n_ntiles, ntile = blockIdx.y % L.n_ntiles;
+    const int tap0 = blockIdx.z * L.taps_per_cta;
+    const int ntap = min(L.taps_per_cta, L.ntaps - tap0);
+    const PlaneView& SA = L.swap ? L.G : L.P;       // M side (128-channel tile)
+    const PlaneView& SB = L.swap ? L.P : L.G;       // N side (NT-channel tile)
+    const int ca0 = mtile * 128, cb0 = ntile * L.NT;
+    const int rowsA = L.swap ? kWgRK : kWgRK + kWgSpan;
+    const int rowsB = L.swap ? kWgRK + kWgSpan : kWgRK;
+    const uint32_t planeA = 16u * rowsA, planeB = 16u * rowsB;           // atom-plane strides
+    const int atomsA = 16, atomsB = L.NT / 8;
+    const uint32_t bytesA = 2u * atomsA * planeA, bytesB = 2u * atomsB * planeB;
+    const uint32_t stage_bytes = bytesA + bytesB;
+    int dmin = L.d[tap0];
+    for (int t = 1; t < ntap; ++t) dmin = min(dmin, L.d[tap0 + t]);
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int FULL = 0, EMPTY = kWgStages, ACC = 2 * kWgStages;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC + 1);
+    if (tid == 0) {
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(BAR(FULL + i), kWorkerThreads); mbar_init(BAR(EMPTY + i), 1); }
+        mbar_init(BAR(ACC), 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const int nchunks = (r1 - r0 + kWgRK - 1) / kWgRK;
+
+    if (warp < 4) {
+        // ===================== converter =====================
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const int st = ci % kWgStages;
+            mbar_wait(BAR(EMPTY + st), ((ci / kWgStages) & 1) ^ 1);
+            uint8_t* S = smem + st * stage_bytes;
+            const int rc = r0 + ci * kWgRK;                      // first G row of this chunk
+            // items: (side, row, 16-channel group)
+            const int gA = 8, gB = (L.NT + 15) / 16;             // 16-channel groups per side (A tile = 128 ch)
+            const int itemsA = rowsA * gA, items = itemsA + rowsB * gB;
+            for (int it = tid; it < items; it += kWorkerThreads) {
+                const bool isA = it < itemsA;
+                const int k = isA ? it : it - itemsA;
+                const int ng = isA ? gA : gB;
+                const int rr = k / ng, g = k % ng;
+                const bool isP = isA != (L.swap != 0);
+                const PlaneView& V = isA ? SA : SB;
+                const int c0 = (isA ? ca0 : cb0) + g * 16;
+                float x[16];
+                int row = isP ? (rc + dmin + rr) : (rc + rr);
+                bool valid = c0 < V.C;
+                if (!isP && (row >= r1 || row < r0)) valid = false;      // G rows outside this CTA's range contribute 0
+                if (valid) load_row16(V, b, row, c0, x);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] = 0.f;
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+                    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[i] = pack_bf16x2(x[2 * i] - __bfloat162float(h0), x[2 * i + 1] - __bfloat162float(h1));
+                }
+                const uint32_t plane = isA ? planeA : planeB;
+                uint8_t* base = S + (isA ? 0u : bytesA) + (uint32_t)(2 * g) * plane + 16u * rr;
+                const uint32_t lo_off = (isA ? atomsA : atomsB) * plane;
+                if (isA || (2 * g) < atomsB) {
+                    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(base + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                if (isA || (2 * g + 1) < atomsB) {
+                    *reinterpret_cast<uint4*>(base + plane) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(base + plane + lo_off) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(BAR(FULL + st));
+        }
+        // ===================== epilogue: accumulators -> atomic adds into dW =====================
+        mbar_wait(BAR(ACC), 0);
+        tc_fence_after();
+        const int m = ca0 + warp * 32 + lane;                    // M-side channel of this thread
+        const bool m_ok = m < SA.C;
+        const int sM = L.swap ? L.w_sg : L.w_sp, sN = L.swap ? L.w_sp : L.w_sg;
+        for (int t = 0; t < ntap; ++t) {
+            float* dst_t = L.dW + (long long)L.woff[tap0 + t] + (long long)m * sM;
+            for (int cb = 0; cb < L.NT; cb += 16) {
+                if (cb0 + cb >= SB.C) break;
+                __syncwarp();
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * L.NT + cb), v);
+                if (!m_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = cb0 + cb + j;
+                    if (n < SB.C) atomicAdd(dst_t + (long long)n * sN, v[j] * L.scale);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        if (lane == 0) {
+            // both operands MN-major: idesc a_major (bit 15) = b_major (bit 16) = 1
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(L.NT >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t accum = 0;
+            for (int ci = 0; ci < nchunks; ++ci) {
+                const int st = ci % kWgStages;
+                mbar_wait(BAR(FULL + st), (ci / kWgStages) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
+                for (int ks = 0; ks < kWgRK / 16; ++ks) {
+                    for (int t = 0; t < ntap; ++t) {
+                        const uint32_t shift = 16u * (uint32_t)(L.d[tap0 + t] - dmin);
+                        const uint32_t a0 = sa + 256u * ks + (L.swap ? 0u : shift);
+                        const uint32_t b0 = sb + 256u * ks + (L.swap ? shift : 0u);
+                        const uint64_t a_hi = umma_desc(a0, 128, planeA), a_lo = umma_desc(a0 + atomsA * planeA, 128, planeA);
+                        const uint64_t b_hi = umma_desc(b0, 128, planeB), b_lo = umma_desc(b0 + atomsB * planeB, 128, planeB);
+                        const uint32_t td = tmem_base + (uint32_t)(t * L.NT);
+                        umma_bf16(td, a_lo, b_hi, idesc, accum);
+                        umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                    }
+                    accum = 1u;
+                }
+                umma_commit(BAR(EMPTY + st));
+            }
+            umma_commit(BAR(ACC));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L.tmem_cols);
+    }
+}
+
+static size_t wgrad_smem_bytes(const UmmaWgradLaunch& L) {
+    const int rowsA = L.swap ? kWgRK : kWgRK + kWgSpan, rowsB = L.swap ? kWgRK + kWgSpan : kWgRK;
+    const size_t stage = 2u * 16 * 16 * rowsA + 2u * (L.NT / 8) * 16 * rowsB;
+    return kWgStages * stage + (2 * kWgStages + 1) * 8 + 16;
+}
+
+bool umma_plan_wgrad(UmmaWgradLaunch* L) {
+    const int Cp = L->P.C, Cg = L->G.C;
+    if (Cp % 8 || Cg % 8 || Cp < 16 || Cg < 16 || L->ntaps < 1 || L->ntaps > 16) return false;
+    if (L->P.rstride % 4 || L->G.rstride % 4 || L->P.bstride % 4 || L->G.bstride % 4) return false;
+    if ((reinterpret_cast<uintptr_t>(L->P.base) & 15) || (reinterpret_cast<uintptr_t>(L->G.base) & 15)) return false;
+    int dmin = L->d[0], dmax = L->d[0];
+    for (int t = 1; t < L->ntaps; ++t) { dmin = min(dmin, L->d[t]); dmax = max(dmax, L->d[t]); }
+    if (dmax - dmin > kWgSpan) return false;
+    const int rows = L->m_hi - L->m_lo;
+    if (rows <= 0) return false;
+    L->swap = (Cg > Cp) ? 1 : 0;                       // the wider side fills the 128-row M dimension
+    const int Cm = L->swap ? Cg : Cp, Cn = L->swap ? Cp : Cg;
+    L->n_mtiles = (Cm + 127) / 128;
+    int NT = (Cn + 15) / 16 * 16;
+    L->n_ntiles = 1;
+    while (NT > 128) { L->n_ntiles *= 2; NT = ((Cn + L->n_ntiles - 1) / L->n_ntiles + 15) / 16 * 16; }
+    L->NT = NT;
+    int tpc = 512 / NT;
+    if (tpc > 8) tpc = 8;
+    if (tpc > L->ntaps) tpc = L->ntaps;
+    L->n_tapsets = (L->ntaps + tpc - 1) / tpc;
+    tpc = (L->ntaps + L->n_tapsets - 1) / L->n_tapsets;   // balance
+    L->taps_per_cta = tpc;
+    int tm = 32;
+    while (tm < tpc * NT) tm *= 2;
+    L->tmem_cols = tm;
+    // rows per CTA: aim at ~2 CTAs per SM over the launch, at least 4 chunks each
+    const long long tiles = (long long)L->n_mtiles * L->n_ntiles * L->n_tapsets;
+    long long per = ((long long)rows * L->batch * tiles + 148 * 2 - 1) / (148 * 2);
+    per = (per + kWgRK - 1) / kWgRK * kWgRK;
+    if (per < 4 * kWgRK) per = 4 * kWgRK;
+    if (per > rows) per = (rows + kWgRK - 1) / kWgRK * kWgRK;
+    L->rows_per_cta = (int)per;
+    L->chunks_per_batch = (rows + L->rows_per_cta - 1) / L->rows_per_cta;
+    return wgrad_smem_bytes(*L) <= 200 * 1024;
+}
+
+cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(L.batch * L.chunks_per_batch, L.n_mtiles * L.n_ntiles, L.n_tapsets);
+    wgrad_umma_kernel<<<grid, 192, wgrad_smem_bytes(L), stream>>>(L);
     return cudaGetLastError();
 }
 

@@ -63,6 +63,30 @@ struct UmmaChoice {         // tiling decisions for one ConvLaunch
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 
+// wgrad on tensor cores: dW[woff_t + cp*w_sp + cg*w_sg] += scale * sum_{b, m in [m_lo,m_hi)} P[b, m+d_t, cp] * G[b, m, cg]
+// GEMM with the ROWS as the reduction dimension: both operands are MN-major (channels contiguous).
+struct UmmaWgradLaunch {
+    PlaneView P;            // activation side (tap-shifted; may be a MID plane)
+    PlaneView G;            // gradient side (pre-activation gradient), rows m
+    int m_lo, m_hi, batch;
+    int ntaps;
+    int d[16];
+    int woff[16];
+    float* dW;
+    int w_sp, w_sg;         // element strides of dW along the P-channel / G-channel index
+    float scale;
+    int swap;               // 0: A (M side) = P, B (N side) = G;  1: A = G, B = P
+    int NT;                 // N-tile width (multiple of 16, <= 128)
+    int n_mtiles, n_ntiles; // tiles of 128 / NT channels
+    int taps_per_cta, n_tapsets;
+    int rows_per_cta, chunks_per_batch;
+    int tmem_cols;
+};
+
+cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream);
+// fills the tiling fields of L (P, G, taps, dW, strides already set); false = not eligible
+bool umma_plan_wgrad(UmmaWgradLaunch* L);
+
 size_t umma_smem_bytes(const UmmaLaunch& L);
 cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream);
 cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream);

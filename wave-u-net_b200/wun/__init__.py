@@ -18,7 +18,7 @@ SYMBOLS = [
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
     "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step",
     "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
-    "wun_layer_kernel",
+    "wun_layer_kernel", "wun_debug_tensor",
 ]
 
 
@@ -71,6 +71,7 @@ def _load():
     lib.wun_version.restype = ctypes.c_char_p
     lib.wun_describe.argtypes = [H, ctypes.c_char_p, I64]
     lib.wun_describe.restype = I64
+    lib.wun_debug_tensor.argtypes = [H, ctypes.c_char_p, I64, ctypes.c_int, P(I64), P(I64), P(ctypes.c_int32)]
     lib.wun_layer_kernel.argtypes = [H, ctypes.c_int, ctypes.c_int]
     lib.wun_layer_kernel.restype = ctypes.c_char_p
     return lib
@@ -167,6 +168,15 @@ class Engine(object):
 
     def layer_kernel(self, layer, pass_):
         return lib.wun_layer_kernel(self._h, int(layer), int(pass_)).decode()
+
+    def debug_tensor(self, name, batch, training):
+        """View [batch, rows, C] of a saved activation inside the current workspace (tests only)."""
+        off, rows, ch = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        check(lib.wun_debug_tensor(self._h, name.encode(), int(batch), 1 if training else 0, ctypes.byref(off),
+                                   ctypes.byref(rows), ctypes.byref(ch)))
+        ws = next(iter(self._ws.values()))
+        n = int(batch) * rows.value * ch.value
+        return ws[off.value:off.value + n].view(int(batch), rows.value, ch.value)
 
     # ---- device calls (torch tensors supply memory and the stream) --------------------------------
     def _workspace(self, batch, training, device):
