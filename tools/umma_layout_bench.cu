@@ -34,7 +34,7 @@ __device__ __forceinline__ void commit(uint32_t bar) { asm volatile("tcgen05.com
 
 // ---------------- timing ----------------
 // layout: 0 none, 6 = 32B, 4 = 64B, 2 = 128B.  One CTA per SM, lane 0 of warp 0 issues `iters` x 4 MMAs.
-__global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int iters, int shift_rows, long long* out, int nacc, int smem_fill_kb) {
+__global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int iters, int shift_rows, long long* out, int nacc, int smem_fill_kb, int acc_stride, int run_len) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_holder;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int ite
     for (int i = threadIdx.x; i < smem_fill_kb * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_holder)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_holder)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -61,19 +61,18 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int ite
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-            const uint32_t st = (uint32_t)N;   // accumulators N columns apart (nacc*N <= 256)
-            if (nacc == 1) { mma(tm, ad, bd, idesc, 1); mma(tm, ad, bd, idesc, 1); mma(tm, ad, bd, idesc, 1); mma(tm, ad, bd, idesc, 1); }
-            else if (nacc == 2) { mma(tm, ad, bd, idesc, 1); mma(tm + st, ad, bd, idesc, 1); mma(tm, ad, bd, idesc, 1); mma(tm + st, ad, bd, idesc, 1); }
-            else { mma(tm, ad, bd, idesc, 1); mma(tm + st, ad, bd, idesc, 1); mma(tm + 2 * st, ad, bd, idesc, 1); mma(tm + 3 * st, ad, bd, idesc, 1); }
+            // 12 MMAs per iteration: accumulator changes every run_len MMAs, accumulators acc_stride columns apart
+            #pragma unroll
+            for (int q = 0; q < 12; ++q) mma(tm + (uint32_t)(((q / run_len) % nacc) * acc_stride), ad, bd, idesc, 1);
         }
         commit(smem_u32(&bar));
         mbar_wait(smem_u32(&bar), 0);
         long long t1 = clock64();
-        if (blockIdx.x == 0) out[0] = t1 - t0;
+        if (blockIdx.x == 0) out[0] = (t1 - t0) / 3;   // normalise to 4 MMAs per iteration
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tm) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
 // ---------------- correctness of shifted, swizzled A reads ----------------
@@ -154,20 +153,20 @@ int main() {
     CK(cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     const int layouts[4] = {0, 6, 4, 2};
     const char* names[4] = {"NONE", "SW32", "SW64", "SW128"};
-    printf("== cycles per MMA (M=128, K=16 bf16, SWIZZLE_NONE): nacc = accumulators rotated, ctas/SM = 1 or 2 ==\n");
-    for (int N : {48, 64, 96, 128})
-        for (int nacc : {1, 2, 4})
-            for (int per_sm : {1, 2}) {
-                if (nacc * N > 256) continue;
-                const int iters = 500;
-                const int smem_kb = 64;
-                time_kernel<<<148 * per_sm, 128, smem_kb * 1024>>>(0, N, iters, 0, dout, nacc, smem_kb);
-                cudaError_t e = cudaDeviceSynchronize();
-                if (e != cudaSuccess) { printf("N=%d: ERROR %s\n", N, cudaGetErrorString(e)); return 1; }
-                long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
-                printf("N=%3d nacc=%d ctas/SM=%d : %7.1f cycles/MMA per CTA -> %.1f per SM (ideal %d)\n", N, nacc, per_sm,
-                       (double)cyc / (iters * 4), (double)cyc / (iters * 4) / per_sm, N / 2);
-            }
+    printf("== cycles per MMA vs accumulator placement (M=128, K=16, SWIZZLE_NONE, 1 CTA/SM) ==\n");
+    for (int N : {96, 48})
+        for (int nacc : {1, 2})
+            for (int stride : {N, 128, 256})
+                for (int run : {1, 3, 12}) {
+                    if (nacc == 1 && (stride != N || run != 1)) continue;
+                    if ((nacc - 1) * stride + N > 512) continue;
+                    const int iters = 300, smem_kb = 64;
+                    time_kernel<<<148, 128, smem_kb * 1024>>>(0, N, iters, 0, dout, nacc, smem_kb, stride, run);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("ERROR %s\n", cudaGetErrorString(e)); return 1; }
+                    long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
+                    printf("N=%3d nacc=%d stride=%3d switch-every=%2d : %6.1f cycles/MMA\n", N, nacc, stride, run, (double)cyc / (iters * 4));
+                }
     return 0;
     printf("== shifted-start correctness: D[m][n] must equal A[m+shift][koff/2 + n] ==\n");
     float* dres; CK(cudaMalloc(&dres, 2 * 128 * 16 * 4));

@@ -46,12 +46,11 @@ __device__ __forceinline__ float plane_load(const PlaneView& P, int b, int r, in
 // plane convolution: out_cls[b, m, n] = epi( sum_terms plane[b, m+d, :] . W_term[:, n] )
 //   grid  = (ceil(max_rows/BM), ceil(N/BN), batch*ncls),  128 threads, 8x8 register tile / thread
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int CK>
 __global__ void __launch_bounds__(128) plane_conv_kernel(const __grid_constant__ ConvLaunch L) {
     constexpr int NTH = BN / 8;
     constexpr int MTH = 128 / NTH;
     constexpr int BM = MTH * 8;
-    constexpr int CK = 8;
     constexpr int SPAN = 36;
     constexpr int SR = BM + SPAN;               // == 4 (mod 32): conflict-free transposed stores
     __shared__ float slab[CK][SR];
@@ -156,9 +155,17 @@ void launch_plane_conv_simt(const ConvLaunch& L, cudaStream_t stream) {
     const int nth = bn / 8, bm = (128 / nth) * 8;
     dim3 grid((L.max_rows + bm - 1) / bm, (L.N + bn - 1) / bn, L.batch * L.ncls);
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
-    if (bn == 64) plane_conv_kernel<64><<<grid, 128, 0, stream>>>(L);
-    else if (bn == 32) plane_conv_kernel<32><<<grid, 128, 0, stream>>>(L);
-    else plane_conv_kernel<16><<<grid, 128, 0, stream>>>(L);
+    int maxc = 0;
+    for (int p = 0; p < L.nplanes; ++p) maxc = (L.planes[p].C > maxc) ? L.planes[p].C : maxc;
+    if (maxc <= 2) {            // first layer (mono / stereo input): 2-channel chunks instead of 8
+        if (bn == 64) plane_conv_kernel<64, 2><<<grid, 128, 0, stream>>>(L);
+        else if (bn == 32) plane_conv_kernel<32, 2><<<grid, 128, 0, stream>>>(L);
+        else plane_conv_kernel<16, 2><<<grid, 128, 0, stream>>>(L);
+    } else {
+        if (bn == 64) plane_conv_kernel<64, 8><<<grid, 128, 0, stream>>>(L);
+        else if (bn == 32) plane_conv_kernel<32, 8><<<grid, 128, 0, stream>>>(L);
+        else plane_conv_kernel<16, 8><<<grid, 128, 0, stream>>>(L);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,9 +245,83 @@ __global__ void __launch_bounds__(128) plane_wgrad_kernel(const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad for planes with very few channels (the first layer: C_in = 1 or 2).  Thread = (tap, channel, 4 output
+// columns); the row chunk is staged in shared memory.  grid = (row chunks * batch), 256 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plane_wgrad_smallc_kernel(const __grid_constant__ WgradLaunch L) {
+    constexpr int RK = 128, XR = RK + 16;
+    __shared__ float Xs[XR][4];
+    __shared__ __align__(16) float Gs[RK][64];
+    const int tid = threadIdx.x;
+    const int C = L.plane.C, N = L.N, NQ = (N + 3) / 4;
+    const int rows = L.m_hi - L.m_lo;
+    const int chunks = (rows + L.rows_per_cta - 1) / L.rows_per_cta;
+    const int b = blockIdx.x / chunks;
+    const int mc0 = L.m_lo + (blockIdx.x % chunks) * L.rows_per_cta;
+    const int mc1 = min(mc0 + L.rows_per_cta, L.m_hi);
+    int dmin = L.d[0], dmax = L.d[0];
+    for (int i = 1; i < L.nterms; ++i) { dmin = min(dmin, L.d[i]); dmax = max(dmax, L.d[i]); }
+    const int span = dmax - dmin;
+    const int OG = L.nterms * C * NQ;                // output groups (tap, c, column quad)
+    float acc[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[u][j] = 0.f;
+    for (int mb = mc0; mb < mc1; mb += RK) {
+        const int nr = min(RK, mc1 - mb);
+        for (int idx = tid; idx < (RK + span) * 4; idx += 256) {
+            const int c = idx & 3, rr = idx >> 2;
+            Xs[rr][c] = (rr < nr + span && c < C) ? plane_load(L.plane, b, mb + dmin + rr, c) : 0.f;
+        }
+        for (int idx = tid; idx < RK * 64; idx += 256) {
+            const int n = idx & 63, rr = idx >> 6;
+            Gs[rr][n] = (rr < nr && n < N) ? plane_load(L.dpre, b, mb + rr, n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int og = tid + u * 256;
+            if (og < OG) {
+                const int nq = og % NQ, tc = og / NQ;
+                const int c = tc % C, doff = L.d[tc / C] - dmin;
+                for (int r = 0; r < RK; ++r) {
+                    const float x = Xs[r + doff][c];
+                    const float4 g = *reinterpret_cast<const float4*>(&Gs[r][nq * 4]);
+                    acc[u][0] = fmaf(x, g.x, acc[u][0]); acc[u][1] = fmaf(x, g.y, acc[u][1]);
+                    acc[u][2] = fmaf(x, g.z, acc[u][2]); acc[u][3] = fmaf(x, g.w, acc[u][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int og = tid + u * 256;
+        if (og >= OG) continue;
+        const int nq = og % NQ, tc = og / NQ;
+        const int c = tc % C, t = tc / C;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = nq * 4 + j;
+            if (n < N) atomicAdd(L.dW + (long long)L.woff[t] + (long long)c * L.w_sk + (long long)n * L.w_sn, acc[u][j] * L.scale);
+        }
+    }
+}
+
 void launch_plane_wgrad_simt(WgradLaunch L, cudaStream_t stream) {
     const int rows = L.m_hi - L.m_lo;
     if (rows <= 0 || L.nterms <= 0) return;
+    if (L.plane.C <= 4 && L.N <= 64 && L.nterms * L.plane.C * ((L.N + 3) / 4) <= 512) {
+        long long per = ((long long)rows * L.batch + 148 * 6 - 1) / (148 * 6);
+        per = ((per + 127) / 128) * 128;
+        if (per > rows) per = ((rows + 127) / 128) * 128;
+        L.rows_per_cta = (int)per;
+        const int chunks = (rows + L.rows_per_cta - 1) / L.rows_per_cta;
+        plane_wgrad_smallc_kernel<<<chunks * L.batch, 256, 0, stream>>>(L);
+        return;
+    }
     const int tiles = ((L.plane.C + 15) / 16) * ((L.N + 63) / 64);
     // aim at ~8 CTAs per SM over the whole launch, at least 32 rows per CTA
     long long target = 148LL * 8;

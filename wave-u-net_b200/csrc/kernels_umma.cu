@@ -225,27 +225,41 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
             const int nchunk = (P.C + 15) >> 4;
             for (int c = 0; c < nchunk; ++c, ++ji) {
                 const int st = ji % kSlabStages;
-                if (tid == 0) { T_WAIT(6, mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1)); }
-                else mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
-                const long long t_fill = T_NOW();
                 uint8_t* S = slab0 + st * slab_bytes;
                 const uint32_t atom_stride = 16u * L.rows_alloc;
-                for (int rr = tid; rr < L.rows_alloc; rr += kWorkerThreads) {
-                    float x[16];
-                    load_row16(P, b, m_base + G.dmin + rr, c * 16, x);
-                    uint32_t hi[8], lo[8];
+                const long long t_fill = T_NOW();
+                // Loads of up to kRB rows per thread are issued together and BEFORE the stage-free wait, so their
+                // latency overlaps the wait; only the convert + st.shared part needs the stage.
+                constexpr int kRB = 3;
+                bool waited = false;
+                for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
+                    float x[kRB][16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-                        const float r0 = x[2 * i] - __bfloat162float(h0), r1 = x[2 * i + 1] - __bfloat162float(h1);
-                        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        lo[i] = pack_bf16x2(r0, r1);
+                    for (int u = 0; u < kRB; ++u) {
+                        const int rr = rbase + u * kWorkerThreads + tid;
+                        if (rr < L.rows_alloc) load_row16(P, b, m_base + G.dmin + rr, c * 16, x[u]);
                     }
-                    uint4* d = reinterpret_cast<uint4*>(S + 16u * rr);
-                    *d = make_uint4(hi[0], hi[1], hi[2], hi[3]);                                                  // hi, atom 0
-                    *reinterpret_cast<uint4*>(S + atom_stride + 16u * rr) = make_uint4(hi[4], hi[5], hi[6], hi[7]);   // hi, atom 1
-                    *reinterpret_cast<uint4*>(S + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(S + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (!waited) {
+                        if (tid == 0) { T_WAIT(6, mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1)); }
+                        else mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kRB; ++u) {
+                        const int rr = rbase + u * kWorkerThreads + tid;
+                        if (rr >= L.rows_alloc) continue;
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[u][2 * i]), h1 = __float2bfloat16_rn(x[u][2 * i + 1]);
+                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i] = pack_bf16x2(x[u][2 * i] - __bfloat162float(h0), x[u][2 * i + 1] - __bfloat162float(h1));
+                        }
+                        *reinterpret_cast<uint4*>(S + 16u * rr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);                       // hi, atom 0
+                        *reinterpret_cast<uint4*>(S + atom_stride + 16u * rr) = make_uint4(hi[4], hi[5], hi[6], hi[7]);        // hi, atom 1
+                        *reinterpret_cast<uint4*>(S + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(S + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
                 }
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 mbar_arrive(BAR(SLAB_FULL + st));
@@ -258,45 +272,64 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
         tc_fence_after();
         const long long t_epi = T_NOW();
         const int n0 = split * NPAD;
+        // Stage each 128 x CW accumulator block in shared memory (the slab / weight ring is idle now: every MMA
+        // has retired), then write it out with one warp per output row: fully coalesced stores, and the
+        // LeakyReLU-slope / accumulate reads of the dgrad epilogue are coalesced too.
+        float* stage = reinterpret_cast<float*>(smem);
+        const int CW = (NPAD < 128) ? NPAD : 128;          // columns staged at a time
+        const int SW = CW + 4;                              // padded row stride (floats): conflict-free float4 rows
         for (int mt = 0; mt < L.MT; ++mt) {
-            const int m = m_base + mt * 128 + warp * 32 + lane;
-            const bool row_ok = m < K.out.m_hi;
-            const long long roff = (long long)b * K.out.bstride + (long long)m * K.out.rstride;
-            const bool accum = row_ok && (m >= K.out.acc_lo && m < K.out.acc_hi);
-            for (int cb = 0; cb < NPAD; cb += 16) {
-                if (n0 + cb >= L.N) break;           // warp-uniform
-                __syncwarp();                        // tcgen05.ld is .sync.aligned: reconverge after masked stores
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + cb), v);
-                if (!row_ok) continue;
+            for (int c0 = 0; c0 < NPAD; c0 += CW) {
+                if (n0 + c0 >= L.N) break;
+                const int cw = min(CW, NPAD - c0);
+                // phase 1: thread = accumulator row (TMEM lane)
+                for (int cb = 0; cb < cw; cb += 16) {
+                    __syncwarp();
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + c0 + cb), v);
+                    if (L.epilogue == EPI_BIAS_LRELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + cb + j;
-                    if (n < L.N) {
-                        float y = v[j];
-                        if (L.epilogue == EPI_BIAS_LRELU) {
-                            if (L.bias) y += __ldg(L.bias + n);
-                            y = fmaxf(0.2f * y, y);
-                        } else if (L.epilogue == EPI_SLOPE && K.out.saved) {
-                            const float s = __ldg(K.out.saved + roff + n);
-                            y *= (s > 0.f) ? 1.f : 0.2f;
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c0 + cb + j;
+                            float y = v[j] + ((L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f);
+                            v[j] = fmaxf(0.2f * y, y);
                         }
-                        v[j] = y;
                     }
-                }
-                float* dst = K.out.base + roff + n0 + cb;
-                if (n0 + cb + 16 <= L.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    float4* dst = reinterpret_cast<float4*>(stage + (size_t)(warp * 32 + lane) * SW + cb);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (accum) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                        d4[q] = o;
-                    }
-                } else {
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + cb + j < L.N) dst[j] = accum ? (dst[j] + v[j]) : v[j];
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // phase 2: warp = output row, lanes = columns
+                const int ncols = min(cw, L.N - (n0 + c0));
+                for (int r = warp; r < 128; r += 4) {
+                    const int m = m_base + mt * 128 + r;
+                    if (m >= K.out.m_hi) break;
+                    const long long roff = (long long)b * K.out.bstride + (long long)m * K.out.rstride + n0 + c0;
+                    const bool accum = (m >= K.out.acc_lo && m < K.out.acc_hi);
+                    float* dst = K.out.base + roff;
+                    const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (ncols % 4 == 0);
+                    if (vec) {
+                        for (int q = lane; q < ncols / 4; q += 32) {
+                            float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
+                            if (L.epilogue == EPI_SLOPE && K.out.saved) {
+                                const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
+                                o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
+                                o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
+                            }
+                            if (accum) { const float4 old = reinterpret_cast<float4*>(dst)[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                            reinterpret_cast<float4*>(dst)[q] = o;
+                        }
+                    } else {
+                        for (int j = lane; j < ncols; j += 32) {
+                            float o = stage[(size_t)r * SW + j];
+                            if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
+                            if (accum) o += dst[j];
+                            dst[j] = o;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is overwritten by the next block
             }
         }
         tc_fence_before();
@@ -405,7 +438,9 @@ constexpr int kWgRK = 64;          // rows per pipeline stage
 constexpr int kWgSpan = 16;        // extra P rows per stage (max tap shift span)
 constexpr int kWgStages = 2;
 
-__global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constant__ UmmaWgradLaunch L) {
+constexpr int kWgConvThreads = 256;   // 8 converter warps (0-7); warp 8 = TMEM alloc + MMA issue
+
+__global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constant__ UmmaWgradLaunch L) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / L.chunks_per_batch;
@@ -433,79 +468,95 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
     const int FULL = 0, EMPTY = kWgStages, ACC = 2 * kWgStages;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC + 1);
     if (tid == 0) {
-        for (int i = 0; i < kWgStages; ++i) { mbar_init(BAR(FULL + i), kWorkerThreads); mbar_init(BAR(EMPTY + i), 1); }
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(BAR(FULL + i), kWgConvThreads); mbar_init(BAR(EMPTY + i), 1); }
         mbar_init(BAR(ACC), 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const int nchunks = (r1 - r0 + kWgRK - 1) / kWgRK;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ===================== converter =====================
+        // items of a chunk: (side, row, 16-channel group); A side = 8 groups (128 channels), B side = NT/16 groups
+        const int gA = 8, gB = (L.NT + 15) / 16;
+        const int itemsA = rowsA * gA, items = itemsA + rowsB * gB;
+        constexpr int kIB = 4;                                   // items in flight per thread
         for (int ci = 0; ci < nchunks; ++ci) {
             const int st = ci % kWgStages;
-            mbar_wait(BAR(EMPTY + st), ((ci / kWgStages) & 1) ^ 1);
             uint8_t* S = smem + st * stage_bytes;
             const int rc = r0 + ci * kWgRK;                      // first G row of this chunk
-            // items: (side, row, 16-channel group)
-            const int gA = 8, gB = (L.NT + 15) / 16;             // 16-channel groups per side (A tile = 128 ch)
-            const int itemsA = rowsA * gA, items = itemsA + rowsB * gB;
-            for (int it = tid; it < items; it += kWorkerThreads) {
-                const bool isA = it < itemsA;
-                const int k = isA ? it : it - itemsA;
-                const int ng = isA ? gA : gB;
-                const int rr = k / ng, g = k % ng;
-                const bool isP = isA != (L.swap != 0);
-                const PlaneView& V = isA ? SA : SB;
-                const int c0 = (isA ? ca0 : cb0) + g * 16;
-                float x[16];
-                int row = isP ? (rc + dmin + rr) : (rc + rr);
-                bool valid = c0 < V.C;
-                if (!isP && (row >= r1 || row < r0)) valid = false;      // G rows outside this CTA's range contribute 0
-                if (valid) load_row16(V, b, row, c0, x);
-                else {
+            bool waited = false;
+            for (int ibase = 0; ibase < items; ibase += kIB * kWgConvThreads) {
+                float x[kIB][16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) x[i] = 0.f;
-                }
-                uint32_t hi[8], lo[8];
+                for (int u = 0; u < kIB; ++u) {
+                    const int it = ibase + u * kWgConvThreads + tid;
+                    if (it >= items) continue;
+                    const bool isA = it < itemsA;
+                    const int k = isA ? it : it - itemsA;
+                    const int ng = isA ? gA : gB;
+                    const int rr = k / ng, g = k % ng;
+                    const bool isP = isA != (L.swap != 0);
+                    const PlaneView& V = isA ? SA : SB;
+                    const int c0 = (isA ? ca0 : cb0) + g * 16;
+                    const int row = isP ? (rc + dmin + rr) : (rc + rr);
+                    bool valid = c0 < V.C;
+                    if (!isP && (row >= r1 || row < r0)) valid = false;   // G rows outside this CTA's range contribute 0
+                    if (valid) load_row16(V, b, row, c0, x[u]);
+                    else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-                    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[i] = pack_bf16x2(x[2 * i] - __bfloat162float(h0), x[2 * i + 1] - __bfloat162float(h1));
+                        for (int i = 0; i < 16; ++i) x[u][i] = 0.f;
+                    }
                 }
-                const uint32_t plane = isA ? planeA : planeB;
-                uint8_t* base = S + (isA ? 0u : bytesA) + (uint32_t)(2 * g) * plane + 16u * rr;
-                const uint32_t lo_off = (isA ? atomsA : atomsB) * plane;
-                if (isA || (2 * g) < atomsB) {
+                if (!waited) { mbar_wait(BAR(EMPTY + st), ((ci / kWgStages) & 1) ^ 1); waited = true; }
+#pragma unroll
+                for (int u = 0; u < kIB; ++u) {
+                    const int it = ibase + u * kWgConvThreads + tid;
+                    if (it >= items) continue;
+                    const bool isA = it < itemsA;
+                    const int k = isA ? it : it - itemsA;
+                    const int ng = isA ? gA : gB;
+                    const int rr = k / ng, g = k % ng;
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[u][2 * i]), h1 = __float2bfloat16_rn(x[u][2 * i + 1]);
+                        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[i] = pack_bf16x2(x[u][2 * i] - __bfloat162float(h0), x[u][2 * i + 1] - __bfloat162float(h1));
+                    }
+                    const uint32_t plane = isA ? planeA : planeB;
+                    uint8_t* base = S + (isA ? 0u : bytesA) + (uint32_t)(2 * g) * plane + 16u * rr;
+                    const uint32_t lo_off = (isA ? atomsA : atomsB) * plane;
                     *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(base + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
-                if (isA || (2 * g + 1) < atomsB) {
-                    *reinterpret_cast<uint4*>(base + plane) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(base + plane + lo_off) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (isA || (2 * g + 1) < atomsB) {
+                        *reinterpret_cast<uint4*>(base + plane) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<uint4*>(base + plane + lo_off) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
                 }
             }
             fence_proxy_async();
             mbar_arrive(BAR(FULL + st));
         }
         // ===================== epilogue: accumulators -> atomic adds into dW =====================
+        // TMEM lane quarter = warp % 4; the two warps of a quarter split the taps.
         mbar_wait(BAR(ACC), 0);
         tc_fence_after();
-        const int m = ca0 + warp * 32 + lane;                    // M-side channel of this thread
+        const int q4 = warp & 3;
+        const int m = ca0 + q4 * 32 + lane;                      // M-side channel of this thread
         const bool m_ok = m < SA.C;
         const int sM = L.swap ? L.w_sg : L.w_sp, sN = L.swap ? L.w_sp : L.w_sg;
-        for (int t = 0; t < ntap; ++t) {
+        for (int t = (warp >> 2); t < ntap; t += 2) {
             float* dst_t = L.dW + (long long)L.woff[tap0 + t] + (long long)m * sM;
             for (int cb = 0; cb < L.NT; cb += 16) {
                 if (cb0 + cb >= SB.C) break;
                 __syncwarp();
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * L.NT + cb), v);
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * L.NT + cb), v);
                 if (!m_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -515,7 +566,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
             }
         }
         tc_fence_before();
-    } else if (warp == 4) {
+    } else {
         if (lane == 0) {
             // both operands MN-major: idesc a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(L.NT >> 3) << 17) | ((128u >> 4) << 24);
@@ -525,20 +576,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
                 mbar_wait(BAR(FULL + st), (ci / kWgStages) & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
-                for (int ks = 0; ks < kWgRK / 16; ++ks) {
-                    for (int t = 0; t < ntap; ++t) {
-                        const uint32_t shift = 16u * (uint32_t)(L.d[tap0 + t] - dmin);
+                // tap-outer order: 12 consecutive MMAs per accumulator
+                for (int t = 0; t < ntap; ++t) {
+                    const uint32_t shift = 16u * (uint32_t)(L.d[tap0 + t] - dmin);
+                    const uint32_t td = tmem_base + (uint32_t)(t * L.NT);
+                    for (int ks = 0; ks < kWgRK / 16; ++ks) {
                         const uint32_t a0 = sa + 256u * ks + (L.swap ? 0u : shift);
                         const uint32_t b0 = sb + 256u * ks + (L.swap ? shift : 0u);
                         const uint64_t a_hi = umma_desc(a0, 128, planeA), a_lo = umma_desc(a0 + atomsA * planeA, 128, planeA);
                         const uint64_t b_hi = umma_desc(b0, 128, planeB), b_lo = umma_desc(b0 + atomsB * planeB, 128, planeB);
-                        const uint32_t td = tmem_base + (uint32_t)(t * L.NT);
-                        umma_bf16(td, a_lo, b_hi, idesc, accum);
+                        umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
                         umma_bf16(td, a_hi, b_lo, idesc, 1u);
                         umma_bf16(td, a_hi, b_hi, idesc, 1u);
                     }
-                    accum = 1u;
                 }
+                accum = 1u;
                 umma_commit(BAR(EMPTY + st));
             }
             umma_commit(BAR(ACC));
@@ -546,7 +598,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(const __grid_constan
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, L.tmem_cols);
     }
@@ -603,7 +655,7 @@ cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid(L.batch * L.chunks_per_batch, L.n_mtiles * L.n_ntiles, L.n_tapsets);
-    wgrad_umma_kernel<<<grid, 192, wgrad_smem_bytes(L), stream>>>(L);
+    wgrad_umma_kernel<<<grid, 288, wgrad_smem_bytes(L), stream>>>(L);
     return cudaGetLastError();
 }
 
