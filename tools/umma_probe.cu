@@ -173,10 +173,12 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
     CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgd, gdec.data(), gdec.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgo, godd.data(), godd.size() * 4, cudaMemcpyHostToDevice));
-    std::vector<UmmaWgradLaunch> launches;
+    UmmaWgradLaunch WL;
+    memset(&WL, 0, sizeof(WL));
+    WL.batch = p.B; WL.dW = ddw; WL.w_sp = p.Cout; WL.w_sg = 1; WL.scale = 1.f;
     for (int q = 0; q < 2; ++q)
         for (int par = 0; par < 2; ++par) {
-            UmmaWgradLaunch W;
+            WgGroup W;
             memset(&W, 0, sizeof(W));
             W.P.base = dx + par * p.Cin; W.P.bstride = (long long)p.T * p.Cin; W.P.rstride = 2 * p.Cin;
             W.P.r_lo = 0; W.P.r_hi = (par == 0) ? (p.T + 1) / 2 : p.T / 2; W.P.C = p.Cin; W.P.kind = PLANE_DIRECT;
@@ -185,19 +187,19 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
             W.G.rstride = p.Cout; W.G.C = p.Cout; W.G.kind = PLANE_DIRECT;
             W.m_lo = (q == 0) ? 0 : mo_lo; W.m_hi = (q == 0) ? Td : mo_hi;
             W.G.r_lo = W.m_lo; W.G.r_hi = W.m_hi;
-            W.batch = p.B; W.dW = ddw; W.w_sp = p.Cout; W.w_sg = 1; W.scale = 1.f;
             for (int j = 0; j < p.fs; ++j) {
                 int e = q + j;
                 if ((e & 1) != par) continue;
                 W.d[W.ntaps] = e >> 1; W.woff[W.ntaps] = j * p.Cin * p.Cout; ++W.ntaps;
             }
             if (W.m_hi <= W.m_lo || W.ntaps == 0) continue;
-            if (!umma_plan_wgrad(&W)) { printf("[%s] wgrad not eligible\n", name); exit(4); }
-            launches.push_back(W);
+            WL.grp[WL.ngroups++] = W;
         }
-    const UmmaWgradLaunch& W0 = launches[0];
-    printf("[%s] wgrad B=%d T=%d Cin=%d Cout=%d swap=%d NT=%d mtiles=%d ntiles=%d taps/cta=%d tapsets=%d rows/cta=%d tmem=%d\n", name, p.B, p.T,
-           p.Cin, p.Cout, W0.swap, W0.NT, W0.n_mtiles, W0.n_ntiles, W0.taps_per_cta, W0.n_tapsets, W0.rows_per_cta, W0.tmem_cols);
+    if (!umma_plan_wgrad(&WL)) { printf("[%s] wgrad not eligible\n", name); exit(4); }
+    std::vector<UmmaWgradLaunch> launches(1, WL);
+    const WgGroup& W0 = WL.grp[0];
+    printf("[%s] wgrad B=%d T=%d Cin=%d Cout=%d swap=%d NT=%d mtiles=%d ntiles=%d taps/cta=%d tapsets=%d chunks/cta=%d grid=(%d,%d,%d)\n", name, p.B, p.T,
+           p.Cin, p.Cout, W0.swap, W0.NT, W0.n_mtiles, W0.n_ntiles, W0.taps_per_cta, W0.n_tapsets, W0.chunks_per_cta, WL.grid_x, WL.grid_y, WL.grid_z);
     CK(cudaMemset(ddw, 0, wn * 4));
     for (auto& W : launches) CK(launch_wgrad_umma(W, 0));
     cudaError_t e = cudaDeviceSynchronize();
@@ -236,7 +238,7 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= timing_iters;
         const double flops = 2.0 * p.B * ((double)Td + n_odd) * p.fs * p.Cin * p.Cout;
-        printf("[%s] wgrad time %.1f us (4 launches)  %.1f useful TFLOP/s\n", name, ms * 1e3, flops / (ms * 1e-3) * 1e-12);
+        printf("[%s] wgrad time %.1f us (1 launch)  %.1f useful TFLOP/s\n", name, ms * 1e3, flops / (ms * 1e-3) * 1e-12);
     }
     cudaFree(dx); cudaFree(dgd); cudaFree(dgo); cudaFree(ddw);
 }

@@ -318,11 +318,12 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
 static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale, int layer_index) {
     const Plan& P = h->plan;
     h->cur_layer = layer_index;
+    // collect (class, plane) groups
+    std::vector<WgradLaunch> groups;
     for (const auto& c : op.classes) {
         if (c.m_hi <= c.m_lo) continue;
         PlaneView dpre = make_plane_on(h, c.out, P.grad_twin[c.out.tensor], view_bstride(h, c.out), c.m_lo, c.m_hi);
-        // bias gradient
-        ++h->launches;
+        ++h->launches;                                         // bias gradient
         if (!h->dry) launch_colsum(dpre, h->batch, scale, grads + P.params[op.b_param].offset, h->stream);
         size_t i = 0;
         while (i < c.terms.size()) {
@@ -341,24 +342,37 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
             W.N = op.cout; W.w_sk = op.cout; W.w_sn = 1;
             W.dW = grads + P.params[op.w_param].offset;
             W.scale = scale; W.batch = h->batch;
-            ++h->launches;
-            // tensor-core wgrad when eligible
-            UmmaWgradLaunch U;
-            memset(&U, 0, sizeof(U));
-            U.P = W.plane; U.G = W.dpre; U.m_lo = W.m_lo; U.m_hi = W.m_hi; U.batch = W.batch; U.ntaps = W.nterms;
-            for (int t = 0; t < W.nterms; ++t) { U.d[t] = W.d[t]; U.woff[t] = W.woff[t]; }
-            U.dW = W.dW; U.w_sp = W.w_sk; U.w_sg = W.w_sn; U.scale = W.scale;
-            const bool use_umma = h->umma_enabled && h->umma_pass[2] && umma_plan_wgrad(&U);
-            const size_t slot = (size_t)h->cur_layer * 3 + 2;
-            if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
-            if (h->dry) continue;
-            if (use_umma) {
-                cudaError_t e = launch_wgrad_umma(U, h->stream);
-                if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 wgrad launch: ") + cudaGetErrorString(e));
-            } else {
-                launch_plane_wgrad_simt(W, h->stream);
-            }
+            groups.push_back(W);
         }
+    }
+    // tensor cores: all groups of the layer in ONE launch
+    bool use_umma = h->umma_enabled && h->umma_pass[2] && !groups.empty() && groups.size() <= (size_t)kWgMaxGroups;
+    UmmaWgradLaunch U;
+    if (use_umma) {
+        memset(&U, 0, sizeof(U));
+        U.ngroups = (int)groups.size(); U.batch = h->batch; U.dW = groups[0].dW;
+        U.w_sp = op.cout; U.w_sg = 1; U.scale = scale;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            WgGroup& G = U.grp[g];
+            G.P = groups[g].plane; G.G = groups[g].dpre; G.m_lo = groups[g].m_lo; G.m_hi = groups[g].m_hi;
+            G.ntaps = groups[g].nterms;
+            for (int t = 0; t < G.ntaps; ++t) { G.d[t] = groups[g].d[t]; G.woff[t] = groups[g].woff[t]; }
+        }
+        use_umma = umma_plan_wgrad(&U);
+    }
+    const size_t slot = (size_t)h->cur_layer * 3 + 2;
+    if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
+    if (use_umma) {
+        ++h->launches;
+        if (!h->dry) {
+            cudaError_t e = launch_wgrad_umma(U, h->stream);
+            if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 wgrad launch: ") + cudaGetErrorString(e));
+        }
+        return WUN_OK;
+    }
+    for (const auto& W : groups) {
+        ++h->launches;
+        if (!h->dry) launch_plane_wgrad_simt(W, h->stream);
     }
     return WUN_OK;
 }

@@ -440,27 +440,38 @@ constexpr int kWgStages = 2;
 
 constexpr int kWgConvThreads = 256;   // 8 converter warps (0-7); warp 8 = TMEM alloc + MMA issue
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constant__ UmmaWgradLaunch L) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x / L.chunks_per_batch;
-    const int r0 = L.m_lo + (blockIdx.x % L.chunks_per_batch) * L.rows_per_cta;
-    const int r1 = min(r0 + L.rows_per_cta, L.m_hi);
-    if (r0 >= r1) return;
-    const int mtile = blockIdx.y / L.n_ntiles, ntile = blockIdx.y % L.n_ntiles;
-    const int tap0 = blockIdx.z * L.taps_per_cta;
-    const int ntap = min(L.taps_per_cta, L.ntaps - tap0);
-    const PlaneView& SA = L.swap ? L.G : L.P;       // M side (128-channel tile)
-    const PlaneView& SB = L.swap ? L.P : L.G;       // N side (NT-channel tile)
-    const int ca0 = mtile * 128, cb0 = ntile * L.NT;
-    const int rowsA = L.swap ? kWgRK : kWgRK + kWgSpan;
-    const int rowsB = L.swap ? kWgRK + kWgSpan : kWgRK;
+    // group / tap set of this CTA
+    int gi = 0;
+    while (gi + 1 < L.ngroups && (int)blockIdx.z >= L.grp[gi + 1].z0) ++gi;
+    const WgGroup& Gp = L.grp[gi];
+    const int tapset = blockIdx.z - Gp.z0;
+    if ((int)blockIdx.x >= Gp.n_ctas_x || (int)blockIdx.y >= Gp.n_mtiles * Gp.n_ntiles) return;
+    const int total_chunks = L.batch * Gp.chunks_per_batch;
+    const int g0 = blockIdx.x * Gp.chunks_per_cta;
+    const int g1 = min(g0 + Gp.chunks_per_cta, total_chunks);
+    if (g0 >= g1) return;
+    const int mtile = blockIdx.y / Gp.n_ntiles, ntile = blockIdx.y % Gp.n_ntiles;
+    const int tap0 = tapset * Gp.taps_per_cta;
+    const int ntap = min(Gp.taps_per_cta, Gp.ntaps - tap0);
+    const int NT = Gp.NT, swap = Gp.swap;
+    const PlaneView& SA = swap ? Gp.G : Gp.P;       // M side (128-channel tile)
+    const PlaneView& SB = swap ? Gp.P : Gp.G;       // N side (NT-channel tile)
+    const int ca0 = mtile * 128, cb0 = ntile * NT;
+    const int rowsA = swap ? kWgRK : kWgRK + kWgSpan;
+    const int rowsB = swap ? kWgRK + kWgSpan : kWgRK;
     const uint32_t planeA = 16u * rowsA, planeB = 16u * rowsB;           // atom-plane strides
-    const int atomsA = 16, atomsB = L.NT / 8;
+    const int atomsA = 16, atomsB = NT / 8;
     const uint32_t bytesA = 2u * atomsA * planeA, bytesB = 2u * atomsB * planeB;
     const uint32_t stage_bytes = bytesA + bytesB;
-    int dmin = L.d[tap0];
-    for (int t = 1; t < ntap; ++t) dmin = min(dmin, L.d[tap0 + t]);
+    int dmin = Gp.d[tap0];
+    for (int t = 1; t < ntap; ++t) dmin = min(dmin, Gp.d[tap0 + t]);
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
     const uint32_t bar0 = smem_u32(bars);
@@ -472,23 +483,26 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         mbar_init(BAR(ACC), 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), Gp.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const int nchunks = (r1 - r0 + kWgRK - 1) / kWgRK;
+    const int nchunks = g1 - g0;
 
     if (warp < 8) {
         // ===================== converter =====================
         // items of a chunk: (side, row, 16-channel group); A side = 8 groups (128 channels), B side = NT/16 groups
-        const int gA = 8, gB = (L.NT + 15) / 16;
+        const int gA = 8, gB = (NT + 15) / 16;
         const int itemsA = rowsA * gA, items = itemsA + rowsB * gB;
         constexpr int kIB = 4;                                   // items in flight per thread
         for (int ci = 0; ci < nchunks; ++ci) {
             const int st = ci % kWgStages;
             uint8_t* S = smem + st * stage_bytes;
-            const int rc = r0 + ci * kWgRK;                      // first G row of this chunk
+            const int gch = g0 + ci;                              // batch-folded chunk index
+            const int b = gch / Gp.chunks_per_batch;
+            const int rc = Gp.m_lo + (gch % Gp.chunks_per_batch) * kWgRK;   // first G row of this chunk
+            const int rend = min(rc + kWgRK, Gp.m_hi);
             bool waited = false;
             for (int ibase = 0; ibase < items; ibase += kIB * kWgConvThreads) {
                 float x[kIB][16];
@@ -500,12 +514,12 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                     const int k = isA ? it : it - itemsA;
                     const int ng = isA ? gA : gB;
                     const int rr = k / ng, g = k % ng;
-                    const bool isP = isA != (L.swap != 0);
+                    const bool isP = isA != (swap != 0);
                     const PlaneView& V = isA ? SA : SB;
                     const int c0 = (isA ? ca0 : cb0) + g * 16;
                     const int row = isP ? (rc + dmin + rr) : (rc + rr);
                     bool valid = c0 < V.C;
-                    if (!isP && (row >= r1 || row < r0)) valid = false;   // G rows outside this CTA's range contribute 0
+                    if (!isP && row >= rend) valid = false;       // G rows beyond the chunk / class contribute 0
                     if (valid) load_row16(V, b, row, c0, x[u]);
                     else {
 #pragma unroll
@@ -542,26 +556,32 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
             fence_proxy_async();
             mbar_arrive(BAR(FULL + st));
         }
-        // ===================== epilogue: accumulators -> atomic adds into dW =====================
+        // ===================== epilogue: accumulators -> reductions into dW =====================
         // TMEM lane quarter = warp % 4; the two warps of a quarter split the taps.
         mbar_wait(BAR(ACC), 0);
         tc_fence_after();
         const int q4 = warp & 3;
         const int m = ca0 + q4 * 32 + lane;                      // M-side channel of this thread
         const bool m_ok = m < SA.C;
-        const int sM = L.swap ? L.w_sg : L.w_sp, sN = L.swap ? L.w_sp : L.w_sg;
+        const int sM = swap ? L.w_sg : L.w_sp, sN = swap ? L.w_sp : L.w_sg;
         for (int t = (warp >> 2); t < ntap; t += 2) {
-            float* dst_t = L.dW + (long long)L.woff[tap0 + t] + (long long)m * sM;
-            for (int cb = 0; cb < L.NT; cb += 16) {
+            float* dst_t = L.dW + (long long)Gp.woff[tap0 + t] + (long long)m * sM;
+            for (int cb = 0; cb < NT; cb += 16) {
                 if (cb0 + cb >= SB.C) break;
                 __syncwarp();
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * L.NT + cb), v);
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * NT + cb), v);
                 if (!m_ok) continue;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = cb0 + cb + j;
-                    if (n < SB.C) atomicAdd(dst_t + (long long)n * sN, v[j] * L.scale);
+                for (int j = 0; j < 16; ++j) v[j] *= L.scale;
+                float* dst = dst_t + (long long)(cb0 + cb) * sN;
+                if (sN == 1 && cb0 + cb + 16 <= SB.C && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (cb0 + cb + j < SB.C) atomicAdd(dst + (long long)j * sN, v[j]);
                 }
             }
         }
@@ -569,7 +589,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
     } else {
         if (lane == 0) {
             // both operands MN-major: idesc a_major (bit 15) = b_major (bit 16) = 1
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(L.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
             uint32_t accum = 0;
             for (int ci = 0; ci < nchunks; ++ci) {
                 const int st = ci % kWgStages;
@@ -578,11 +598,11 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                 const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
                 // tap-outer order: 12 consecutive MMAs per accumulator
                 for (int t = 0; t < ntap; ++t) {
-                    const uint32_t shift = 16u * (uint32_t)(L.d[tap0 + t] - dmin);
-                    const uint32_t td = tmem_base + (uint32_t)(t * L.NT);
+                    const uint32_t shift = 16u * (uint32_t)(Gp.d[tap0 + t] - dmin);
+                    const uint32_t td = tmem_base + (uint32_t)(t * NT);
                     for (int ks = 0; ks < kWgRK / 16; ++ks) {
-                        const uint32_t a0 = sa + 256u * ks + (L.swap ? 0u : shift);
-                        const uint32_t b0 = sb + 256u * ks + (L.swap ? shift : 0u);
+                        const uint32_t a0 = sa + 256u * ks + (swap ? 0u : shift);
+                        const uint32_t b0 = sb + 256u * ks + (swap ? shift : 0u);
                         const uint64_t a_hi = umma_desc(a0, 128, planeA), a_lo = umma_desc(a0 + atomsA * planeA, 128, planeA);
                         const uint64_t b_hi = umma_desc(b0, 128, planeB), b_lo = umma_desc(b0 + atomsB * planeB, 128, planeB);
                         umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
@@ -600,50 +620,70 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, L.tmem_cols);
+        tmem_dealloc(tmem_base, Gp.tmem_cols);
     }
 }
 
+static size_t wgrad_stage_bytes(int swap, int NT) {
+    const int rowsA = swap ? kWgRK : kWgRK + kWgSpan, rowsB = swap ? kWgRK + kWgSpan : kWgRK;
+    return 2u * 16 * 16 * rowsA + 2u * (NT / 8) * 16 * rowsB;
+}
+
 static size_t wgrad_smem_bytes(const UmmaWgradLaunch& L) {
-    const int rowsA = L.swap ? kWgRK : kWgRK + kWgSpan, rowsB = L.swap ? kWgRK + kWgSpan : kWgRK;
-    const size_t stage = 2u * 16 * 16 * rowsA + 2u * (L.NT / 8) * 16 * rowsB;
+    size_t stage = 0;
+    for (int g = 0; g < L.ngroups; ++g) stage = max(stage, wgrad_stage_bytes(L.grp[g].swap, L.grp[g].NT));
     return kWgStages * stage + (2 * kWgStages + 1) * 8 + 16;
 }
 
 bool umma_plan_wgrad(UmmaWgradLaunch* L) {
-    const int Cp = L->P.C, Cg = L->G.C;
-    if (Cp % 8 || Cg % 8 || Cp < 16 || Cg < 16 || L->ntaps < 1 || L->ntaps > 16) return false;
-    if (L->P.rstride % 4 || L->G.rstride % 4 || L->P.bstride % 4 || L->G.bstride % 4) return false;
-    if ((reinterpret_cast<uintptr_t>(L->P.base) & 15) || (reinterpret_cast<uintptr_t>(L->G.base) & 15)) return false;
-    int dmin = L->d[0], dmax = L->d[0];
-    for (int t = 1; t < L->ntaps; ++t) { dmin = min(dmin, L->d[t]); dmax = max(dmax, L->d[t]); }
-    if (dmax - dmin > kWgSpan) return false;
-    const int rows = L->m_hi - L->m_lo;
-    if (rows <= 0) return false;
-    L->swap = (Cg > Cp) ? 1 : 0;                       // the wider side fills the 128-row M dimension
-    const int Cm = L->swap ? Cg : Cp, Cn = L->swap ? Cp : Cg;
-    L->n_mtiles = (Cm + 127) / 128;
-    int NT = (Cn + 15) / 16 * 16;
-    L->n_ntiles = 1;
-    while (NT > 128) { L->n_ntiles *= 2; NT = ((Cn + L->n_ntiles - 1) / L->n_ntiles + 15) / 16 * 16; }
-    L->NT = NT;
-    int tpc = 512 / NT;
-    if (tpc > 8) tpc = 8;
-    if (tpc > L->ntaps) tpc = L->ntaps;
-    L->n_tapsets = (L->ntaps + tpc - 1) / tpc;
-    tpc = (L->ntaps + L->n_tapsets - 1) / L->n_tapsets;   // balance
-    L->taps_per_cta = tpc;
-    int tm = 32;
-    while (tm < tpc * NT) tm *= 2;
-    L->tmem_cols = tm;
-    // rows per CTA: aim at ~2 CTAs per SM over the launch, at least 4 chunks each
-    const long long tiles = (long long)L->n_mtiles * L->n_ntiles * L->n_tapsets;
-    long long per = ((long long)rows * L->batch * tiles + 148 * 2 - 1) / (148 * 2);
-    per = (per + kWgRK - 1) / kWgRK * kWgRK;
-    if (per < 4 * kWgRK) per = 4 * kWgRK;
-    if (per > rows) per = (rows + kWgRK - 1) / kWgRK * kWgRK;
-    L->rows_per_cta = (int)per;
-    L->chunks_per_batch = (rows + L->rows_per_cta - 1) / L->rows_per_cta;
+    if (L->ngroups < 1 || L->ngroups > kWgMaxGroups) return false;
+    long long work = 0;        // ~MMA work units of the launch, to size the K ranges
+    for (int gi = 0; gi < L->ngroups; ++gi) {
+        WgGroup& G = L->grp[gi];
+        const int Cp = G.P.C, Cg = G.G.C;
+        if (Cp % 8 || Cg % 8 || Cp < 16 || Cg < 16 || G.ntaps < 1 || G.ntaps > kWgMaxTaps) return false;
+        if (G.P.rstride % 4 || G.G.rstride % 4 || G.P.bstride % 4 || G.G.bstride % 4) return false;
+        if ((reinterpret_cast<uintptr_t>(G.P.base) & 15) || (reinterpret_cast<uintptr_t>(G.G.base) & 15)) return false;
+        int dmin = G.d[0], dmax = G.d[0];
+        for (int t = 1; t < G.ntaps; ++t) { dmin = min(dmin, G.d[t]); dmax = max(dmax, G.d[t]); }
+        if (dmax - dmin > kWgSpan) return false;
+        const int rows = G.m_hi - G.m_lo;
+        if (rows <= 0) return false;
+        G.swap = (Cg > Cp) ? 1 : 0;                       // the wider side fills the 128-row M dimension
+        const int Cm = G.swap ? Cg : Cp, Cn = G.swap ? Cp : Cg;
+        G.n_mtiles = (Cm + 127) / 128;
+        int NT = (Cn + 15) / 16 * 16;
+        G.n_ntiles = 1;
+        while (NT > 128) { G.n_ntiles *= 2; NT = ((Cn + G.n_ntiles - 1) / G.n_ntiles + 15) / 16 * 16; }
+        G.NT = NT;
+        int tpc = 512 / NT;
+        if (tpc > kWgMaxTaps) tpc = kWgMaxTaps;
+        if (tpc > G.ntaps) tpc = G.ntaps;
+        G.n_tapsets = (G.ntaps + tpc - 1) / tpc;
+        tpc = (G.ntaps + G.n_tapsets - 1) / G.n_tapsets;   // balance
+        G.taps_per_cta = tpc;
+        int tm = 32;
+        while (tm < tpc * NT) tm *= 2;
+        G.tmem_cols = tm;
+        G.chunks_per_batch = (rows + kWgRK - 1) / kWgRK;
+        work += (long long)L->batch * G.chunks_per_batch * G.n_tapsets * G.n_mtiles * G.n_ntiles;
+    }
+    // K range per CTA: ~1.25 CTAs per SM over the whole launch, but at least 8 chunks (the dW reduction at the end of a
+    // CTA costs as much as ~10 chunks of MMAs)
+    long long per = (work + 184) / 185;
+    if (per < 8) per = 8;
+    int z = 0, gx = 0, gy = 0;
+    for (int gi = 0; gi < L->ngroups; ++gi) {
+        WgGroup& G = L->grp[gi];
+        const long long total = (long long)L->batch * G.chunks_per_batch;
+        G.chunks_per_cta = (int)min(per, total);
+        G.n_ctas_x = (int)((total + G.chunks_per_cta - 1) / G.chunks_per_cta);
+        G.z0 = z;
+        z += G.n_tapsets;
+        gx = max(gx, G.n_ctas_x);
+        gy = max(gy, G.n_mtiles * G.n_ntiles);
+    }
+    L->grid_x = gx; L->grid_y = gy; L->grid_z = z;
     return wgrad_smem_bytes(*L) <= 200 * 1024;
 }
 
@@ -654,7 +694,7 @@ cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid(L.batch * L.chunks_per_batch, L.n_mtiles * L.n_ntiles, L.n_tapsets);
+    dim3 grid(L.grid_x, L.grid_y, L.grid_z);
     wgrad_umma_kernel<<<grid, 288, wgrad_smem_bytes(L), stream>>>(L);
     return cudaGetLastError();
 }

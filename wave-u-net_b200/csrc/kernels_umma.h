@@ -63,28 +63,43 @@ struct UmmaChoice {         // tiling decisions for one ConvLaunch
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 
-// wgrad on tensor cores: dW[woff_t + cp*w_sp + cg*w_sg] += scale * sum_{b, m in [m_lo,m_hi)} P[b, m+d_t, cp] * G[b, m, cg]
-// GEMM with the ROWS as the reduction dimension: both operands are MN-major (channels contiguous).
-struct UmmaWgradLaunch {
+// wgrad on tensor cores: for every group (one forward class x one input plane)
+//   dW[woff_t + cp*w_sp + cg*w_sg] += scale * sum_{b, m in [m_lo,m_hi)} P[b, m+d_t, cp] * G[b, m, cg]
+// A GEMM with the ROWS as the reduction dimension: both operands are MN-major (channels contiguous).
+constexpr int kWgMaxGroups = 8;
+constexpr int kWgMaxTaps = 8;
+
+struct WgGroup {
     PlaneView P;            // activation side (tap-shifted; may be a MID plane)
     PlaneView G;            // gradient side (pre-activation gradient), rows m
-    int m_lo, m_hi, batch;
+    int m_lo, m_hi;
     int ntaps;
-    int d[16];
-    int woff[16];
-    float* dW;
-    int w_sp, w_sg;         // element strides of dW along the P-channel / G-channel index
-    float scale;
+    int d[kWgMaxTaps];
+    int woff[kWgMaxTaps];
+    // tiling (filled by umma_plan_wgrad)
     int swap;               // 0: A (M side) = P, B (N side) = G;  1: A = G, B = P
     int NT;                 // N-tile width (multiple of 16, <= 128)
     int n_mtiles, n_ntiles; // tiles of 128 / NT channels
     int taps_per_cta, n_tapsets;
-    int rows_per_cta, chunks_per_batch;
+    int chunks_per_batch;   // 64-row chunks per batch element
+    int chunks_per_cta;     // consecutive (batch-folded) chunks one CTA reduces
+    int n_ctas_x;           // ceil(batch*chunks_per_batch / chunks_per_cta)
     int tmem_cols;
+    int z0;                 // first blockIdx.z of this group (one z per tap set)
+};
+
+struct UmmaWgradLaunch {
+    WgGroup grp[kWgMaxGroups];
+    int ngroups;
+    int batch;
+    float* dW;
+    int w_sp, w_sg;         // element strides of dW along the P-channel / G-channel index
+    float scale;
+    int grid_x, grid_y, grid_z;
 };
 
 cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream);
-// fills the tiling fields of L (P, G, taps, dW, strides already set); false = not eligible
+// fills the tiling fields (groups' P, G, taps and the common fields already set); false = not eligible
 bool umma_plan_wgrad(UmmaWgradLaunch* L);
 
 size_t umma_smem_bytes(const UmmaLaunch& L);
