@@ -61,9 +61,22 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int ite
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-            // 12 MMAs per iteration: accumulator changes every run_len MMAs, accumulators acc_stride columns apart
-            #pragma unroll
-            for (int q = 0; q < 12; ++q) mma(tm + (uint32_t)(((q / run_len) % nacc) * acc_stride), ad, bd, idesc, 1);
+            // 12 MMAs per iteration; pattern chosen by run_len (1: ABAB.., 3: AAABBB.., 12: all A then all B next iter)
+            const uint32_t A0 = tm, B0 = tm + (uint32_t)acc_stride * (nacc - 1);
+            if (run_len == 1) {
+                mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1);
+                mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1);
+                mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1);
+            } else if (run_len == 3) {
+                mma(A0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1);
+                mma(B0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1); mma(A0, ad, bd, idesc, 1);
+                mma(A0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1); mma(B0, ad, bd, idesc, 1);
+            } else {
+                const uint32_t X = (i & 1) ? B0 : A0;
+                mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1);
+                mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1);
+                mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1); mma(X, ad, bd, idesc, 1);
+            }
         }
         commit(smem_u32(&bar));
         mbar_wait(smem_u32(&bar), 0);
@@ -156,7 +169,7 @@ int main() {
     printf("== cycles per MMA vs accumulator placement (M=128, K=16, SWIZZLE_NONE, 1 CTA/SM) ==\n");
     for (int N : {96, 48})
         for (int nacc : {1, 2})
-            for (int stride : {N, 128, 256})
+            for (int stride : {N, 64, 128, 256})
                 for (int run : {1, 3, 12}) {
                     if (nacc == 1 && (stride != N || run != 1)) continue;
                     if ((nacc - 1) * stride + N > 512) continue;

@@ -239,6 +239,15 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= timing_iters;
         const double flops = 2.0 * p.B * ((double)Td + n_odd) * p.fs * p.Cin * p.Cout;
         printf("[%s] wgrad time %.1f us (1 launch)  %.1f useful TFLOP/s\n", name, ms * 1e3, flops / (ms * 1e-3) * 1e-12);
+#ifdef WUN_UMMA_TIMING
+        unsigned long long tt[16];
+        CK(cudaMemcpyFromSymbol(tt, g_umma_timing, sizeof(tt)));
+        const double n = (double)tt[0];
+        printf("   per-CTA cycles: mma loop %.0f (wait full %.0f) | conv wait-empty %.0f | epi wait-acc %.0f epi %.0f | chunks/CTA %.1f stages %d (CTAs %.0f)\n",
+               tt[3] / n, tt[4] / n, tt[6] / n, tt[8] / n, tt[9] / n, tt[7] / n, WL.nstages, n / (timing_iters + 1));
+        memset(tt, 0, sizeof(tt));
+        CK(cudaMemcpyToSymbol(g_umma_timing, tt, sizeof(tt)));
+#endif
     }
     cudaFree(dx); cudaFree(dgd); cudaFree(dgo); cudaFree(ddw);
 }

@@ -175,10 +175,10 @@ __device__ unsigned long long g_umma_timing[16];
 #endif
 
 constexpr int kSlabStages = 3;
-constexpr int kBStages = 6;
+constexpr int kBStagesMax = 6;   // weight ring: L.nbs stages of L.TB taps each
 constexpr int kWorkerThreads = 128;
 
-__global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_constant__ UmmaLaunch L) {
+__global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_constant__ UmmaLaunch L) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cls = blockIdx.z % L.ncls, b = blockIdx.z / L.ncls;
@@ -194,21 +194,27 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
     const uint32_t bblk_bytes = 64u * NPAD;                  // [hi|lo][2 atoms][NPAD/8][8][16 B]
     uint8_t* slab0 = smem;
     uint8_t* bring0 = smem + kSlabStages * slab_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bring0 + kBStages * bblk_bytes);
+    const int TB = L.TB, nbs = L.nbs;
+    const uint32_t bstage_bytes = bblk_bytes * TB;
+    // the epilogue re-uses the (then idle) pipeline memory as a 128 x (CW+4) fp32 staging tile: barriers live
+    // behind whichever of the two is larger
+    const uint32_t pipe_bytes = kSlabStages * slab_bytes + nbs * bstage_bytes;
+    const uint32_t epi_bytes = 128u * ((uint32_t)(NPAD < 128 ? NPAD : 128) + 4u) * 4u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((pipe_bytes > epi_bytes ? pipe_bytes : epi_bytes) + 127u) / 128u * 128u);
     // bars: slab_full[3], slab_empty[3], b_full[6], b_empty[6], acc_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int SLAB_FULL = 0, SLAB_EMPTY = kSlabStages, B_FULL = 2 * kSlabStages, B_EMPTY = 2 * kSlabStages + kBStages,
-              ACC_FULL = 2 * kSlabStages + 2 * kBStages;
+    const int SLAB_FULL = 0, SLAB_EMPTY = kSlabStages, B_FULL = 2 * kSlabStages, B_EMPTY = 2 * kSlabStages + kBStagesMax,
+              ACC_FULL = 2 * kSlabStages + 2 * kBStagesMax;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
 
     if (tid == 0) {
         for (int i = 0; i < kSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
-        for (int i = 0; i < kBStages; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        for (int i = 0; i < kBStagesMax; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
         mbar_init(BAR(ACC_FULL), 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -216,14 +222,17 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
     if (tid == 0) { T_ADD(0, 1); T_ADD(2, T_NOW() - t_start); }
 
     // job = (group, 16-channel chunk); K-step = (job, term)
-    if (warp < 4) {
+    if (warp < 8) {
         // ===================== converter: fill slabs =====================
+        // two teams of 4 warps take alternate jobs, so two jobs' global-load latencies are in flight at once
+        const int team = warp >> 2, ttid = tid & 127;
         int ji = 0;
         for (int g = 0; g < K.ngroups; ++g) {
             const UmmaGroup& G = K.groups[g];
             const PlaneView& P = L.planes[G.plane];
             const int nchunk = (P.C + 15) >> 4;
             for (int c = 0; c < nchunk; ++c, ++ji) {
+                if ((ji & 1) != team) continue;
                 const int st = ji % kSlabStages;
                 uint8_t* S = slab0 + st * slab_bytes;
                 const uint32_t atom_stride = 16u * L.rows_alloc;
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                     float x[kRB][16];
 #pragma unroll
                     for (int u = 0; u < kRB; ++u) {
-                        const int rr = rbase + u * kWorkerThreads + tid;
+                        const int rr = rbase + u * kWorkerThreads + ttid;
                         if (rr < L.rows_alloc) load_row16(P, b, m_base + G.dmin + rr, c * 16, x[u]);
                     }
                     if (!waited) {
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                     }
 #pragma unroll
                     for (int u = 0; u < kRB; ++u) {
-                        const int rr = rbase + u * kWorkerThreads + tid;
+                        const int rr = rbase + u * kWorkerThreads + ttid;
                         if (rr >= L.rows_alloc) continue;
                         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -266,7 +275,8 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                 if (tid == 0) T_ADD(7, T_NOW() - t_fill);
             }
         }
-        // ===================== epilogue =====================
+        // ===================== epilogue (team 0: TMEM lane quarter = warp id) =====================
+        if (team == 0) {
         if (tid == 0) { T_WAIT(8, mbar_wait(BAR(ACC_FULL), 0)); }
         else mbar_wait(BAR(ACC_FULL), 0);
         tc_fence_after();
@@ -332,15 +342,16 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is overwritten by the next block
             }
         }
-        tc_fence_before();
         if (tid == 0) T_ADD(9, T_NOW() - t_epi);
-    } else if (warp == 4) {
+        }
+        tc_fence_before();
+    } else if (warp == 8) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t atom_stride = 16u * L.rows_alloc;
             const uint32_t b_lbo = 16u * NPAD;       // between the two K atoms of a weight block
-            int ji = 0, bi = 0;
+            int ji = 0, bi = 0;                      // bi counts weight STAGES (TB taps each)
             const long long t_mma = T_NOW();
             uint32_t first = 0;                      // accumulate flag: 0 for the very first K step
             for (int g = 0; g < K.ngroups; ++g) {
@@ -351,24 +362,28 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
                     T_WAIT(4, mbar_wait(BAR(SLAB_FULL + st), (ji / kSlabStages) & 1));
                     tc_fence_after();
                     const uint32_t sa = smem_u32(slab0 + st * slab_bytes);
-                    for (int t = G.term_begin; t < G.term_end; ++t, ++bi) {
-                        const int bs = bi % kBStages;
-                        T_WAIT(5, mbar_wait(BAR(B_FULL + bs), (bi / kBStages) & 1));
+                    // descriptor bases of this slab stage; a tap shift only adds (rows * 16 B) >> 4 to the address field
+                    const uint64_t a_hi0 = umma_desc(sa, atom_stride, 128), a_lo0 = umma_desc(sa + 2 * atom_stride, atom_stride, 128);
+                    for (int t0 = G.term_begin; t0 < G.term_end; t0 += TB, ++bi) {
+                        const int bs = bi % nbs;
+                        T_WAIT(5, mbar_wait(BAR(B_FULL + bs), (bi / nbs) & 1));
                         tc_fence_after();
-                        const uint32_t sb = smem_u32(bring0 + bs * bblk_bytes);
-                        const uint64_t b_hi = umma_desc(sb, b_lbo, 128);
-                        const uint64_t b_lo = umma_desc(sb + 32u * NPAD, b_lbo, 128);
-                        const uint32_t roff = 16u * (uint32_t)(L.d[t] - G.dmin);
-                        for (int mt = 0; mt < L.MT; ++mt) {
-                            const uint32_t a0 = sa + roff + 16u * 128u * mt;
-                            const uint64_t a_hi = umma_desc(a0, atom_stride, 128);
-                            const uint64_t a_lo = umma_desc(a0 + 2 * atom_stride, atom_stride, 128);
-                            const uint32_t td = tmem_base + (uint32_t)(mt * NPAD);
-                            umma_bf16(td, a_lo, b_hi, idesc, first);
-                            umma_bf16(td, a_hi, b_lo, idesc, 1u);
-                            umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                        const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
+                        const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 32u * NPAD, b_lbo, 128);
+                        const int nt = min(TB, G.term_end - t0);
+                        for (int tt = 0; tt < nt; ++tt) {
+                            const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
+                            const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
+                            const uint64_t aoff = (uint64_t)(uint32_t)(L.d[t0 + tt] - G.dmin);
+                            for (int mt = 0; mt < L.MT; ++mt) {
+                                const uint64_t a_hi = a_hi0 + aoff + (uint64_t)(128u * mt), a_lo = a_lo0 + aoff + (uint64_t)(128u * mt);
+                                const uint32_t td = tmem_base + (uint32_t)(mt * NPAD);
+                                umma_bf16(td, a_lo, b_hi, idesc, first);
+                                umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                                umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                            }
+                            first = 1u;
                         }
-                        first = 1u;
                         umma_commit(BAR(B_EMPTY + bs));       // weight stage free once these MMAs retire
                     }
                     umma_commit(BAR(SLAB_EMPTY + st));        // slab stage free
@@ -383,22 +398,27 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
         if (lane == 0) {
             const uint8_t* src = K.wpack[split];
             int bi = 0;
+            size_t blk = 0;                          // running block (tap) index into the packed stream
             for (int g = 0; g < K.ngroups; ++g) {
                 const UmmaGroup& G = K.groups[g];
                 const int nchunk = (L.planes[G.plane].C + 15) >> 4;
-                const int nblk = nchunk * (G.term_end - G.term_begin);
-                for (int i = 0; i < nblk; ++i, ++bi) {
-                    const int bs = bi % kBStages;
-                    T_WAIT(10, mbar_wait(BAR(B_EMPTY + bs), ((bi / kBStages) & 1) ^ 1));
-                    mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes);
-                    bulk_g2s(smem_u32(bring0 + bs * bblk_bytes), src + (size_t)bi * bblk_bytes, bblk_bytes, BAR(B_FULL + bs));
+                const int nterm = G.term_end - G.term_begin;
+                for (int c = 0; c < nchunk; ++c) {
+                    for (int t0 = 0; t0 < nterm; t0 += TB, ++bi) {
+                        const int nt = min(TB, nterm - t0);
+                        const int bs = bi % nbs;
+                        T_WAIT(10, mbar_wait(BAR(B_EMPTY + bs), ((bi / nbs) & 1) ^ 1));
+                        mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes * nt);
+                        bulk_g2s(smem_u32(bring0 + bs * bstage_bytes), src + blk * bblk_bytes, bblk_bytes * nt, BAR(B_FULL + bs));
+                        blk += nt;
+                    }
                 }
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, L.tmem_cols);
     }
@@ -406,7 +426,9 @@ __global__ void __launch_bounds__(192, 1) plane_conv_umma_kernel(const __grid_co
 }
 
 size_t umma_smem_bytes(const UmmaLaunch& L) {
-    return (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)kBStages * 64u * L.NPAD + (2 * kSlabStages + 2 * kBStages + 1) * 8 + 16;
+    const size_t pipe = (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
+    const size_t epi = 128u * ((size_t)(L.NPAD < 128 ? L.NPAD : 128) + 4u) * 4u;
+    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * kSlabStages + 2 * kBStagesMax + 1) * 8 + 16;
 }
 
 cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
@@ -424,7 +446,7 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     }
     if (max_tiles <= 0) return cudaSuccess;
     dim3 grid(max_tiles, L.nsplit, L.batch * L.ncls);
-    plane_conv_umma_kernel<<<grid, 192, smem, stream>>>(L);
+    plane_conv_umma_kernel<<<grid, 320, smem, stream>>>(L);
     return cudaGetLastError();
 }
 
@@ -436,7 +458,7 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgRK = 64;          // rows per pipeline stage
 constexpr int kWgSpan = 16;        // extra P rows per stage (max tap shift span)
-constexpr int kWgStages = 2;
+constexpr int kWgStagesMax = 3;    // pipeline stages: as many as fit in shared memory (L.nstages)
 
 constexpr int kWgConvThreads = 256;   // 8 converter warps (0-7); warp 8 = TMEM alloc + MMA issue
 
@@ -473,13 +495,14 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
     int dmin = Gp.d[tap0];
     for (int t = 1; t < ntap; ++t) dmin = min(dmin, Gp.d[tap0 + t]);
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+    const int nst = L.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int FULL = 0, EMPTY = kWgStages, ACC = 2 * kWgStages;
+    const int FULL = 0, EMPTY = kWgStagesMax, ACC = 2 * kWgStagesMax;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC + 1);
     if (tid == 0) {
-        for (int i = 0; i < kWgStages; ++i) { mbar_init(BAR(FULL + i), kWgConvThreads); mbar_init(BAR(EMPTY + i), 1); }
+        for (int i = 0; i < kWgStagesMax; ++i) { mbar_init(BAR(FULL + i), kWgConvThreads); mbar_init(BAR(EMPTY + i), 1); }
         mbar_init(BAR(ACC), 1);
         fence_barrier_init();
     }
@@ -497,7 +520,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         const int itemsA = rowsA * gA, items = itemsA + rowsB * gB;
         constexpr int kIB = 4;                                   // items in flight per thread
         for (int ci = 0; ci < nchunks; ++ci) {
-            const int st = ci % kWgStages;
+            const int st = ci % nst;
             uint8_t* S = smem + st * stage_bytes;
             const int gch = g0 + ci;                              // batch-folded chunk index
             const int b = gch / Gp.chunks_per_batch;
@@ -526,7 +549,11 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                         for (int i = 0; i < 16; ++i) x[u][i] = 0.f;
                     }
                 }
-                if (!waited) { mbar_wait(BAR(EMPTY + st), ((ci / kWgStages) & 1) ^ 1); waited = true; }
+                if (!waited) {
+                    if (tid == 0) { T_WAIT(6, mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1)); }
+                    else mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
+                    waited = true;
+                }
 #pragma unroll
                 for (int u = 0; u < kIB; ++u) {
                     const int it = ibase + u * kWgConvThreads + tid;
@@ -558,8 +585,10 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         }
         // ===================== epilogue: accumulators -> reductions into dW =====================
         // TMEM lane quarter = warp % 4; the two warps of a quarter split the taps.
-        mbar_wait(BAR(ACC), 0);
+        if (tid == 0) { T_WAIT(8, mbar_wait(BAR(ACC), 0)); }
+        else mbar_wait(BAR(ACC), 0);
         tc_fence_after();
+        const long long t_epi = T_NOW();
         const int q4 = warp & 3;
         const int m = ca0 + q4 * 32 + lane;                      // M-side channel of this thread
         const bool m_ok = m < SA.C;
@@ -585,15 +614,17 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                 }
             }
         }
+        if (tid == 0) { T_ADD(9, T_NOW() - t_epi); T_ADD(0, 1); T_ADD(7, nchunks); }
         tc_fence_before();
     } else {
         if (lane == 0) {
+            const long long t_mma = T_NOW();
             // both operands MN-major: idesc a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
             uint32_t accum = 0;
             for (int ci = 0; ci < nchunks; ++ci) {
-                const int st = ci % kWgStages;
-                mbar_wait(BAR(FULL + st), (ci / kWgStages) & 1);
+                const int st = ci % nst;
+                T_WAIT(4, mbar_wait(BAR(FULL + st), (ci / nst) & 1));
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
                 // tap-outer order: 12 consecutive MMAs per accumulator
@@ -614,6 +645,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                 umma_commit(BAR(EMPTY + st));
             }
             umma_commit(BAR(ACC));
+            T_ADD(3, T_NOW() - t_mma);
         }
         __syncwarp();
     }
@@ -632,7 +664,7 @@ static size_t wgrad_stage_bytes(int swap, int NT) {
 static size_t wgrad_smem_bytes(const UmmaWgradLaunch& L) {
     size_t stage = 0;
     for (int g = 0; g < L.ngroups; ++g) stage = max(stage, wgrad_stage_bytes(L.grp[g].swap, L.grp[g].NT));
-    return kWgStages * stage + (2 * kWgStages + 1) * 8 + 16;
+    return L.nstages * stage + (2 * kWgStagesMax + 1) * 8 + 16;
 }
 
 bool umma_plan_wgrad(UmmaWgradLaunch* L) {
@@ -668,11 +700,23 @@ bool umma_plan_wgrad(UmmaWgradLaunch* L) {
         G.chunks_per_batch = (rows + kWgRK - 1) / kWgRK;
         work += (long long)L->batch * G.chunks_per_batch * G.n_tapsets * G.n_mtiles * G.n_ntiles;
     }
-    // K range per CTA: ~1.25 CTAs per SM over the whole launch, but at least 8 chunks (the dW reduction at the end of a
-    // CTA costs as much as ~10 chunks of MMAs)
-    long long per = (work + 184) / 185;
-    if (per < 8) per = 8;
+    // K range per CTA: the launch should be ONE full wave (1 CTA per SM, 148 SMs): every CTA runs concurrently and
+    // pays the dW reduction once.  Start from work/148 and grow until the (per-group rounded) CTA count fits.
+    const int kSMs = 148;
+    long long per = (work + kSMs - 1) / kSMs;
+    if (per < 2) per = 2;
     int z = 0, gx = 0, gy = 0;
+    for (int iter = 0; iter < 64; ++iter) {
+        long long ctas = 0;
+        for (int gi = 0; gi < L->ngroups; ++gi) {
+            const WgGroup& G = L->grp[gi];
+            const long long total = (long long)L->batch * G.chunks_per_batch;
+            const long long c = min(per, total);
+            ctas += ((total + c - 1) / c) * G.n_tapsets * G.n_mtiles * G.n_ntiles;
+        }
+        if (ctas <= kSMs) break;
+        per += (per + 15) / 16;
+    }
     for (int gi = 0; gi < L->ngroups; ++gi) {
         WgGroup& G = L->grp[gi];
         const long long total = (long long)L->batch * G.chunks_per_batch;
@@ -684,6 +728,8 @@ bool umma_plan_wgrad(UmmaWgradLaunch* L) {
         gy = max(gy, G.n_mtiles * G.n_ntiles);
     }
     L->grid_x = gx; L->grid_y = gy; L->grid_z = z;
+    L->nstages = kWgStagesMax;
+    while (L->nstages > 2 && wgrad_smem_bytes(*L) > 200 * 1024) --L->nstages;
     return wgrad_smem_bytes(*L) <= 200 * 1024;
 }
 
@@ -786,6 +832,15 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     while (tm < MT * ch->NPAD) tm *= 2;
     ch->tmem_cols = tm;
     ch->pack_bytes = (bytes + 255) / 256 * 256;
+    // weight ring: stages of TB taps (fewer barrier round trips for the single MMA-issuing thread); ~48 KB total
+    const int blk = 64 * ch->NPAD;
+    int TB = 24576 / blk;
+    if (TB > 4) TB = 4;
+    if (TB < 1) TB = 1;
+    int nbs = 49152 / (TB * blk);
+    if (nbs > kBStagesMax) nbs = kBStagesMax;
+    if (nbs < 2) nbs = 2;
+    ch->TB = TB; ch->nbs = nbs;
     return true;
 }
 
@@ -806,7 +861,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     memset(&PL, 0, sizeof(PL));
     for (int p = 0; p < L.nplanes; ++p) U.planes[p] = L.planes[p];
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
-    U.tmem_cols = ch.tmem_cols; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
+    U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
     PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
     int nterm_total = 0;
     for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);

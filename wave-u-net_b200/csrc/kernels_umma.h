@@ -34,6 +34,7 @@ struct UmmaLaunch {
     int MT;                 // 128-row tiles per CTA
     int rows_alloc;         // slab rows per stage  (>= MT*128 + max row-shift span)
     int tmem_cols;          // power of two >= MT*NPAD
+    int TB, nbs;            // weight ring: nbs stages of TB taps
     const float* bias;
     int epilogue;
     int batch;
@@ -59,7 +60,7 @@ struct UmmaPackLaunch {
 };
 
 struct UmmaChoice {         // tiling decisions for one ConvLaunch
-    int NPAD, nsplit, MT, rows_alloc, tmem_cols;
+    int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs;
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 
@@ -96,6 +97,7 @@ struct UmmaWgradLaunch {
     int w_sp, w_sg;         // element strides of dW along the P-channel / G-channel index
     float scale;
     int grid_x, grid_y, grid_z;
+    int nstages;            // shared-memory pipeline stages (2 or 3)
 };
 
 cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream);
