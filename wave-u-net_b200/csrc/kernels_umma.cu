@@ -207,6 +207,11 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
     const int SLAB_FULL = 0, SLAB_EMPTY = kSlabStages, B_FULL = 2 * kSlabStages, B_EMPTY = 2 * kSlabStages + kBStagesMax,
               ACC_FULL = 2 * kSlabStages + 2 * kBStagesMax;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
+    float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // NPAD floats: this split's bias
+    for (int i = tid; i < NPAD; i += blockDim.x) {
+        const int n = split * NPAD + i;
+        bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f;
+    }
 
     if (tid == 0) {
         for (int i = 0; i < kSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
@@ -300,8 +305,7 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
                     if (L.epilogue == EPI_BIAS_LRELU) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int n = n0 + c0 + cb + j;
-                            float y = v[j] + ((L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f);
+                            const float y = v[j] + bias_s[c0 + cb + j];
                             v[j] = fmaxf(0.2f * y, y);
                         }
                     }
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
 size_t umma_smem_bytes(const UmmaLaunch& L) {
     const size_t pipe = (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
     const size_t epi = 128u * ((size_t)(L.NPAD < 128 ? L.NPAD : 128) + 4u) * 4u;
-    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * kSlabStages + 2 * kBStagesMax + 1) * 8 + 16;
+    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * kSlabStages + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD;
 }
 
 cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
@@ -535,8 +539,8 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                     if (it >= items) continue;
                     const bool isA = it < itemsA;
                     const int k = isA ? it : it - itemsA;
-                    const int ng = isA ? gA : gB;
-                    const int rr = k / ng, g = k % ng;
+                    const int nr = isA ? rowsA : rowsB;        // consecutive threads -> consecutive rows (conflict-free st.shared)
+                    const int g = k / nr, rr = k - g * nr;
                     const bool isP = isA != (swap != 0);
                     const PlaneView& V = isA ? SA : SB;
                     const int c0 = (isA ? ca0 : cb0) + g * 16;
@@ -560,8 +564,8 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                     if (it >= items) continue;
                     const bool isA = it < itemsA;
                     const int k = isA ? it : it - itemsA;
-                    const int ng = isA ? gA : gB;
-                    const int rr = k / ng, g = k % ng;
+                    const int nr = isA ? rowsA : rowsB;
+                    const int g = k / nr, rr = k - g * nr;
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -627,15 +631,18 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
                 T_WAIT(4, mbar_wait(BAR(FULL + st), (ci / nst) & 1));
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
-                // tap-outer order: 12 consecutive MMAs per accumulator
+                // tap-outer order: 12 consecutive MMAs per accumulator; descriptors advance by plain adds on the address field
+                const uint64_t a_hi0 = umma_desc(sa, 128, planeA), a_lo0 = umma_desc(sa + atomsA * planeA, 128, planeA);
+                const uint64_t b_hi0 = umma_desc(sb, 128, planeB), b_lo0 = umma_desc(sb + atomsB * planeB, 128, planeB);
                 for (int t = 0; t < ntap; ++t) {
-                    const uint32_t shift = 16u * (uint32_t)(Gp.d[tap0 + t] - dmin);
+                    const uint64_t shift = (uint64_t)(uint32_t)(Gp.d[tap0 + t] - dmin);    // rows == 16-byte units
+                    const uint64_t sha = swap ? 0ull : shift, shb = swap ? shift : 0ull;
                     const uint32_t td = tmem_base + (uint32_t)(t * NT);
+#pragma unroll
                     for (int ks = 0; ks < kWgRK / 16; ++ks) {
-                        const uint32_t a0 = sa + 256u * ks + (swap ? 0u : shift);
-                        const uint32_t b0 = sb + 256u * ks + (swap ? shift : 0u);
-                        const uint64_t a_hi = umma_desc(a0, 128, planeA), a_lo = umma_desc(a0 + atomsA * planeA, 128, planeA);
-                        const uint64_t b_hi = umma_desc(b0, 128, planeB), b_lo = umma_desc(b0 + atomsB * planeB, 128, planeB);
+                        const uint64_t koff = (uint64_t)(16 * ks);           // 16 rows * 16 B >> 4
+                        const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
+                        const uint64_t b_hi = b_hi0 + shb + koff, b_lo = b_lo0 + shb + koff;
                         umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
                         umma_bf16(td, a_hi, b_lo, idesc, 1u);
                         umma_bf16(td, a_hi, b_hi, idesc, 1u);
