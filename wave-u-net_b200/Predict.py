@@ -1,0 +1,29 @@
+"""Prediction entry point (stand-in for /root/reference/Predict.py:1-17):
+
+    python Predict.py with cfg.full_44KHz model_path=checkpoints/123/123-2000.npz input_path=mix.npy [output_path=out]
+
+input_path: a .npy float array [n_frames, n_channels] already at model_config["expected_sr"] (decoding / resampling
+audio files needs librosa + ffmpeg, which the reference uses at Evaluate.py:172 and which are out of scope here).
+Writes <output_path or input_path>_<source>.npy per source (reference writes _<source>.wav, Evaluate.py:193).
+"""
+import sys
+
+import numpy as np
+
+import Config
+import Evaluate
+
+
+def main(cfg, model_path, input_path, output_path=None):
+    model_config = cfg["model_config"]
+    mix = np.load(input_path)
+    preds = Evaluate.produce_source_estimates(model_config, model_path, mix)
+    base = output_path if output_path is not None else input_path
+    for name, audio in preds.items():
+        np.save("%s_%s.npy" % (base, name), audio)
+    return preds
+
+
+if __name__ == "__main__":
+    cfg, extras = Config.parse_command_line(sys.argv[1:])
+    main(cfg, extras.get("model_path"), extras["input_path"], extras.get("output_path"))
