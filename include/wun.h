@@ -144,6 +144,12 @@ int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity);
  * Names: dec<i>, odd<i> (live even / odd rows of down block i), z (bottleneck), up<i>, and g_<name> twins. */
 int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,
                      int64_t* rows, int32_t* channels);
+/* Benchmark hook: (re)pack the weights of conv layer `layer` (0..L-1 down, L bottleneck, L+1..2L up) once and enqueue its
+ * FORWARD kernel `iters` times on `stream`, reading the activations a previous wun_forward_backward left in `workspace`.
+ * *flops_per_launch receives the layer's algorithmic (live-position) FLOPs at this batch.  bench.py times it with CUDA
+ * events for the dominant-kernel roofline. */
+int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, const float* mix, int64_t batch,
+                       void* workspace, int64_t workspace_bytes, void* stream, double* flops_per_launch);
 /* Which kernel family a conv layer uses: "simt" or "umma".  layer: 0..L-1 down, L bottleneck,
  * L+1..2L up.  pass: 0 fwd, 1 dgrad, 2 wgrad. */
 const char* wun_layer_kernel(const WunHandle* h, int layer, int pass);

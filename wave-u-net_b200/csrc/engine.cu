@@ -60,6 +60,7 @@ struct WunHandle {
     size_t arena_bytes = 0;              // scratch for packed bf16 weights (max over launches)
     std::vector<std::string> kernel_used;   // [layer*3 + pass] -> "simt" | "umma" (filled by dry runs)
     int cur_layer = 0, cur_pass = 0;
+    int debug_iters = 0;                 // > 0: wun_debug_run_conv - pack once, enqueue the conv kernel this many times
     // per-call state
     bool dry = false;
     int64_t launches = 0;
@@ -207,6 +208,14 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
         h->launches += 2;                       // weight pack + conv
         if (h->dry) { h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); return WUN_OK; }
         uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total);
+        if (h->debug_iters > 0) {
+            UmmaLaunch U; UmmaPackLaunch PL;
+            cudaError_t e0 = umma_build(L, ch, arena, &U, &PL);
+            if (e0 == cudaSuccess) e0 = launch_umma_pack(PL, h->stream);
+            for (int i = 0; i < h->debug_iters && e0 == cudaSuccess; ++i) e0 = launch_plane_conv_umma(U, h->stream);
+            if (e0 != cudaSuccess) return set_err(WUN_E_CUDA, std::string("debug conv launch: ") + cudaGetErrorString(e0));
+            return WUN_OK;
+        }
         cudaError_t e = umma_run_conv(L, ch, arena, h->stream);
         if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(e));
         return WUN_OK;
@@ -651,6 +660,31 @@ int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
         buf[n] = 0;
     }
     return (int64_t)s.size() + 1;
+}
+
+int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, const float* mix, int64_t batch,
+                       void* workspace, int64_t workspace_bytes, void* stream, double* flops_per_launch) {
+    if (!h || iters < 1) return set_err(WUN_E_INVALID, "bad argument");
+    const int L = h->plan.cfg.num_layers;
+    if (layer < 0 || layer > 2 * L) return set_err(WUN_E_INVALID, "layer out of range");
+    int rc = begin_call(h, params, mix, batch, true, workspace, workspace_bytes, stream, false);
+    if (rc != WUN_OK) return rc;
+    const ConvOp& op = (layer < L) ? h->plan.down[layer] : (layer == L ? h->plan.bottleneck : h->plan.up[layer - L - 1]);
+    if (flops_per_launch) {
+        double f = 0;
+        for (const auto& c : op.classes) {
+            double ks = 0;
+            for (const auto& t : c.terms) ks += op.planes[t.plane].C;
+            f += 2.0 * std::max(0, c.m_hi - c.m_lo) * ks * op.cout;
+        }
+        *flops_per_launch = f * batch;
+    }
+    h->debug_iters = iters;
+    rc = conv_forward(h, op, layer);
+    h->debug_iters = 0;
+    if (rc != WUN_OK) return rc;
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
 }
 
 int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,

@@ -18,7 +18,7 @@ SYMBOLS = [
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
     "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step",
     "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
-    "wun_layer_kernel", "wun_debug_tensor",
+    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv",
 ]
 
 
@@ -72,6 +72,7 @@ def _load():
     lib.wun_describe.argtypes = [H, ctypes.c_char_p, I64]
     lib.wun_describe.restype = I64
     lib.wun_debug_tensor.argtypes = [H, ctypes.c_char_p, I64, ctypes.c_int, P(I64), P(I64), P(ctypes.c_int32)]
+    lib.wun_debug_run_conv.argtypes = [H, ctypes.c_int, ctypes.c_int, VP, VP, I64, VP, I64, VP, P(ctypes.c_double)]
     lib.wun_layer_kernel.argtypes = [H, ctypes.c_int, ctypes.c_int]
     lib.wun_layer_kernel.restype = ctypes.c_char_p
     return lib
@@ -177,6 +178,16 @@ class Engine(object):
         ws = next(iter(self._ws.values()))
         n = int(batch) * rows.value * ch.value
         return ws[off.value:off.value + n].view(int(batch), rows.value, ch.value)
+
+    def run_conv_layer(self, layer, iters, params, mix):
+        """Benchmark hook: enqueue the forward kernel of one conv layer `iters` times (after a training step filled
+        the workspace).  Returns the layer's algorithmic FLOPs per launch."""
+        B = mix.shape[0]
+        ws = self._workspace(B, True, mix.device)
+        fl = ctypes.c_double()
+        check(lib.wun_debug_run_conv(self._h, int(layer), int(iters), params.data_ptr(), mix.data_ptr(), B,
+                                     ws.data_ptr(), ws.numel() * 4, self._stream(), ctypes.byref(fl)))
+        return fl.value
 
     # ---- device calls (torch tensors supply memory and the stream) --------------------------------
     def _workspace(self, batch, training, device):
