@@ -55,7 +55,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -106,7 +106,6 @@ def cpu_step_rate(cfg, seconds_budget, steps=None, warmup=1):
     import numpy as np
     import torch
     from oracle import wave_unet_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     t_in, t_out = O.get_padding(cfg, cfg["num_frames"])
     params = O.init_params(cfg, seed=1337)
     mix, targets = O.synthetic_batch(cfg, 1, t_in, t_out, seed=1)
@@ -118,6 +117,17 @@ def cpu_step_rate(cfg, seconds_budget, steps=None, warmup=1):
         for k in params:
             params[k], m[k], v[k] = O.adam_update(params[k], grads[k], m[k], v[k], step, 1e-4)
 
+    # "all the host threads it can use": one window's convs do not scale past a few dozen threads (oneDNN
+    # oversubscribes badly on 100+ core hosts), so pick the fastest of a few thread counts, then time with that.
+    ncpu = os.cpu_count() or 1
+    best_t, best_n = None, 1
+    for nthr in sorted(set([min(ncpu, c) for c in (8, 16, 32, 64, ncpu)])):
+        torch.set_num_threads(nthr)
+        one(1)
+        t0 = time.perf_counter(); one(1); dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_t, best_n = dt, nthr
+    torch.set_num_threads(best_n)
     for i in range(warmup):
         one(i + 1)
     t0 = time.perf_counter()
@@ -208,15 +218,18 @@ def run_ours(args, rank, world, local_rank):
             else:
                 step_device()
 
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
         for _ in range(args.warmup):
+            run_step()
+        t_spin = time.time()
+        while rank == 0 and len(clocks.lines) < 2 and time.time() - t_spin < 3.0:   # let nvidia-smi come up under load
             run_step()
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -265,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- dominant kernel: the tcgen05 forward conv of the heaviest layer, timed alone with CUDA events --------------
     L = cfg["num_layers"]
-    dom_layer = max(range(1, L), key=lambda i: (i + 1) * i * (t_in >> (i + 1)))      # ~ C_in*C_out*rows
+    dom_layer = 3 if L > 3 else L - 1            # down3: 72->96 channels, 33.9 GFLOP at B=16 - the largest layer (ties down2)
     with torch.cuda.stream(stream):
         dom_flops = eng.run_conv_layer(dom_layer, 3, sep.params, mix_d)             # warm-up
         stream.synchronize()
@@ -321,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
