@@ -61,6 +61,13 @@ struct WunHandle {
     std::vector<std::string> kernel_used;   // [layer*3 + pass] -> "simt" | "umma" (filled by dry runs)
     int cur_layer = 0, cur_pass = 0;
     int debug_iters = 0;                 // > 0: wun_debug_run_conv - pack once, enqueue the conv kernel this many times
+    // weight-gradient kernels run on an internal side stream, concurrently with the dgrad chain on the caller's stream
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> fork_events;
+    cudaEvent_t join_event = nullptr;
+    int fork_used = 0;
+    bool use_side = true;                // WUN_SIDE_STREAM=0 disables
+    cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
     // per-call state
     bool dry = false;
     int64_t launches = 0;
@@ -333,7 +340,7 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
         if (c.m_hi <= c.m_lo) continue;
         PlaneView dpre = make_plane_on(h, c.out, P.grad_twin[c.out.tensor], view_bstride(h, c.out), c.m_lo, c.m_hi);
         ++h->launches;                                         // bias gradient
-        if (!h->dry) launch_colsum(dpre, h->batch, scale, grads + P.params[op.b_param].offset, h->stream);
+        if (!h->dry) launch_colsum(dpre, h->batch, scale, grads + P.params[op.b_param].offset, h->wstream);
         size_t i = 0;
         while (i < c.terms.size()) {
             WgradLaunch W;
@@ -374,15 +381,29 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     if (use_umma) {
         ++h->launches;
         if (!h->dry) {
-            cudaError_t e = launch_wgrad_umma(U, h->stream);
+            cudaError_t e = launch_wgrad_umma(U, h->wstream);
             if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 wgrad launch: ") + cudaGetErrorString(e));
         }
         return WUN_OK;
     }
     for (const auto& W : groups) {
         ++h->launches;
-        if (!h->dry) launch_plane_wgrad_simt(W, h->stream);
+        if (!h->dry) launch_plane_wgrad_simt(W, h->wstream);
     }
+    return WUN_OK;
+}
+
+// fork: everything enqueued on the main stream so far is visible to the side stream
+static int fork_side(WunHandle* h) {
+    if (h->dry || h->wstream == h->stream) return WUN_OK;
+    if (h->fork_used >= (int)h->fork_events.size()) {
+        cudaEvent_t e;
+        WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->fork_events.push_back(e);
+    }
+    cudaEvent_t ev = h->fork_events[h->fork_used++];
+    WUN_CUDA_OK(cudaEventRecord(ev, h->stream));
+    WUN_CUDA_OK(cudaStreamWaitEvent(h->side, ev, 0));
     return WUN_OK;
 }
 
@@ -439,6 +460,15 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     const Plan& P = h->plan;
     const int L = P.cfg.num_layers;
     int rc;
+    h->wstream = h->stream;
+    h->fork_used = 0;
+    if (!h->dry && h->use_side) {
+        if (!h->side) {
+            WUN_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+            WUN_CUDA_OK(cudaEventCreateWithFlags(&h->join_event, cudaEventDisableTiming));
+        }
+        h->wstream = h->side;
+    }
     OutputLaunch O;
     fill_output_launch(h, &O, targets, nullptr, nullptr, 1);
     h->launches += 2;
@@ -448,6 +478,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     }
     for (int i = L - 1; i >= 0; --i) {
         const ConvOp& op = P.up[i];
+        if ((rc = fork_side(h)) != WUN_OK) return rc;
         if ((rc = conv_wgrad(h, op, grads, scale, L + 1 + i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, op, h->bwd_up[i], L + 1 + i)) != WUN_OK) return rc;
         const UpsampleSpec& us = P.ups[i];
@@ -463,11 +494,17 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         ++h->launches;
         if (!h->dry) launch_upsample_bwd(U, h->stream);
     }
+    if ((rc = fork_side(h)) != WUN_OK) return rc;
     if ((rc = conv_wgrad(h, P.bottleneck, grads, scale, L)) != WUN_OK) return rc;
     if ((rc = conv_dgrad(h, P.bottleneck, h->bwd_bottleneck, L)) != WUN_OK) return rc;
     for (int i = L - 1; i >= 0; --i) {
+        if ((rc = fork_side(h)) != WUN_OK) return rc;
         if ((rc = conv_wgrad(h, P.down[i], grads, scale, i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i], i)) != WUN_OK) return rc;
+    }
+    if (!h->dry && h->wstream != h->stream) {       // join: the caller's stream continues only after all wgrads
+        WUN_CUDA_OK(cudaEventRecord(h->join_event, h->side));
+        WUN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->join_event, 0));
     }
     return WUN_OK;
 }
@@ -527,6 +564,7 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     h->umma_enabled = !(dis && dis[0] == '1');
     { const char* names[3] = {"WUN_UMMA_FWD", "WUN_UMMA_DGRAD", "WUN_UMMA_WGRAD"};
       for (int i = 0; i < 3; ++i) { const char* v = getenv(names[i]); h->umma_pass[i] = !(v && v[0] == '0'); } }
+    { const char* v = getenv("WUN_SIDE_STREAM"); h->use_side = !(v && v[0] == '0'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);
@@ -544,7 +582,12 @@ int wun_create(const WunConfig* cfg, int64_t num_frames, WunHandle** out) {
 }
 
 int wun_destroy(WunHandle* h) {
-    if (h) delete h;
+    if (h) {
+        for (auto e : h->fork_events) cudaEventDestroy(e);
+        if (h->join_event) cudaEventDestroy(h->join_event);
+        if (h->side) cudaStreamDestroy(h->side);
+        delete h;
+    }
     return WUN_OK;
 }
 

@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(128) plane_wgrad_kernel(const __grid_constant_
 __global__ void __launch_bounds__(256) plane_wgrad_smallc_kernel(const __grid_constant__ WgradLaunch L) {
     constexpr int RK = 128, XR = RK + 16;
     __shared__ float Xs[XR][4];
-    __shared__ __align__(16) float Gs[RK][64];
+    __shared__ __align__(16) float Gs[RK * 64];
     const int tid = threadIdx.x;
-    const int C = L.plane.C, N = L.N, NQ = (N + 3) / 4;
+    const int C = L.plane.C, N = L.N, NQ = (N + 3) / 4, NP = NQ * 4;
     const int rows = L.m_hi - L.m_lo;
     const int chunks = (rows + L.rows_per_cta - 1) / L.rows_per_cta;
     const int b = blockIdx.x / chunks;
@@ -264,6 +264,11 @@ __global__ void __launch_bounds__(256) plane_wgrad_smallc_kernel(const __grid_co
     for (int i = 1; i < L.nterms; ++i) { dmin = min(dmin, L.d[i]); dmax = max(dmax, L.d[i]); }
     const int span = dmax - dmin;
     const int OG = L.nterms * C * NQ;                // output groups (tap, c, column quad)
+    // when there are few output groups, several thread groups split the rows of a chunk between them
+    const int parts = (OG <= 128) ? 256 / OG : 1;
+    const int og = (OG <= 128) ? tid % OG : tid;
+    const int part = (OG <= 128) ? tid / OG : 0;
+    const bool active = (OG <= 128) ? (part < parts) : true;
     float acc[2][4];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
@@ -275,32 +280,35 @@ __global__ void __launch_bounds__(256) plane_wgrad_smallc_kernel(const __grid_co
             const int c = idx & 3, rr = idx >> 2;
             Xs[rr][c] = (rr < nr + span && c < C) ? plane_load(L.plane, b, mb + dmin + rr, c) : 0.f;
         }
-        for (int idx = tid; idx < RK * 64; idx += 256) {
-            const int n = idx & 63, rr = idx >> 6;
-            Gs[rr][n] = (rr < nr && n < N) ? plane_load(L.dpre, b, mb + rr, n) : 0.f;
+        for (int idx = tid; idx < RK * NP; idx += 256) {
+            const int n = idx % NP, rr = idx / NP;
+            Gs[idx] = (rr < nr && n < N) ? plane_load(L.dpre, b, mb + rr, n) : 0.f;
         }
         __syncthreads();
+        if (active) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int og = tid + u * 256;
-            if (og < OG) {
-                const int nq = og % NQ, tc = og / NQ;
-                const int c = tc % C, doff = L.d[tc / C] - dmin;
-                for (int r = 0; r < RK; ++r) {
-                    const float x = Xs[r + doff][c];
-                    const float4 g = *reinterpret_cast<const float4*>(&Gs[r][nq * 4]);
-                    acc[u][0] = fmaf(x, g.x, acc[u][0]); acc[u][1] = fmaf(x, g.y, acc[u][1]);
-                    acc[u][2] = fmaf(x, g.z, acc[u][2]); acc[u][3] = fmaf(x, g.w, acc[u][3]);
+            for (int u = 0; u < 2; ++u) {
+                const int o = og + u * 256;
+                if (o < OG && (u == 0 || OG > 128)) {
+                    const int nq = o % NQ, tc = o / NQ;
+                    const int c = tc % C, doff = L.d[tc / C] - dmin;
+                    for (int r = part; r < RK; r += parts) {
+                        const float x = Xs[r + doff][c];
+                        const float4 g = *reinterpret_cast<const float4*>(&Gs[r * NP + nq * 4]);
+                        acc[u][0] = fmaf(x, g.x, acc[u][0]); acc[u][1] = fmaf(x, g.y, acc[u][1]);
+                        acc[u][2] = fmaf(x, g.z, acc[u][2]); acc[u][3] = fmaf(x, g.w, acc[u][3]);
+                    }
                 }
             }
         }
         __syncthreads();
     }
+    if (!active) return;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-        const int og = tid + u * 256;
-        if (og >= OG) continue;
-        const int nq = og % NQ, tc = og / NQ;
+        const int o = og + u * 256;
+        if (o >= OG || (u == 1 && OG <= 128)) continue;
+        const int nq = o % NQ, tc = o / NQ;
         const int c = tc % C, t = tc / C;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

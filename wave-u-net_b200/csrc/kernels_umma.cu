@@ -839,12 +839,18 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     while (tm < MT * ch->NPAD) tm *= 2;
     ch->tmem_cols = tm;
     ch->pack_bytes = (bytes + 255) / 256 * 256;
-    // weight ring: stages of TB taps (fewer barrier round trips for the single MMA-issuing thread); ~48 KB total
+    // weight ring: stages of TB taps (fewer barrier round trips for the single MMA-issuing thread).  Launches that
+    // fill the GPU keep it at ~48 KB so two CTAs fit per SM; launches with fewer CTAs than SMs (the deep layers) are
+    // weight-stream-latency bound, so they get a deep ring instead.
+    long long n_ctas = 0;
+    for (int q = 0; q < L.ncls; ++q)
+        n_ctas += (long long)((L.cls[q].m_hi - L.cls[q].m_lo + MT * 128 - 1) / (MT * 128)) * ch->nsplit * L.batch;
+    const bool sparse = n_ctas <= 148;
     const int blk = 64 * ch->NPAD;
-    int TB = 24576 / blk;
+    int TB = (sparse ? 36864 : 24576) / blk;
     if (TB > 4) TB = 4;
     if (TB < 1) TB = 1;
-    int nbs = 49152 / (TB * blk);
+    int nbs = (sparse ? 147456 : 49152) / (TB * blk);
     if (nbs > kBStagesMax) nbs = kBStagesMax;
     if (nbs < 2) nbs = 2;
     ch->TB = TB; ch->nbs = nbs;
