@@ -64,9 +64,9 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,7 +75,10 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.06)]
+        if not inside:                       # timed region shorter than one sample: take the samples closest to it
+            inside = [ln for (ts, ln) in self.lines[-2:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -178,6 +181,9 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()                       # samples are time-stamped; only those inside the timed region are reported
     cfg = Config.build_config([PRESET], experiment_id=0)["model_config"]
     B = BATCH_PER_GPU
     t_in, t_out, mix_np, tg_np = build_problem(cfg, B, seed=1337 + rank)
@@ -218,27 +224,23 @@ def run_ours(args, rank, world, local_rank):
             else:
                 step_device()
 
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
         for _ in range(args.warmup):
-            run_step()
-        t_spin = time.time()
-        while rank == 0 and len(clocks.lines) < 2 and time.time() - t_spin < 3.0:   # let nvidia-smi come up under load
             run_step()
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.perf_counter()
         e0.record(stream)
         for _ in range(args.steps):
             run_step()
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
+        t_end = time.perf_counter()
         ms_total = e0.elapsed_time(e1)
-        clk = clocks.stop() if rank == 0 else None
+        clk = clocks.stop(t_begin, t_end) if rank == 0 else None
         if world > 1:
             t = torch.tensor([ms_total], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
