@@ -124,7 +124,7 @@ def cpu_step_rate(cfg, seconds_budget, steps=None, warmup=1):
     # oversubscribes badly on 100+ core hosts), so pick the fastest of a few thread counts, then time with that.
     ncpu = os.cpu_count() or 1
     best_t, best_n = None, 1
-    for nthr in sorted(set([min(ncpu, c) for c in (8, 16, 32, 64, ncpu)])):
+    for nthr in sorted(set([min(ncpu, c) for c in (8, 16, 32)])):     # >32 threads only loses (measured: 128 threads = 100x slower)
         torch.set_num_threads(nthr)
         one(1)
         t0 = time.perf_counter(); one(1); dt = time.perf_counter() - t0

@@ -19,6 +19,8 @@ sep._ensure_params(eng, torch.device("cuda"), create=True)
 mix_d, tg_d = torch.from_numpy(mix).cuda(), torch.from_numpy(tg).cuda()
 sep.loss_and_gradients(mix_d, tg_d)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()          # ncu --profile-from-start off: only the launches below are profiled
 fl = eng.run_conv_layer(layer, iters, sep.params, mix_d)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("layer", layer, "GFLOP/launch", fl * 1e-9)
