@@ -76,7 +76,12 @@ static double run_case(const char* name, Problem p, bool check, int timing_iters
         ch.MT = p.MT; ch.rows_alloc = p.MT * 128 + span;
         int tm = 32; while (tm < ch.MT * ch.NPAD) tm *= 2;
         ch.tmem_cols = tm;
+        if (ch.persistent) {
+            if (2 * ch.MT * ch.NPAD > 512) ch.persistent = 0;
+            else { tm = 32; while (tm < 2 * ch.MT * ch.NPAD) tm *= 2; ch.tmem_cols = tm; }
+        }
     }
+    printf("[%s] persistent=%d TB=%d nbs=%d\n", name, ch.persistent, ch.TB, ch.nbs);
     const int NPAD = ch.NPAD;
     uint8_t* arena;
     CK(cudaMalloc(&arena, ch.pack_bytes));
@@ -265,7 +270,7 @@ int main(int argc, char** argv) {
     run_case("tiny",       { 1, 300,   16, 16,  3, 1, 1,   40, 101}, true, 0);
     run_case("taps15",     { 2, 1500,  32, 48, 15, 1, 1,  200, 401}, true, 0);
     run_case("cin24_mt2",  { 2, 1500,  24, 48, 15, 2, 1,  200, 401}, true, 0);
-    run_case("c72_n96_mt3",{ 2, 3000,  72, 96, 15, 3, 1,  500, 801}, true, 0);
+    run_case("c72_n96",    { 2, 3000,  72, 96, 15, 0, 1,  500, 801}, true, 0);
     run_case("n72pad_mt2", { 2, 1000,  48, 72, 15, 2, 1,  100, 301}, true, 0);
     run_case("nsplit",     { 2, 300,   64, 288, 15, 1, 2,  50, 101}, true, 0);
     run_wgrad("wg_tiny",   { 1, 300,   16, 16,  3, 1, 1,   40, 101}, true, 0);
@@ -284,17 +289,11 @@ int main(int argc, char** argv) {
         run_case("down3_only", {16, 18419, 72, 96, 15, mt, 1, 8174, 2057}, false, 3);
         return 0;
     }
-    run_case("down3_mt1",  {16, 18419, 72, 96, 15, 1, 1, 8174, 2057}, false, 20);
-    run_case("down5_mt1",  {16, 4595, 120, 144, 15, 1, 1, 2030, 521}, false, 20);
     // M4 layers at B=16 (T = input rows of the layer)
-    run_case("down1",      {16, 73715, 24, 48, 15, 4, 1, 32750, 8201}, true, 20);
-    run_case("down2_mt2",  {16, 36851, 48, 72, 15, 2, 1, 16366, 4105}, false, 20);
-    run_case("down2_mt4",  {16, 36851, 48, 72, 15, 4, 1, 16366, 4105}, false, 20);
-    run_case("down3_mt2",  {16, 18419, 72, 96, 15, 2, 1, 8174, 2057}, false, 20);
-    run_case("down3_mt4",  {16, 18419, 72, 96, 15, 4, 1, 8174, 2057}, false, 20);
-    run_case("down4_mt2",  {16, 9203,  96, 120, 15, 2, 1, 4078, 1033}, false, 20);
-    run_case("down4_mt4",  {16, 9203,  96, 120, 15, 4, 1, 4078, 1033}, false, 20);
-    run_case("down5_mt3",  {16, 4595, 120, 144, 15, 3, 1, 2030, 521}, false, 20);
-    run_case("down7_mt2",  {16, 1139, 168, 192, 15, 2, 1, 494, 137}, false, 20);
+    run_case("down1",      {16, 73715, 24, 48, 15, 0, 1, 32750, 8201}, true, 20);
+    run_case("down2_mt2",  {16, 36851, 48, 72, 15, 0, 1, 16366, 4105}, false, 20);
+    run_case("down3_mt2",  {16, 18419, 72, 96, 15, 0, 1, 8174, 2057}, false, 20);
+    run_case("down4_mt2",  {16, 9203,  96, 120, 15, 0, 1, 4078, 1033}, false, 20);
+    run_case("down7_mt2",  {16, 1139, 168, 192, 15, 0, 1, 494, 137}, false, 20);
     return 0;
 }

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels_umma.h"
@@ -178,7 +179,12 @@ constexpr int kSlabStages = 3;
 constexpr int kBStagesMax = 6;   // weight ring: L.nbs stages of L.TB taps each
 constexpr int kWorkerThreads = 128;
 
-__global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_constant__ UmmaLaunch L) {
+// NTEAMS converter teams (4 warps each) take jobs round-robin: 2 teams / 3 slab stages when two CTAs share an SM (dense
+// launches), 4 teams / 6 stages for the sparse deep-layer launches whose K loop is converter-latency bound.
+template <int NTEAMS>
+__global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plane_conv_umma_kernel(const __grid_constant__ UmmaLaunch L) {
+    constexpr int kSlabStages = (NTEAMS == 2) ? 3 : 6;
+    constexpr int kMmaWarp = NTEAMS * 4, kSlabMax = 6;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cls = blockIdx.z % L.ncls, b = blockIdx.z / L.ncls;
@@ -204,8 +210,8 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
     // bars: slab_full[3], slab_empty[3], b_full[6], b_empty[6], acc_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int SLAB_FULL = 0, SLAB_EMPTY = kSlabStages, B_FULL = 2 * kSlabStages, B_EMPTY = 2 * kSlabStages + kBStagesMax,
-              ACC_FULL = 2 * kSlabStages + 2 * kBStagesMax;
+    const int SLAB_FULL = 0, SLAB_EMPTY = kSlabMax, B_FULL = 2 * kSlabMax, B_EMPTY = 2 * kSlabMax + kBStagesMax,
+              ACC_FULL = 2 * kSlabMax + 2 * kBStagesMax;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
     float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // NPAD floats: this split's bias
     for (int i = tid; i < NPAD; i += blockDim.x) {
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
         mbar_init(BAR(ACC_FULL), 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
     if (tid == 0) { T_ADD(0, 1); T_ADD(2, T_NOW() - t_start); }
 
     // job = (group, 16-channel chunk); K-step = (job, term)
-    if (warp < 8) {
+    if (warp < kMmaWarp) {
         // ===================== converter: fill slabs =====================
         // two teams of 4 warps take alternate jobs, so two jobs' global-load latencies are in flight at once
         const int team = warp >> 2, ttid = tid & 127;
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
             const PlaneView& P = L.planes[G.plane];
             const int nchunk = (P.C + 15) >> 4;
             for (int c = 0; c < nchunk; ++c, ++ji) {
-                if ((ji & 1) != team) continue;
+                if ((ji % NTEAMS) != team) continue;
                 const int st = ji % kSlabStages;
                 uint8_t* S = slab0 + st * slab_bytes;
                 const uint32_t atom_stride = 16u * L.rows_alloc;
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
         if (tid == 0) T_ADD(9, T_NOW() - t_epi);
         }
         tc_fence_before();
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
@@ -422,35 +428,327 @@ __global__ void __launch_bounds__(320, 2) plane_conv_umma_kernel(const __grid_co
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, L.tmem_cols);
     }
     if (tid == 0) T_ADD(1, T_NOW() - t_start);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant for launches with many row tiles (the big layers): ONE CTA per SM loops over tiles,
+// the TMEM accumulator is double-buffered and a dedicated epilogue warp group drains tile k while the MMA
+// warp already issues tile k+1 - so the tensor pipe of an SM is fed by a single, never-interrupted issuer
+// (measured floor 56 cycles/MMA at N=96 vs ~70 with two interleaving CTAs) and there is no per-tile
+// prologue / TMEM allocation / wave tail.
+// Warps: 0-7 converters (two teams), 8 MMA issue + TMEM alloc, 9 weight loader, 10-13 epilogue.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPersThreads = 448;
+
+struct TileCoord { int cls, b, split, m_base; };
+
+__device__ __forceinline__ TileCoord decode_tile(const UmmaLaunch& L, int t) {
+    TileCoord tc;
+    tc.split = t % L.nsplit;
+    t /= L.nsplit;
+    const int rows_tile = L.MT * 128;
+    int q = 0;
+    for (; q < L.ncls - 1; ++q) {
+        const int nt = (L.cls[q].out.m_hi - L.cls[q].out.m_lo + rows_tile - 1) / rows_tile * L.batch;
+        if (t < nt) break;
+        t -= nt;
+    }
+    const int tiles_q = (L.cls[q].out.m_hi - L.cls[q].out.m_lo + rows_tile - 1) / rows_tile;
+    tc.cls = q;
+    tc.b = t / tiles_q;
+    tc.m_base = L.cls[q].out.m_lo + (t % tiles_q) * rows_tile;
+    return tc;
+}
+
+__global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NPAD = L.NPAD;
+    const uint32_t slab_bytes = 64u * L.rows_alloc;
+    const uint32_t bblk_bytes = 64u * NPAD;
+    const int TB = L.TB, nbs = L.nbs;
+    const uint32_t bstage_bytes = bblk_bytes * TB;
+    const int CW = (NPAD < 128) ? NPAD : 128;
+    const int SW = CW + 4;
+    uint8_t* slab0 = smem;
+    uint8_t* bring0 = smem + kSlabStages * slab_bytes;
+    float* stage = reinterpret_cast<float*>(bring0 + nbs * bstage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + (size_t)128 * SW * 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int SLAB_FULL = 0, SLAB_EMPTY = kSlabStages, B_FULL = 2 * kSlabStages, B_EMPTY = 2 * kSlabStages + kBStagesMax,
+              ACC_FULL = 2 * kSlabStages + 2 * kBStagesMax, ACC_EMPTY = ACC_FULL + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_EMPTY + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // nsplit * NPAD floats
+    for (int i = tid; i < NPAD * L.nsplit; i += blockDim.x) bias_s[i] = (L.bias && i < L.N) ? __ldg(L.bias + i) : 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < kSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
+        for (int i = 0; i < kBStagesMax; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t acc_cols = (uint32_t)(L.MT * NPAD);               // columns of one accumulator buffer
+
+    if (warp < 8) {
+        // ===================== converters =====================
+        const int team = warp >> 2, ttid = tid & 127;
+        int jg = 0;                                                   // job counter across tiles
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(L, t);
+            const UmmaClass& K = L.cls[tc.cls];
+            for (int g = 0; g < K.ngroups; ++g) {
+                const UmmaGroup& G = K.groups[g];
+                const PlaneView& P = L.planes[G.plane];
+                const int nchunk = (P.C + 15) >> 4;
+                for (int c = 0; c < nchunk; ++c, ++jg) {
+                    if ((jg & 1) != team) continue;
+                    const int st = jg % kSlabStages;
+                    uint8_t* S = slab0 + st * slab_bytes;
+                    const uint32_t atom_stride = 16u * L.rows_alloc;
+                    constexpr int kRB = 3;
+                    bool waited = false;
+                    for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
+                        float x[kRB][16];
+#pragma unroll
+                        for (int u = 0; u < kRB; ++u) {
+                            const int rr = rbase + u * kWorkerThreads + ttid;
+                            if (rr < L.rows_alloc) load_row16(P, tc.b, tc.m_base + G.dmin + rr, c * 16, x[u]);
+                        }
+                        if (!waited) { mbar_wait(BAR(SLAB_EMPTY + st), ((jg / kSlabStages) & 1) ^ 1); waited = true; }
+#pragma unroll
+                        for (int u = 0; u < kRB; ++u) {
+                            const int rr = rbase + u * kWorkerThreads + ttid;
+                            if (rr >= L.rows_alloc) continue;
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(x[u][2 * i]), h1 = __float2bfloat16_rn(x[u][2 * i + 1]);
+                                hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                lo[i] = pack_bf16x2(x[u][2 * i] - __bfloat162float(h0), x[u][2 * i + 1] - __bfloat162float(h1));
+                            }
+                            *reinterpret_cast<uint4*>(S + 16u * rr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(S + atom_stride + 16u * rr) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                            *reinterpret_cast<uint4*>(S + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            *reinterpret_cast<uint4*>(S + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(BAR(SLAB_FULL + st));
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t atom_stride = 16u * L.rows_alloc;
+            const uint32_t b_lbo = 16u * NPAD;
+            int jg = 0, bg = 0, k = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+                const TileCoord tc = decode_tile(L, t);
+                const UmmaClass& K = L.cls[tc.cls];
+                const int buf = k & 1;
+                mbar_wait(BAR(ACC_EMPTY + buf), ((k >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                uint32_t first = 0;
+                for (int g = 0; g < K.ngroups; ++g) {
+                    const UmmaGroup& G = K.groups[g];
+                    const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                    for (int c = 0; c < nchunk; ++c, ++jg) {
+                        const int st = jg % kSlabStages;
+                        mbar_wait(BAR(SLAB_FULL + st), (jg / kSlabStages) & 1);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(slab0 + st * slab_bytes);
+                        const uint64_t a_hi0 = umma_desc(sa, atom_stride, 128), a_lo0 = umma_desc(sa + 2 * atom_stride, atom_stride, 128);
+                        for (int t0 = G.term_begin; t0 < G.term_end; t0 += TB, ++bg) {
+                            const int bs = bg % nbs;
+                            mbar_wait(BAR(B_FULL + bs), (bg / nbs) & 1);
+                            tc_fence_after();
+                            const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
+                            const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 32u * NPAD, b_lbo, 128);
+                            const int nt = min(TB, G.term_end - t0);
+                            for (int tt = 0; tt < nt; ++tt) {
+                                const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
+                                const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
+                                const uint64_t aoff = (uint64_t)(uint32_t)(L.d[t0 + tt] - G.dmin);
+                                for (int mt = 0; mt < L.MT; ++mt) {
+                                    const uint64_t a_hi = a_hi0 + aoff + (uint64_t)(128u * mt), a_lo = a_lo0 + aoff + (uint64_t)(128u * mt);
+                                    const uint32_t td = tmem_base + buf * acc_cols + (uint32_t)(mt * NPAD);
+                                    umma_bf16(td, a_lo, b_hi, idesc, first);
+                                    umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                                    umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                                }
+                                first = 1u;
+                            }
+                            umma_commit(BAR(B_EMPTY + bs));
+                        }
+                        umma_commit(BAR(SLAB_EMPTY + st));
+                    }
+                }
+                umma_commit(BAR(ACC_FULL + buf));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===================== weight loader =====================
+        if (lane == 0) {
+            int bg = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(L, t);
+                const UmmaClass& K = L.cls[tc.cls];
+                const uint8_t* src = K.wpack[tc.split];
+                size_t blk = 0;
+                for (int g = 0; g < K.ngroups; ++g) {
+                    const UmmaGroup& G = K.groups[g];
+                    const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                    const int nterm = G.term_end - G.term_begin;
+                    for (int c = 0; c < nchunk; ++c)
+                        for (int t0 = 0; t0 < nterm; t0 += TB, ++bg) {
+                            const int nt = min(TB, nterm - t0);
+                            const int bs = bg % nbs;
+                            mbar_wait(BAR(B_EMPTY + bs), ((bg / nbs) & 1) ^ 1);
+                            mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes * nt);
+                            bulk_g2s(smem_u32(bring0 + bs * bstage_bytes), src + blk * bblk_bytes, bblk_bytes * nt, BAR(B_FULL + bs));
+                            blk += nt;
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps (10-13): TMEM lane quarter = warp & 3 =====================
+        const int q4 = warp & 3, ew = warp - 10;
+        int k = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+            const TileCoord tc = decode_tile(L, t);
+            const UmmaClass& K = L.cls[tc.cls];
+            const int buf = k & 1;
+            const int n0 = tc.split * NPAD;
+            mbar_wait(BAR(ACC_FULL + buf), (k >> 1) & 1);
+            tc_fence_after();
+            const int c0_last = min((NPAD - 1) / CW, (L.N - n0 - 1) / CW) * CW;      // last column block that holds real channels
+            for (int mt = 0; mt < L.MT; ++mt) {
+                for (int c0 = 0; c0 < NPAD; c0 += CW) {
+                    const bool last_block = (mt == L.MT - 1) && (c0 == c0_last);
+                    if (n0 + c0 < L.N) {
+                        const int cw = min(CW, NPAD - c0);
+                        for (int cb = 0; cb < cw; cb += 16) {
+                            __syncwarp();
+                            float v[16];
+                            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)(mt * NPAD + c0 + cb), v);
+                            if (L.epilogue == EPI_BIAS_LRELU) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const float y = v[j] + bias_s[n0 + c0 + cb + j];
+                                    v[j] = fmaxf(0.2f * y, y);
+                                }
+                            }
+                            float4* dst = reinterpret_cast<float4*>(stage + (size_t)(q4 * 32 + lane) * SW + cb);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    }
+                    if (last_block) {                       // every tcgen05.ld of this buffer has completed: hand it back
+                        tc_fence_before();
+                        mbar_arrive(BAR(ACC_EMPTY + buf));
+                    }
+                    if (n0 + c0 < L.N) {
+                        const int cw = min(CW, NPAD - c0);
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        const int ncols = min(cw, L.N - (n0 + c0));
+                        for (int r = ew; r < 128; r += 4) {
+                            const int m = tc.m_base + mt * 128 + r;
+                            if (m >= K.out.m_hi) break;
+                            const long long roff = (long long)tc.b * K.out.bstride + (long long)m * K.out.rstride + n0 + c0;
+                            const bool accum = (m >= K.out.acc_lo && m < K.out.acc_hi);
+                            float* dst = K.out.base + roff;
+                            const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (ncols % 4 == 0);
+                            if (vec) {
+                                for (int q = lane; q < ncols / 4; q += 32) {
+                                    float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
+                                    if (L.epilogue == EPI_SLOPE && K.out.saved) {
+                                        const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
+                                        o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
+                                        o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
+                                    }
+                                    if (accum) { const float4 old = reinterpret_cast<float4*>(dst)[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                                    reinterpret_cast<float4*>(dst)[q] = o;
+                                }
+                            } else {
+                                for (int j = lane; j < ncols; j += 32) {
+                                    float o = stage[(size_t)r * SW + j];
+                                    if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
+                                    if (accum) o += dst[j];
+                                    dst[j] = o;
+                                }
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L.tmem_cols);
+    }
+}
+
+static size_t umma_pers_smem_bytes(const UmmaLaunch& L) {
+    const size_t CW = (L.NPAD < 128) ? L.NPAD : 128;
+    return (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD + 128u * (CW + 4) * 4 +
+           (2 * kSlabStages + 2 * kBStagesMax + 4) * 8 + 32 + 4 * (size_t)L.NPAD * L.nsplit;
+}
+
 size_t umma_smem_bytes(const UmmaLaunch& L) {
-    const size_t pipe = (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
+    const size_t nslab = (L.nteams == 4) ? 6 : 3;
+    const size_t pipe = nslab * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
     const size_t epi = 128u * ((size_t)(L.NPAD < 128 ? L.NPAD : 128) + 4u) * 4u;
-    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * kSlabStages + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD;
+    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * 6 + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD;
 }
 
 cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
-    const size_t smem = umma_smem_bytes(L);
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(plane_conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(plane_conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(plane_conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(plane_conv_umma_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int max_tiles = 0;
+    int max_tiles = 0, total = 0;
     for (int q = 0; q < L.ncls; ++q) {
         const int rows = L.cls[q].out.m_hi - L.cls[q].out.m_lo;
-        max_tiles = max(max_tiles, (rows + L.MT * 128 - 1) / (L.MT * 128));
+        const int tq = (rows + L.MT * 128 - 1) / (L.MT * 128);
+        max_tiles = max(max_tiles, tq);
+        total += tq * L.batch;
     }
+    total *= L.nsplit;
     if (max_tiles <= 0) return cudaSuccess;
+    if (L.persistent) {
+        const int grid = total < 148 ? total : 148;
+        plane_conv_umma_persistent<<<grid, kPersThreads, umma_pers_smem_bytes(L), stream>>>(L, total);
+        return cudaGetLastError();
+    }
+    const size_t smem = umma_smem_bytes(L);
     dim3 grid(max_tiles, L.nsplit, L.batch * L.ncls);
-    plane_conv_umma_kernel<<<grid, 320, smem, stream>>>(L);
+    if (L.nteams == 4) plane_conv_umma_kernel<4><<<grid, 4 * 128 + 64, smem, stream>>>(L);
+    else plane_conv_umma_kernel<2><<<grid, 2 * 128 + 64, smem, stream>>>(L);
     return cudaGetLastError();
 }
 
@@ -809,7 +1107,16 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     const int npad_total = (L.N + 15) / 16 * 16;
     if (npad_total > 512) return false;
     ch->nsplit = (npad_total <= 256) ? 1 : 2;
-    ch->NPAD = (ch->nsplit == 1) ? npad_total : (((L.N + 1) / 2 + 15) / 16 * 16);
+    {   // deep layers have fewer row tiles than there are SMs: split the output channels over more CTAs (each CTA then
+        // runs cheaper MMAs; the K loop of a tile is the critical path of these latency-bound launches)
+        long long tiles128 = 0;
+        for (int q = 0; q < L.ncls; ++q) tiles128 += (long long)((L.cls[q].m_hi - L.cls[q].m_lo + 127) / 128) * L.batch;
+        const char* env = getenv("WUN_NSPLIT_MAX");
+        const int smax = env ? atoi(env) : 2;        // measured: 2 helps (10.72 -> 10.56 ms/step), 4 hurts
+        while (ch->nsplit * 2 <= smax && tiles128 * ch->nsplit * 2 <= 148 && (L.N + ch->nsplit * 2 - 1) / (ch->nsplit * 2) >= 48)
+            ch->nsplit *= 2;
+    }
+    ch->NPAD = (ch->nsplit == 1) ? npad_total : (((L.N + ch->nsplit - 1) / ch->nsplit + 15) / 16 * 16);
     int maxspan = 0, max_rows = 0;
     size_t bytes = 0;
     for (int q = 0; q < L.ncls; ++q) {
@@ -854,6 +1161,33 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     if (nbs > kBStagesMax) nbs = kBStagesMax;
     if (nbs < 2) nbs = 2;
     ch->TB = TB; ch->nbs = nbs;
+    {
+        const char* env = getenv("WUN_TEAMS");
+        ch->nteams = (sparse && !(env && env[0] == '2')) ? 4 : 2;
+        if (ch->nteams == 4) {      // 6 slab stages: keep the ring within what is left of ~200 KB
+            const long long left = 200 * 1024 - 6LL * 64 * ch->rows_alloc - 4096;
+            while (ch->nbs > 2 && (long long)ch->nbs * TB * blk > left) --ch->nbs;
+            if ((long long)ch->nbs * TB * blk > left) ch->nteams = 2;
+        }
+    }
+    // persistent one-CTA-per-SM kernel for launches with at least ~3 tiles per SM whose double-buffered accumulators fit TMEM
+    ch->persistent = 0;
+    {
+        // WUN_PERSISTENT: 0 = never, 1 (default) = forward launches with NPAD <= 80 (measured win: down1 +28 %, down2 +12 %,
+        // down3 -4 %), 2 = every eligible launch incl. dgrad
+        const char* env = getenv("WUN_PERSISTENT");
+        const int mode = env ? atoi(env) : 1;
+        const bool allow = (mode == 2) || (mode == 1 && L.epilogue == EPI_BIAS_LRELU && ch->NPAD <= 80);
+        if (allow && n_ctas >= 3 * 148 && 2 * MT * ch->NPAD <= 512) {
+            ch->persistent = 1;
+            ch->nbs = 98304 / (TB * blk);          // one CTA per SM: a deeper weight ring fits
+            if (ch->nbs > kBStagesMax) ch->nbs = kBStagesMax;
+            if (ch->nbs < 2) ch->nbs = 2;
+            int tm2 = 32;
+            while (tm2 < 2 * MT * ch->NPAD) tm2 *= 2;
+            ch->tmem_cols = tm2;
+        }
+    }
     return true;
 }
 
@@ -874,7 +1208,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     memset(&PL, 0, sizeof(PL));
     for (int p = 0; p < L.nplanes; ++p) U.planes[p] = L.planes[p];
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
-    U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
+    U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
     PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
     int nterm_total = 0;
     for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);

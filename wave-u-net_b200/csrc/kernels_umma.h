@@ -8,7 +8,7 @@
 namespace wun {
 
 constexpr int kUmmaMaxGroups = 4;
-constexpr int kUmmaMaxSplit = 2;
+constexpr int kUmmaMaxSplit = 4;
 
 struct UmmaGroup {          // all terms of one class that read the same plane (consecutive row shifts)
     int plane;
@@ -30,11 +30,13 @@ struct UmmaLaunch {
     int ncls;
     int N;                  // real output channels
     int NPAD;               // channels handled per split, multiple of 16, <= 256
-    int nsplit;             // 1 or 2 (N > 256)
+    int nsplit;             // output-channel splits (N > 256, or to spread sparse launches over more SMs)
     int MT;                 // 128-row tiles per CTA
     int rows_alloc;         // slab rows per stage  (>= MT*128 + max row-shift span)
     int tmem_cols;          // power of two >= MT*NPAD
     int TB, nbs;            // weight ring: nbs stages of TB taps
+    int nteams;             // converter teams of the non-persistent kernel: 2 (dense launches) or 4 (sparse)
+    int persistent;         // 1: one-CTA-per-SM tile loop with double-buffered TMEM (big layers)
     const float* bias;
     int epilogue;
     int batch;
@@ -60,7 +62,7 @@ struct UmmaPackLaunch {
 };
 
 struct UmmaChoice {         // tiling decisions for one ConvLaunch
-    int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs;
+    int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs, persistent, nteams;
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 
