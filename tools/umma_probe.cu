@@ -290,6 +290,12 @@ int main(int argc, char** argv) {
         return 0;
     }
     // M4 layers at B=16 (T = input rows of the layer)
+    if (argc > 1 && !strcmp(argv[1], "dgrad")) {       // shapes of the down-block dgrads (few output channels, many rows)
+        run_case("dg1_like", {16, 147443, 48, 24, 15, 0, 1, 65500, 16401}, false, 10);
+        run_case("dg2_like", {16, 73715, 72, 48, 15, 0, 1, 32750, 8201}, false, 10);
+        run_case("dg3_like", {16, 36851, 96, 72, 15, 0, 1, 16366, 4105}, false, 10);
+        return 0;
+    }
     run_case("down1",      {16, 73715, 24, 48, 15, 0, 1, 32750, 8201}, true, 20);
     run_case("down2_mt2",  {16, 36851, 48, 72, 15, 0, 1, 16366, 4105}, false, 20);
     run_case("down3_mt2",  {16, 18419, 72, 96, 15, 0, 1, 8174, 2057}, false, 20);

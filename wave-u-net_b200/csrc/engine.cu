@@ -68,6 +68,13 @@ struct WunHandle {
     int fork_used = 0;
     bool use_side = true;                // WUN_SIDE_STREAM=0 disables
     cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
+    // weight packs are hoisted off the critical path: phase 1 enqueues every pack kernel of the step on the side stream
+    // (they only depend on the parameters), phase 2 enqueues everything else; phase 0 = inline (inference, debug hook)
+    int phase = 0;
+    size_t arena_cur = 0;                // bump pointer into the pack arena (same sequence in phase 1 and 2)
+    size_t arena_sum = 0;                // total pack bytes of one forward+backward (dry run)
+    cudaEvent_t packs_event = nullptr;
+    bool packs_pending = false;          // main stream has not yet waited for the hoisted packs
     // per-call state
     bool dry = false;
     int64_t launches = 0;
@@ -212,21 +219,25 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
     const size_t slot = (size_t)h->cur_layer * 3 + h->cur_pass;
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
     if (use_umma) {
-        h->launches += 2;                       // weight pack + conv
-        if (h->dry) { h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); return WUN_OK; }
-        uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total);
-        if (h->debug_iters > 0) {
-            UmmaLaunch U; UmmaPackLaunch PL;
-            cudaError_t e0 = umma_build(L, ch, arena, &U, &PL);
-            if (e0 == cudaSuccess) e0 = launch_umma_pack(PL, h->stream);
-            for (int i = 0; i < h->debug_iters && e0 == cudaSuccess; ++i) e0 = launch_plane_conv_umma(U, h->stream);
-            if (e0 != cudaSuccess) return set_err(WUN_E_CUDA, std::string("debug conv launch: ") + cudaGetErrorString(e0));
-            return WUN_OK;
+        if (h->phase != 1) h->launches += 2;    // weight pack + conv (counted once)
+        if (h->dry) { h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); h->arena_sum += ch.pack_bytes; return WUN_OK; }
+        uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total) + h->arena_cur;
+        h->arena_cur += ch.pack_bytes;
+        UmmaLaunch U; UmmaPackLaunch PL;
+        cudaError_t e = umma_build(L, ch, arena, &U, &PL);
+        if (e == cudaSuccess && h->phase != 2) e = launch_umma_pack(PL, (h->phase == 1) ? h->side : h->stream);
+        if (e == cudaSuccess && h->phase != 1) {
+            if (h->packs_pending) {             // first tensor-core conv of the step: the hoisted packs must have landed
+                e = cudaStreamWaitEvent(h->stream, h->packs_event, 0);
+                h->packs_pending = false;
+            }
+            const int iters = (h->debug_iters > 0) ? h->debug_iters : 1;
+            for (int i = 0; i < iters && e == cudaSuccess; ++i) e = launch_plane_conv_umma(U, h->stream);
         }
-        cudaError_t e = umma_run_conv(L, ch, arena, h->stream);
         if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(e));
         return WUN_OK;
     }
+    if (h->phase == 1) return WUN_OK;
     ++h->launches;
     if (!h->dry) launch_plane_conv_simt(L, h->stream);
     return WUN_OK;
@@ -339,8 +350,8 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     for (const auto& c : op.classes) {
         if (c.m_hi <= c.m_lo) continue;
         PlaneView dpre = make_plane_on(h, c.out, P.grad_twin[c.out.tensor], view_bstride(h, c.out), c.m_lo, c.m_hi);
-        ++h->launches;                                         // bias gradient
-        if (!h->dry) launch_colsum(dpre, h->batch, scale, grads + P.params[op.b_param].offset, h->wstream);
+        if (h->phase != 1) ++h->launches;                      // bias gradient
+        if (!h->dry && h->phase != 1) launch_colsum(dpre, h->batch, scale, grads + P.params[op.b_param].offset, h->wstream);
         size_t i = 0;
         while (i < c.terms.size()) {
             WgradLaunch W;
@@ -378,6 +389,7 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     }
     const size_t slot = (size_t)h->cur_layer * 3 + 2;
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
+    if (h->phase == 1) return WUN_OK;
     if (use_umma) {
         ++h->launches;
         if (!h->dry) {
@@ -393,9 +405,18 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     return WUN_OK;
 }
 
+static int ensure_side(WunHandle* h) {
+    if (!h->side) {
+        WUN_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        WUN_CUDA_OK(cudaEventCreateWithFlags(&h->join_event, cudaEventDisableTiming));
+        WUN_CUDA_OK(cudaEventCreateWithFlags(&h->packs_event, cudaEventDisableTiming));
+    }
+    return WUN_OK;
+}
+
 // fork: everything enqueued on the main stream so far is visible to the side stream
 static int fork_side(WunHandle* h) {
-    if (h->dry || h->wstream == h->stream) return WUN_OK;
+    if (h->dry || h->phase == 1 || h->wstream == h->stream) return WUN_OK;
     if (h->fork_used >= (int)h->fork_events.size()) {
         cudaEvent_t e;
         WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -437,8 +458,8 @@ static int run_forward(WunHandle* h, const float* targets, float* outputs, float
     for (int i = 0; i < L; ++i) {
         const UpsampleSpec& us = P.ups[i];
         if (us.interp_param >= 0) {
-            ++h->launches;
-            if (!h->dry)
+            if (h->phase != 1) ++h->launches;
+            if (!h->dry && h->phase != 1)
                 launch_sigmoid(h->params + P.params[us.interp_param].offset,
                                const_cast<float*>(tensor_ptr(h, us.wsig_tensor)), us.C, h->stream);
         }
@@ -451,8 +472,8 @@ static int run_forward(WunHandle* h, const float* targets, float* outputs, float
         if ((rc = conv_forward(h, P.up[i], L + 1 + i)) != WUN_OK) return rc;
     OutputLaunch O;
     fill_output_launch(h, &O, targets, outputs, loss, training);
-    ++h->launches;
-    if (!h->dry) launch_output_fwd(O, h->stream);
+    if (h->phase != 1) ++h->launches;
+    if (!h->dry && h->phase != 1) launch_output_fwd(O, h->stream);
     return WUN_OK;
 }
 
@@ -461,18 +482,16 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     const int L = P.cfg.num_layers;
     int rc;
     h->wstream = h->stream;
-    h->fork_used = 0;
+    if (h->phase != 1) h->fork_used = (h->phase == 2) ? 1 : 0;
     if (!h->dry && h->use_side) {
-        if (!h->side) {
-            WUN_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-            WUN_CUDA_OK(cudaEventCreateWithFlags(&h->join_event, cudaEventDisableTiming));
-        }
+        int rcs = ensure_side(h);
+        if (rcs != WUN_OK) return rcs;
         h->wstream = h->side;
     }
     OutputLaunch O;
     fill_output_launch(h, &O, targets, nullptr, nullptr, 1);
-    h->launches += 2;
-    if (!h->dry) {
+    if (h->phase != 1) h->launches += 2;
+    if (!h->dry && h->phase != 1) {
         launch_output_wgrad(O, grads, scale, h->stream);
         launch_output_dgrad(O, const_cast<float*>(tensor_ptr(h, P.grad_twin[P.t_feat])), h->stream);
     }
@@ -491,8 +510,8 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         U.blend = (us.wsig_tensor >= 0) ? tensor_ptr(h, us.wsig_tensor) : nullptr;
         U.dvar = (us.interp_param >= 0) ? grads + P.params[us.interp_param].offset : nullptr;
         U.batch = h->batch; U.N = us.N; U.nmid = us.nmid; U.C = us.C; U.mid_mode = us.mid_mode; U.scale = scale;
-        ++h->launches;
-        if (!h->dry) launch_upsample_bwd(U, h->stream);
+        if (h->phase != 1) ++h->launches;
+        if (!h->dry && h->phase != 1) launch_upsample_bwd(U, h->stream);
     }
     if ((rc = fork_side(h)) != WUN_OK) return rc;
     if ((rc = conv_wgrad(h, P.bottleneck, grads, scale, L)) != WUN_OK) return rc;
@@ -502,7 +521,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         if ((rc = conv_wgrad(h, P.down[i], grads, scale, i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i], i)) != WUN_OK) return rc;
     }
-    if (!h->dry && h->wstream != h->stream) {       // join: the caller's stream continues only after all wgrads
+    if (!h->dry && h->phase != 1 && h->wstream != h->stream) {       // join: the caller's stream continues only after all wgrads
         WUN_CUDA_OK(cudaEventRecord(h->join_event, h->side));
         WUN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->join_event, 0));
     }
@@ -530,7 +549,7 @@ static int begin_call(WunHandle* h, const float* params, const float* mix, int64
     if (dry) return WUN_OK;
     { int rc0 = check_device(); if (rc0 != WUN_OK) return rc0; }
     if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
-    if (ws_bytes < h->lay.total * (int64_t)sizeof(float) + (int64_t)h->arena_bytes)
+    if (ws_bytes < h->lay.total * (int64_t)sizeof(float) + (int64_t)h->arena_sum)
         return set_err(WUN_E_INVALID, "workspace too small");
     if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return set_err(WUN_E_INVALID, "workspace must be 256-byte aligned");
     h->params = params; h->mix = mix; h->ws = (float*)ws; h->stream = (cudaStream_t)stream;
@@ -585,6 +604,7 @@ int wun_destroy(WunHandle* h) {
     if (h) {
         for (auto e : h->fork_events) cudaEventDestroy(e);
         if (h->join_event) cudaEventDestroy(h->join_event);
+        if (h->packs_event) cudaEventDestroy(h->packs_event);
         if (h->side) cudaStreamDestroy(h->side);
         delete h;
     }
@@ -606,7 +626,7 @@ int wun_param_table(const WunHandle* h, WunParamInfo* out, int64_t capacity) {
 int64_t wun_workspace_bytes(const WunHandle* h, int64_t batch, int training) {
     if (!h || batch < 1) return -1;
     Layout l = make_layout(h->plan, batch, training != 0);
-    return l.total * (int64_t)sizeof(float) + (int64_t)h->arena_bytes + 256;
+    return l.total * (int64_t)sizeof(float) + (int64_t)h->arena_sum + 256;
 }
 
 double wun_forward_flops(const WunHandle* h, int64_t batch) { return h ? h->plan.fwd_flops_per_item * batch : 0; }
@@ -617,13 +637,17 @@ double wun_forward_backward_flops(const WunHandle* h, int64_t batch) {
 int64_t wun_launches_forward(const WunHandle* hc) {
     WunHandle* h = const_cast<WunHandle*>(hc);
     if (begin_call(h, nullptr, nullptr, 1, false, nullptr, 0, nullptr, true) != WUN_OK) return -1;
+    const size_t keep = h->arena_sum;
+    h->phase = 0;
     run_forward(h, nullptr, nullptr, nullptr, 0);
+    h->arena_sum = keep;
     return h->launches;
 }
 
 int64_t wun_launches_forward_backward(const WunHandle* hc) {
     WunHandle* h = const_cast<WunHandle*>(hc);
     if (begin_call(h, nullptr, nullptr, 1, true, nullptr, 0, nullptr, true) != WUN_OK) return -1;
+    h->arena_sum = 0; h->phase = 0;
     run_forward(h, nullptr, nullptr, nullptr, 1);
     run_backward(h, nullptr, nullptr, 1.f);
     return h->launches;
@@ -634,6 +658,7 @@ int wun_forward(WunHandle* h, const float* params, const float* mix, int64_t bat
     int rc = begin_call(h, params, mix, batch, false, workspace, workspace_bytes, stream, false);
     if (rc != WUN_OK) return rc;
     if (!outputs) return set_err(WUN_E_INVALID, "outputs is null");
+    h->phase = 0; h->arena_cur = 0;
     rc = run_forward(h, nullptr, outputs, nullptr, training);
     if (rc != WUN_OK) return rc;
     WUN_CUDA_OK(cudaGetLastError());
@@ -648,10 +673,31 @@ int wun_forward_backward(WunHandle* h, const float* params, const float* mix, co
     if (!targets || !loss || !grads) return set_err(WUN_E_INVALID, "targets/loss/grads must not be null");
     WUN_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), h->stream));
     WUN_CUDA_OK(cudaMemsetAsync(grads, 0, sizeof(float) * h->plan.param_numel, h->stream));
+    if (h->use_side && h->umma_enabled) {
+        // phase 1: every weight pack of the step on the side stream, behind the work already enqueued on `stream`
+        rc = ensure_side(h);
+        if (rc != WUN_OK) return rc;
+        if (h->fork_events.empty()) { cudaEvent_t e; WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->fork_events.push_back(e); }
+        WUN_CUDA_OK(cudaEventRecord(h->fork_events[0], h->stream));
+        WUN_CUDA_OK(cudaStreamWaitEvent(h->side, h->fork_events[0], 0));
+        h->phase = 1; h->arena_cur = 0;
+        rc = run_forward(h, targets, outputs, loss, 1);
+        if (rc == WUN_OK) rc = run_backward(h, targets, grads, grad_scale);
+        h->phase = 0;
+        if (rc != WUN_OK) return rc;
+        WUN_CUDA_OK(cudaEventRecord(h->packs_event, h->side));
+        h->packs_pending = true;
+        h->phase = 2;
+    }
+    h->arena_cur = 0;
     rc = run_forward(h, targets, outputs, loss, 1);
+    if (rc == WUN_OK) rc = run_backward(h, targets, grads, grad_scale);
+    h->phase = 0;
     if (rc != WUN_OK) return rc;
-    rc = run_backward(h, targets, grads, grad_scale);
-    if (rc != WUN_OK) return rc;
+    if (h->packs_pending) {                     // no tensor-core conv consumed the packs: still join the side stream
+        WUN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->packs_event, 0));
+        h->packs_pending = false;
+    }
     WUN_CUDA_OK(cudaGetLastError());
     return WUN_OK;
 }
@@ -723,6 +769,7 @@ int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, 
         *flops_per_launch = f * batch;
     }
     h->debug_iters = iters;
+    h->phase = 0; h->arena_cur = 0;
     rc = conv_forward(h, op, layer);
     h->debug_iters = 0;
     if (rc != WUN_OK) return rc;
