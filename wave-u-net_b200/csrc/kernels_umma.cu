@@ -319,37 +319,47 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                // phase 2: warp = output row, lanes = columns
+                __syncwarp();
+                // phase 2: each warp writes out the 32 rows it staged itself (no block barrier needed); lanes run over
+                // (row, 4-column quad) pairs so that narrow layers (N = 24..48) still use every lane and a whole warp
+                // store covers several consecutive rows
                 const int ncols = min(cw, L.N - (n0 + c0));
-                for (int r = warp; r < 128; r += 4) {
-                    const int m = m_base + mt * 128 + r;
-                    if (m >= K.out.m_hi) break;
-                    const long long roff = (long long)b * K.out.bstride + (long long)m * K.out.rstride + n0 + c0;
-                    const bool accum = (m >= K.out.acc_lo && m < K.out.acc_hi);
-                    float* dst = K.out.base + roff;
-                    const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (ncols % 4 == 0);
-                    if (vec) {
-                        for (int q = lane; q < ncols / 4; q += 32) {
-                            float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
-                            if (L.epilogue == EPI_SLOPE && K.out.saved) {
-                                const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
-                                o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
-                                o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
-                            }
-                            if (accum) { const float4 old = reinterpret_cast<float4*>(dst)[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                            reinterpret_cast<float4*>(dst)[q] = o;
+                const long long tile_off = (long long)b * K.out.bstride + n0 + c0;
+                const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
+                if (vec) {
+                    const int Q = ncols >> 2;
+                    for (int it = lane; it < 32 * Q; it += 32) {
+                        const int rl = it / Q, q = it - rl * Q;
+                        const int r = warp * 32 + rl;
+                        const int m = m_base + mt * 128 + r;
+                        if (m >= K.out.m_hi) continue;
+                        const long long roff = tile_off + (long long)m * K.out.rstride;
+                        float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
+                        if (L.epilogue == EPI_SLOPE && K.out.saved) {
+                            const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
+                            o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
+                            o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
                         }
-                    } else {
-                        for (int j = lane; j < ncols; j += 32) {
-                            float o = stage[(size_t)r * SW + j];
-                            if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
-                            if (accum) o += dst[j];
-                            dst[j] = o;
-                        }
+                        float4* dst = reinterpret_cast<float4*>(K.out.base + roff) + q;
+                        if (m >= K.out.acc_lo && m < K.out.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                        *dst = o;
+                    }
+                } else {
+                    for (int it = lane; it < 32 * ncols; it += 32) {
+                        const int rl = it / ncols, j = it - rl * ncols;
+                        const int r = warp * 32 + rl;
+                        const int m = m_base + mt * 128 + r;
+                        if (m >= K.out.m_hi) continue;
+                        const long long roff = tile_off + (long long)m * K.out.rstride;
+                        float o = stage[(size_t)r * SW + j];
+                        if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
+                        float* dst = K.out.base + roff + j;
+                        if (m >= K.out.acc_lo && m < K.out.acc_hi) o += *dst;
+                        *dst = o;
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is overwritten by the next block
+                __syncwarp();                                     // the warp-private staging rows are overwritten by the next block
             }
         }
         if (tid == 0) T_ADD(9, T_NOW() - t_epi);
@@ -664,36 +674,44 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
                     }
                     if (n0 + c0 < L.N) {
                         const int cw = min(CW, NPAD - c0);
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        __syncwarp();
                         const int ncols = min(cw, L.N - (n0 + c0));
-                        for (int r = ew; r < 128; r += 4) {
-                            const int m = tc.m_base + mt * 128 + r;
-                            if (m >= K.out.m_hi) break;
-                            const long long roff = (long long)tc.b * K.out.bstride + (long long)m * K.out.rstride + n0 + c0;
-                            const bool accum = (m >= K.out.acc_lo && m < K.out.acc_hi);
-                            float* dst = K.out.base + roff;
-                            const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (ncols % 4 == 0);
-                            if (vec) {
-                                for (int q = lane; q < ncols / 4; q += 32) {
-                                    float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
-                                    if (L.epilogue == EPI_SLOPE && K.out.saved) {
-                                        const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
-                                        o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
-                                        o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
-                                    }
-                                    if (accum) { const float4 old = reinterpret_cast<float4*>(dst)[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                                    reinterpret_cast<float4*>(dst)[q] = o;
+                        const long long tile_off = (long long)tc.b * K.out.bstride + n0 + c0;
+                        const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
+                                         ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
+                        if (vec) {
+                            const int Q = ncols >> 2;
+                            for (int it = lane; it < 32 * Q; it += 32) {
+                                const int rl = it / Q, q = it - rl * Q;
+                                const int r = q4 * 32 + rl;
+                                const int m = tc.m_base + mt * 128 + r;
+                                if (m >= K.out.m_hi) continue;
+                                const long long roff = tile_off + (long long)m * K.out.rstride;
+                                float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
+                                if (L.epilogue == EPI_SLOPE && K.out.saved) {
+                                    const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
+                                    o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
+                                    o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
                                 }
-                            } else {
-                                for (int j = lane; j < ncols; j += 32) {
-                                    float o = stage[(size_t)r * SW + j];
-                                    if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
-                                    if (accum) o += dst[j];
-                                    dst[j] = o;
-                                }
+                                float4* dst = reinterpret_cast<float4*>(K.out.base + roff) + q;
+                                if (m >= K.out.acc_lo && m < K.out.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                                *dst = o;
+                            }
+                        } else {
+                            for (int it = lane; it < 32 * ncols; it += 32) {
+                                const int rl = it / ncols, j = it - rl * ncols;
+                                const int r = q4 * 32 + rl;
+                                const int m = tc.m_base + mt * 128 + r;
+                                if (m >= K.out.m_hi) continue;
+                                const long long roff = tile_off + (long long)m * K.out.rstride;
+                                float o = stage[(size_t)r * SW + j];
+                                if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
+                                float* dst = K.out.base + roff + j;
+                                if (m >= K.out.acc_lo && m < K.out.acc_hi) o += *dst;
+                                *dst = o;
                             }
                         }
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        __syncwarp();
                     }
                 }
             }
@@ -1177,7 +1195,8 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
         // down3 -4 %), 2 = every eligible launch incl. dgrad
         const char* env = getenv("WUN_PERSISTENT");
         const int mode = env ? atoi(env) : 1;
-        const bool allow = (mode == 2) || (mode == 1 && L.epilogue == EPI_BIAS_LRELU && ch->NPAD <= 80);
+        const bool allow = (mode == 2) || (mode == 1 && L.epilogue == EPI_BIAS_LRELU && ch->NPAD <= 80) ||
+                           (mode == 3 && ch->NPAD <= 80) || (mode == 4 && ch->NPAD <= 48);
         if (allow && n_ctas >= 3 * 148 && 2 * MT * ch->NPAD <= 512) {
             ch->persistent = 1;
             ch->nbs = 98304 / (TB * blk);          // one CTA per SM: a deeper weight ring fits
