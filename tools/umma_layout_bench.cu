@@ -34,7 +34,7 @@ __device__ __forceinline__ void commit(uint32_t bar) { asm volatile("tcgen05.com
 
 // ---------------- timing ----------------
 // layout: 0 none, 6 = 32B, 4 = 64B, 2 = 128B.  One CTA per SM, lane 0 of warp 0 issues `iters` x 4 MMAs.
-__global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int iters, int shift_rows, long long* out, int nacc, int smem_fill_kb, int acc_stride, int run_len) {
+__global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int iters, int shift_rows, long long* out, int nacc, int smem_fill_kb, int acc_stride, int run_len, int b_lbo_mult = 16) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_holder;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int layout, int N, int ite
         const uint32_t rowbytes = layout == 0 ? 16 : (layout == 6 ? 32 : (layout == 4 ? 64 : 128));
         const uint32_t sa = smem_u32(smem) + shift_rows * rowbytes, sb = smem_u32(smem) + 32 * 1024;
         uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
-        if (layout == 0) { a_lbo = 264 * 16; a_sbo = 128; b_lbo = 16 * N; b_sbo = 128; }
+        if (layout == 0) { a_lbo = 264 * 16; a_sbo = 128; b_lbo = b_lbo_mult * N; b_sbo = 128; }
         else { a_lbo = 16; a_sbo = 8 * rowbytes; b_lbo = 16; b_sbo = 8 * rowbytes; }
         const uint32_t bo = (layout == 2) ? ((sa >> 7) & 7) : 0;
         const uint64_t ad = make_desc(sa, a_lbo, a_sbo, layout, bo), bd = make_desc(sb, b_lbo, b_sbo, layout, 0);
@@ -180,6 +180,16 @@ int main() {
                     long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
                     printf("N=%3d nacc=%d stride=%3d switch-every=%2d : %6.1f cycles/MMA\n", N, nacc, stride, run, (double)cyc / (iters * 4));
                 }
+    printf("== cycles per MMA vs A row shift and B atom stride (SWIZZLE_NONE, 1 accumulator) ==\n");
+    for (int N : {32, 48, 64, 96, 128, 192})
+        for (int lm : {16, 32})
+            for (int shift : {0, 1, 4, 8, 13}) {
+                time_kernel<<<148, 128, 64 * 1024>>>(0, N, 300, shift, dout, 1, 64, N, 1, lm);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("ERROR %s\n", cudaGetErrorString(e)); return 1; }
+                long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
+                printf("N=%3d b_lbo=%2d*N shift=%2d : %6.1f cycles/MMA\n", N, lm, shift, (double)cyc / (300 * 4));
+            }
     return 0;
     printf("== shifted-start correctness: D[m][n] must equal A[m+shift][koff/2 + n] ==\n");
     float* dres; CK(cudaMalloc(&dres, 2 * 128 * 16 * 4));

@@ -64,6 +64,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// One lane of a CONVERGED warp, chosen by the hardware.  Unlike `lane == 0` this tells the compiler that exactly one
+// thread runs the region, so every tcgen05.mma / commit / bulk copy inside is a plain instruction instead of an
+// ELECT + retry-branch sequence (measured on the single-thread issue loops, which are the critical path).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -307,7 +315,15 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 for (int cb = 0; cb < cw; cb += 16) {
                     __syncwarp();
                     float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + c0 + cb), v);
+                    if (L.fuse) {
+                        float v2[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 2 * NPAD + c0 + cb), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 2 * NPAD + NPAD + c0 + cb), v2);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                    } else {
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + c0 + cb), v);
+                    }
                     if (L.epilogue == EPI_BIAS_LRELU) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -367,10 +383,11 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
         tc_fence_before();
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*NPAD
             const uint32_t atom_stride = 16u * L.rows_alloc;
-            const uint32_t b_lbo = 16u * NPAD;       // between the two K atoms of a weight block
+            const uint32_t b_lbo = 32u * NPAD;       // between the two K atoms of a weight block
             int ji = 0, bi = 0;                      // bi counts weight STAGES (TB taps each)
             const long long t_mma = T_NOW();
             uint32_t first = 0;                      // accumulate flag: 0 for the very first K step
@@ -389,7 +406,7 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                         T_WAIT(5, mbar_wait(BAR(B_FULL + bs), (bi / nbs) & 1));
                         tc_fence_after();
                         const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
-                        const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 32u * NPAD, b_lbo, 128);
+                        const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
                         const int nt = min(TB, G.term_end - t0);
                         for (int tt = 0; tt < nt; ++tt) {
                             const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
@@ -397,10 +414,18 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                             const uint64_t aoff = (uint64_t)(uint32_t)(L.d[t0 + tt] - G.dmin);
                             for (int mt = 0; mt < L.MT; ++mt) {
                                 const uint64_t a_hi = a_hi0 + aoff + (uint64_t)(128u * mt), a_lo = a_lo0 + aoff + (uint64_t)(128u * mt);
-                                const uint32_t td = tmem_base + (uint32_t)(mt * NPAD);
-                                umma_bf16(td, a_lo, b_hi, idesc, first);
-                                umma_bf16(td, a_hi, b_lo, idesc, 1u);
-                                umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                                if (L.fuse) {
+                                    // fused-N: D[:, 0:NPAD] += A_hi B_hi, D[:, NPAD:2NPAD] += A_hi B_lo in ONE MMA over the
+                                    // [B_hi | B_lo] block, then D[:, 0:NPAD] += A_lo B_hi; the epilogue adds the two halves
+                                    const uint32_t td = tmem_base + (uint32_t)(mt * 2 * NPAD);
+                                    umma_bf16(td, a_hi, b_hi, idesc2, first);
+                                    umma_bf16(td, a_lo, b_hi, idesc, 1u);
+                                } else {
+                                    const uint32_t td = tmem_base + (uint32_t)(mt * NPAD);
+                                    umma_bf16(td, a_lo, b_hi, idesc, first);
+                                    umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                                    umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                                }
                             }
                             first = 1u;
                         }
@@ -415,7 +440,7 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
         __syncwarp();
     } else {
         // ===================== weight loader =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint8_t* src = K.wpack[split];
             int bi = 0;
             size_t blk = 0;                          // running block (tap) index into the packed stream
@@ -559,10 +584,10 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
         }
     } else if (warp == 8) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t atom_stride = 16u * L.rows_alloc;
-            const uint32_t b_lbo = 16u * NPAD;
+            const uint32_t b_lbo = 32u * NPAD;
             int jg = 0, bg = 0, k = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
                 const TileCoord tc = decode_tile(L, t);
@@ -585,7 +610,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
                             mbar_wait(BAR(B_FULL + bs), (bg / nbs) & 1);
                             tc_fence_after();
                             const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
-                            const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 32u * NPAD, b_lbo, 128);
+                            const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
                             const int nt = min(TB, G.term_end - t0);
                             for (int tt = 0; tt < nt; ++tt) {
                                 const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
@@ -611,7 +636,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
         __syncwarp();
     } else if (warp == 9) {
         // ===================== weight loader =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int bg = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(L, t);
@@ -780,13 +805,15 @@ constexpr int kWgRK = 64;          // rows per pipeline stage
 constexpr int kWgSpan = 16;        // extra P rows per stage (max tap shift span)
 constexpr int kWgStagesMax = 3;    // pipeline stages: as many as fit in shared memory (L.nstages)
 
-constexpr int kWgConvThreads = 256;   // 8 converter warps (0-7); warp 8 = TMEM alloc + MMA issue
+// CW converter warps (0..CW-1, a multiple of 4: TMEM lane quarters); warp CW = TMEM alloc + MMA issue
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constant__ UmmaWgradLaunch L) {
+template <int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, 1) wgrad_umma_kernel(const __grid_constant__ UmmaWgradLaunch L) {
+    constexpr int kWgConvThreads = CW * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // group / tap set of this CTA
@@ -826,14 +853,14 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         mbar_init(BAR(ACC), 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), Gp.tmem_cols);
+    if (warp == CW) tmem_alloc(smem_u32(tmem_holder), Gp.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const int nchunks = g1 - g0;
 
-    if (warp < 8) {
+    if (warp < CW) {
         // ===================== converter =====================
         // items of a chunk: (side, row, 16-channel group); A side = 8 groups (128 channels), B side = NT/16 groups
         const int gA = 8, gB = (NT + 15) / 16;
@@ -904,7 +931,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
             mbar_arrive(BAR(FULL + st));
         }
         // ===================== epilogue: accumulators -> reductions into dW =====================
-        // TMEM lane quarter = warp % 4; the two warps of a quarter split the taps.
+        // TMEM lane quarter = warp % 4; the CW/4 warps of a quarter split the taps.
         if (tid == 0) { T_WAIT(8, mbar_wait(BAR(ACC), 0)); }
         else mbar_wait(BAR(ACC), 0);
         tc_fence_after();
@@ -913,7 +940,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         const int m = ca0 + q4 * 32 + lane;                      // M-side channel of this thread
         const bool m_ok = m < SA.C;
         const int sM = swap ? L.w_sg : L.w_sp, sN = swap ? L.w_sp : L.w_sg;
-        for (int t = (warp >> 2); t < ntap; t += 2) {
+        for (int t = (warp >> 2); t < ntap; t += CW / 4) {
             float* dst_t = L.dW + (long long)Gp.woff[tap0 + t] + (long long)m * sM;
             for (int cb = 0; cb < NT; cb += 16) {
                 if (cb0 + cb >= SB.C) break;
@@ -937,7 +964,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         if (tid == 0) { T_ADD(9, T_NOW() - t_epi); T_ADD(0, 1); T_ADD(7, nchunks); }
         tc_fence_before();
     } else {
-        if (lane == 0) {
+        if (elect_one()) {
             const long long t_mma = T_NOW();
             // both operands MN-major: idesc a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
@@ -973,7 +1000,7 @@ __global__ void __launch_bounds__(288, 1) wgrad_umma_kernel(const __grid_constan
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == CW) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Gp.tmem_cols);
     }
@@ -1059,19 +1086,28 @@ bool umma_plan_wgrad(UmmaWgradLaunch* L) {
 cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wgrad_umma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wgrad_umma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid(L.grid_x, L.grid_y, L.grid_z);
-    wgrad_umma_kernel<<<grid, 288, wgrad_smem_bytes(L), stream>>>(L);
+    static const int cw = [] { const char* env = getenv("WUN_WG_WARPS"); return env ? atoi(env) : 12; }();   // measured: 8 -> 12 converter warps = -22 % on down3 (converter-latency bound), 16 is slower
+    if (cw == 16) wgrad_umma_kernel<16><<<grid, 16 * 32 + 32, wgrad_smem_bytes(L), stream>>>(L);
+    else if (cw == 12) wgrad_umma_kernel<12><<<grid, 12 * 32 + 32, wgrad_smem_bytes(L), stream>>>(L);
+    else wgrad_umma_kernel<8><<<grid, 8 * 32 + 32, wgrad_smem_bytes(L), stream>>>(L);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight pre-pack: fp32 W -> hi/lo bf16 blocks in K-step streaming order.  blockIdx.y = job (class, split);
 // one thread per (block, n, k) element.  Block bi = ((group, chunk), term) in the kernel's loop order; element
-// (a, n, kk) of the hi half sits at byte a*16*NPAD + (n/8)*128 + (n%8)*16 + kk*2, the lo half 32*NPAD bytes later.
+// (a, n, kk) of the hi half sits at byte a*32*NPAD + (n/8)*128 + (n%8)*16 + kk*2, the lo half 16*NPAD bytes later:
+// per K atom the block is a K-major [hi rows 0..NPAD) | lo rows NPAD..2*NPAD) matrix, so ONE descriptor with
+// N = 2*NPAD covers [B_hi | B_lo] (fused-N mode) and N = NPAD covers B_hi alone.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) umma_pack_kernel(const __grid_constant__ UmmaPackLaunch PL) {
     const UmmaPackJob& J = PL.jobs[blockIdx.y];
@@ -1093,9 +1129,9 @@ __global__ void __launch_bounds__(256) umma_pack_kernel(const __grid_constant__ 
         const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
         const int a = kk16 >> 3, kk = kk16 & 7;
         uint8_t* blk = J.out + (size_t)bi * 64u * PL.NPAD;
-        const size_t off = (size_t)a * 16u * PL.NPAD + (size_t)(n >> 3) * 128u + (size_t)(n & 7) * 16u + (size_t)kk * 2u;
+        const size_t off = (size_t)a * 32u * PL.NPAD + (size_t)(n >> 3) * 128u + (size_t)(n & 7) * 16u + (size_t)kk * 2u;
         *reinterpret_cast<__nv_bfloat16*>(blk + off) = h;
-        *reinterpret_cast<__nv_bfloat16*>(blk + 32u * PL.NPAD + off) = l;
+        *reinterpret_cast<__nv_bfloat16*>(blk + 16u * PL.NPAD + off) = l;
     }
 }
 
@@ -1163,6 +1199,14 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     int tm = 32;
     while (tm < MT * ch->NPAD) tm *= 2;
     ch->tmem_cols = tm;
+    {   // fused-N mode (2 MMAs per product instead of 3): pays when the MMA is at its shared-memory floor (small N)
+        // WUN_FUSE_N: 0 (default) = off, 1 = launches the persistent kernel does not take, 2 = preferred over persistent.
+        // Measured: no step-time gain (8.583 vs 8.584 ms) - those launches are not MMA-bound - but the separate hi*lo
+        // accumulator halves the worst-case rounding error, so the mode stays available.
+        const char* env = getenv("WUN_FUSE_N");
+        const int mode = env ? atoi(env) : 0;
+        ch->fuse = (mode > 0 && ch->NPAD <= 64) ? mode : 0;
+    }
     ch->pack_bytes = (bytes + 255) / 256 * 256;
     // weight ring: stages of TB taps (fewer barrier round trips for the single MMA-issuing thread).  Launches that
     // fill the GPU keep it at ~48 KB so two CTAs fit per SM; launches with fewer CTAs than SMs (the deep layers) are
@@ -1191,13 +1235,17 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     // persistent one-CTA-per-SM kernel for launches with at least ~3 tiles per SM whose double-buffered accumulators fit TMEM
     ch->persistent = 0;
     {
-        // WUN_PERSISTENT: 0 = never, 1 (default) = forward launches with NPAD <= 80 (measured win: down1 +28 %, down2 +12 %,
-        // down3 -4 %), 2 = every eligible launch incl. dgrad
+        // WUN_PERSISTENT: 0 = never, 1 = forward launches with NPAD <= 80, 2 (default) = every eligible launch incl. dgrad,
+        // 3..6 = experiment subsets.  Measured after the elect_one() issue-loop fix (ms/step, M4 B=16): 0: 9.17, 1: 9.13,
+        // 2: 8.99, 3: 9.17, 5 (fwd, any NPAD): 9.13, 6: 9.12; with 12 wgrad converter warps 1: 8.76, 2: 8.58.
         const char* env = getenv("WUN_PERSISTENT");
-        const int mode = env ? atoi(env) : 1;
+        const int mode = env ? atoi(env) : 2;
         const bool allow = (mode == 2) || (mode == 1 && L.epilogue == EPI_BIAS_LRELU && ch->NPAD <= 80) ||
-                           (mode == 3 && ch->NPAD <= 80) || (mode == 4 && ch->NPAD <= 48);
-        if (allow && n_ctas >= 3 * 148 && 2 * MT * ch->NPAD <= 512) {
+                           (mode == 3 && ch->NPAD <= 80) || (mode == 4 && ch->NPAD <= 48) ||
+                           (mode == 5 && L.epilogue == EPI_BIAS_LRELU) ||
+                           (mode == 6 && (L.epilogue == EPI_BIAS_LRELU || ch->NPAD > 80));
+        if (allow && ch->fuse != 2 && n_ctas >= 3 * 148 && 2 * MT * ch->NPAD <= 512) {
+            ch->fuse = 0;
             ch->persistent = 1;
             ch->nbs = 98304 / (TB * blk);          // one CTA per SM: a deeper weight ring fits
             if (ch->nbs > kBStagesMax) ch->nbs = kBStagesMax;
@@ -1206,6 +1254,12 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
             while (tm2 < 2 * MT * ch->NPAD) tm2 *= 2;
             ch->tmem_cols = tm2;
         }
+    }
+    if (ch->fuse) {
+        ch->fuse = 1;
+        int tmf = 32;
+        while (tmf < 2 * MT * ch->NPAD) tmf *= 2;
+        ch->tmem_cols = tmf;
     }
     return true;
 }
@@ -1227,7 +1281,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     memset(&PL, 0, sizeof(PL));
     for (int p = 0; p < L.nplanes; ++p) U.planes[p] = L.planes[p];
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
-    U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
+    U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.fuse = ch.fuse; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
     PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
     int nterm_total = 0;
     for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);

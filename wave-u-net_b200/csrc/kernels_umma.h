@@ -37,6 +37,7 @@ struct UmmaLaunch {
     int TB, nbs;            // weight ring: nbs stages of TB taps
     int nteams;             // converter teams of the non-persistent kernel: 2 (dense launches) or 4 (sparse)
     int persistent;         // 1: one-CTA-per-SM tile loop with double-buffered TMEM (big layers)
+    int fuse;               // 1: fused-N MMAs over [B_hi | B_lo] (2 per product; accumulator tile = 2*NPAD columns)
     const float* bias;
     int epilogue;
     int batch;
@@ -62,7 +63,7 @@ struct UmmaPackLaunch {
 };
 
 struct UmmaChoice {         // tiling decisions for one ConvLaunch
-    int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs, persistent, nteams;
+    int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs, persistent, nteams, fuse;
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 

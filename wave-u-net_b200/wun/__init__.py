@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libwun.so")
+LIB_PATH = os.environ.get("WUN_LIB") or os.path.join(_PKG, "libwun.so")   # WUN_LIB: A/B-test another build
 
 WUN_OK, WUN_E_INVALID, WUN_E_NOTIMPL, WUN_E_SHAPE, WUN_E_CUDA, WUN_E_NOGPU = 0, -1, -2, -3, -4, -5
 
