@@ -478,7 +478,6 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
 // prologue / TMEM allocation / wave tail.
 // Warps: 0-7 converters (two teams), 8 MMA issue + TMEM alloc, 9 weight loader, 10-13 epilogue.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPersThreads = 448;
 
 struct TileCoord { int cls, b, split, m_base; };
 
@@ -500,7 +499,12 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaLaunch& L, int t) {
     return tc;
 }
 
-__global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+// PT converter teams (4 warps each): warps [0, 4PT) convert, warp 4PT issues MMAs, 4PT+1 streams weights, 4PT+2..4PT+5
+// run the epilogue (4PT+2 = 2 mod 4, so `warp & 3` covers the four TMEM lane quarters).  PT+1 slab stages.
+template <int PT>
+__global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+    constexpr int kSlabStages = PT + 1;
+    constexpr int kMmaWarp = 4 * PT, kLoadWarp = 4 * PT + 1, kEpiWarp0 = 4 * PT + 2;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NPAD = L.NPAD;
@@ -527,14 +531,14 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 128); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t acc_cols = (uint32_t)(L.MT * NPAD);               // columns of one accumulator buffer
 
-    if (warp < 8) {
+    if (warp < kMmaWarp) {
         // ===================== converters =====================
         const int team = warp >> 2, ttid = tid & 127;
         int jg = 0;                                                   // job counter across tiles
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
                 const PlaneView& P = L.planes[G.plane];
                 const int nchunk = (P.C + 15) >> 4;
                 for (int c = 0; c < nchunk; ++c, ++jg) {
-                    if ((jg & 1) != team) continue;
+                    if ((jg % PT) != team) continue;
                     const int st = jg % kSlabStages;
                     uint8_t* S = slab0 + st * slab_bytes;
                     const uint32_t atom_stride = 16u * L.rows_alloc;
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == kLoadWarp) {
         // ===================== weight loader =====================
         if (elect_one()) {
             int bg = 0;
@@ -661,8 +665,8 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
         }
         __syncwarp();
     } else {
-        // ===================== epilogue warps (10-13): TMEM lane quarter = warp & 3 =====================
-        const int q4 = warp & 3, ew = warp - 10;
+        // ===================== epilogue warps: TMEM lane quarter = warp & 3 =====================
+        const int q4 = warp & 3;
         int k = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
             const TileCoord tc = decode_tile(L, t);
@@ -744,7 +748,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, L.tmem_cols);
     }
@@ -752,6 +756,7 @@ __global__ void __launch_bounds__(kPersThreads, 1) plane_conv_umma_persistent(co
 
 static size_t umma_pers_smem_bytes(const UmmaLaunch& L) {
     const size_t CW = (L.NPAD < 128) ? L.NPAD : 128;
+    const size_t kSlabStages = (L.nteams == 3) ? 4 : 3;
     return (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD + 128u * (CW + 4) * 4 +
            (2 * kSlabStages + 2 * kBStagesMax + 4) * 8 + 32 + 4 * (size_t)L.NPAD * L.nsplit;
 }
@@ -770,7 +775,9 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(plane_conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(plane_conv_umma_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        e = cudaFuncSetAttribute(plane_conv_umma_persistent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(plane_conv_umma_persistent<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -785,7 +792,8 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     if (max_tiles <= 0) return cudaSuccess;
     if (L.persistent) {
         const int grid = total < 148 ? total : 148;
-        plane_conv_umma_persistent<<<grid, kPersThreads, umma_pers_smem_bytes(L), stream>>>(L, total);
+        if (L.nteams == 3) plane_conv_umma_persistent<3><<<grid, 3 * 128 + 192, umma_pers_smem_bytes(L), stream>>>(L, total);
+        else plane_conv_umma_persistent<2><<<grid, 2 * 128 + 192, umma_pers_smem_bytes(L), stream>>>(L, total);
         return cudaGetLastError();
     }
     const size_t smem = umma_smem_bytes(L);
@@ -1244,12 +1252,24 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
                            (mode == 3 && ch->NPAD <= 80) || (mode == 4 && ch->NPAD <= 48) ||
                            (mode == 5 && L.epilogue == EPI_BIAS_LRELU) ||
                            (mode == 6 && (L.epilogue == EPI_BIAS_LRELU || ch->NPAD > 80));
-        if (allow && ch->fuse != 2 && n_ctas >= 3 * 148 && 2 * MT * ch->NPAD <= 512) {
+        const char* envm = getenv("WUN_PERS_MIN");
+        const int min_per_sm = envm ? atoi(envm) : 3;
+        if (allow && ch->fuse != 2 && n_ctas >= (long long)min_per_sm * 148 && 2 * MT * ch->NPAD <= 512) {
             ch->fuse = 0;
             ch->persistent = 1;
-            ch->nbs = 98304 / (TB * blk);          // one CTA per SM: a deeper weight ring fits
+            // (128-row tiles for better last-round balance were tried - rounds x height cost model - and lost badly:
+            //  9.04 vs 8.51 ms/step; the 256-row tile amortises the slab halo and the per-tile pipeline ramp.)
+            {   // converter teams of the persistent kernel (WUN_PERS_TEAMS = 2 | 3)
+                const char* envt = getenv("WUN_PERS_TEAMS");
+                ch->nteams = (envt && envt[0] == '2') ? 2 : 3;
+            }
+            // one CTA per SM: a deeper weight ring fits next to the slab stages and the epilogue staging tile
+            const long long cw = (ch->NPAD < 128) ? ch->NPAD : 128;
+            long long left = 218 * 1024 - (long long)(ch->nteams + 1) * 64 * ch->rows_alloc - 128 * (cw + 4) * 4 - 1024 - 4LL * ch->NPAD * ch->nsplit;
+            if (left > 98304) left = 98304;
+            ch->nbs = (int)(left / (TB * blk));
             if (ch->nbs > kBStagesMax) ch->nbs = kBStagesMax;
-            if (ch->nbs < 2) ch->nbs = 2;
+            if (ch->nbs < 2) { ch->nbs = 2; ch->nteams = 2; }
             int tm2 = 32;
             while (tm2 < 2 * MT * ch->NPAD) tm2 *= 2;
             ch->tmem_cols = tm2;
