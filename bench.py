@@ -313,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                      "frac": dom_tf / peaks["tf_burst"], "traffic": traffic,
-                     "kernel": "plane_conv_umma_kernel, forward of down%d (%s rows x %d->%d ch, k=15), %.1f us/launch, "
+                     "kernel": "plane_conv_umma_persistent (tcgen05), forward of down%d (%s rows x %d->%d ch, k=15), %.1f us/launch, "
                                "%.2f algorithmic GFLOP/launch (live positions, 2 FLOP/MAC, the 3 bf16 MMAs per product "
                                "count once)" % (dom_layer, "16x%d" % ((t_in >> (dom_layer + 1))), 24 * dom_layer,
                                                 24 * (dom_layer + 1), dom_us, dom_flops * 1e-9),
