@@ -154,6 +154,13 @@ int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, 
  * L+1..2L up.  pass: 0 fwd, 1 dgrad, 2 wgrad. */
 const char* wun_layer_kernel(const WunHandle* h, int layer, int pass);
 
+
+/* --- checkpoint helper (host only, no GPU needed) --------------------------------------------------
+ * CRC-32C (Castagnoli) of `n` bytes, continuing from `crc` (0 to start): the checksum TensorFlow's V2 checkpoint
+ * format stores (masked) for every index block and tensor.  Used by TFCheckpoint.py, which replaces the
+ * tf.train.Saver calls at Training.py:92-98,113 and Evaluate.py:55-57. */
+uint32_t wun_crc32c(uint32_t crc, const void* data, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,6 +311,83 @@ def forward_backward(cfg, params_np, mix_np, targets_np, dtype=torch.float32, tr
     return float(loss.detach()), outs, grads
 
 
+# ---- LeakyReLU mask-flip analysis -------------------------------------------------------------------------------
+# LeakyReLU's derivative jumps at 0, so a pre-activation that lies within the forward rounding noise of zero can get the
+# other slope in an implementation that is not bit-identical to this one; one such element moves whole gradient
+# tensors of a small net by ~1e-2 although every kernel is exact (measured: tools/grad_diag.py, DESIGN.md 5).  The two
+# helpers below let a checker PROVE that a gradient mismatch is exactly that: list the pre-activations near zero, redo
+# the backward with some of their slopes flipped, and compare again.
+_FLIP_STATE = {"active": False, "call": 0, "flips": (), "record": None, "tol": 0.0}
+
+
+def _leaky_relu_instrumented(x):
+    st = _FLIP_STATE
+    idx = st["call"]
+    st["call"] += 1
+    if st["record"] is not None:
+        with torch.no_grad():
+            rms = x.pow(2).mean().sqrt().clamp_min(1e-30)
+            rel = (x.abs() / rms).reshape(-1)
+            for flat in torch.nonzero(rel < st["tol"]).reshape(-1).tolist():
+                st["record"].append((float(rel[flat]), idx, int(flat)))
+    mine = [f for c, f in st["flips"] if c == idx]
+    if not mine:
+        return F.leaky_relu(x, LEAK)
+    mask = (x.detach() > 0).reshape(-1).clone()
+    for flat in mine:
+        mask[flat] = ~mask[flat]
+    return torch.where(mask.reshape(x.shape), x, LEAK * x)
+
+
+def _run_instrumented(fn, flips=(), record=None, tol=0.0):
+    global leaky_relu
+    saved = leaky_relu
+    _FLIP_STATE.update(active=True, call=0, flips=tuple(flips), record=record, tol=tol)
+    leaky_relu = _leaky_relu_instrumented
+    try:
+        return fn()
+    finally:
+        leaky_relu = saved
+        _FLIP_STATE.update(active=False, call=0, flips=(), record=None, tol=0.0)
+
+
+def near_zero_preactivations(cfg, params_np, mix_np, tol=1e-4, dtype=torch.float64):
+    """[(|x| / rms of its layer, LeakyReLU call index, flat element index)] of every pre-activation with |x| < tol*rms,
+    smallest first.  Call index = order of the LeakyReLUs in forward(): down0..down(L-1), bottleneck, up0..up(L-1)."""
+    rec = []
+    with torch.no_grad():
+        params = _as_torch(params_np, dtype, False)
+        _run_instrumented(lambda: forward(cfg, params, torch.as_tensor(mix_np).to(dtype), True), record=rec, tol=tol)
+    return sorted(rec)
+
+
+def forward_backward_with_flips(cfg, params_np, mix_np, targets_np, flips, dtype=torch.float32):
+    """forward_backward with the LeakyReLU slope of the listed (call index, flat index) elements inverted."""
+    return _run_instrumented(lambda: forward_backward(cfg, params_np, mix_np, targets_np, dtype), flips=flips)
+
+
+def explain_gradient_mismatch(cfg, params_np, mix_np, targets_np, grads_got, tol=1e-3, margin=1e-4, max_candidates=4):
+    """Is `grads_got` (name -> array) the exact gradient for SOME assignment of slopes to the (at most max_candidates)
+    pre-activations within margin*rms of zero?  Returns (flips, worst per-tensor rel-L2) of the best assignment, or
+    (None, worst error without flips) if none brings every tensor within tol."""
+    import itertools
+    cands = [(c, f) for _, c, f in near_zero_preactivations(cfg, params_np, mix_np, margin)][:max_candidates]
+
+    def worst(grads):
+        return max(float(np.linalg.norm(np.asarray(grads_got[n], np.float64) - grads[n]) / max(np.linalg.norm(grads[n]), 1e-30))
+                   for n in grads)
+
+    base = worst(forward_backward(cfg, params_np, mix_np, targets_np)[2])
+    if base <= tol:
+        return (), base
+    for k in range(1, len(cands) + 1):
+        for subset in itertools.combinations(cands, k):
+            w = worst(forward_backward_with_flips(cfg, params_np, mix_np, targets_np, subset)[2])
+            if w <= tol:
+                return tuple(subset), w
+    return None, base
+
+
 def forward_np(cfg, params_np, mix_np, training, dtype=torch.float32):
     with torch.no_grad():
         params = _as_torch(params_np, dtype, False)

@@ -8,6 +8,7 @@ import torch
 
 import Config
 import Evaluate
+import TFCheckpoint
 import Training
 from Models.UnetAudioSeparator import UnetAudioSeparator
 from oracle import wave_unet_oracle as O
@@ -67,17 +68,33 @@ def test_training_entry_point_and_checkpoint(tmp_path):
                               experiment_id=42)
     mc = cfg["model_config"]
     path, sep = Training.train(mc, 42, log_every=0)
-    assert os.path.exists(path) and sep.global_step == 12
-    ck = np.load(path)
-    assert int(ck["global_step"]) == 12
+    # the reference's Saver layout: <base>/<id>/<id>-<global_step>.{index,data-00000-of-00001} + the `checkpoint` state file
+    assert path == os.path.join(str(tmp_path), "42", "42-12") and sep.global_step == 12
+    assert os.path.exists(path + ".index") and os.path.exists(path + ".data-00000-of-00001")
+    assert TFCheckpoint.latest_checkpoint(os.path.dirname(path)) == path
+    ck = TFCheckpoint.read_checkpoint(path)
+    assert int(ck["global_step"]) == 12 and ck["global_step"].dtype == np.int64
     names = [n for n, _, _, _ in sep.param_table()]
-    assert all(n in ck.files for n in names)
+    assert all(n in ck for n in names)
+    assert all("separator_solver/%s/Adam" % n in ck and "separator_solver/%s/Adam_1" % n in ck for n in names)
+    assert len(ck) == 3 * len(names) + 3
     # resume: a fresh separator restored from the checkpoint continues from the same variables / Adam slots
     sep2 = UnetAudioSeparator(mc)
     t_in = int(sep.get_padding(np.array([4, 64, 0]))[0][1])
     Training.load_checkpoint(path, sep2, t_in)
     assert torch.equal(sep2.params.cpu(), sep.params.cpu()) and sep2.global_step == 12
-    assert torch.equal(sep2.adam_v.cpu(), sep.adam_v.cpu())
+    assert torch.equal(sep2.adam_m.cpu(), sep.adam_m.cpu()) and torch.equal(sep2.adam_v.cpu(), sep.adam_v.cpu())
+    # the round-1 .npz container still round-trips
+    legacy = Training.save_checkpoint(str(tmp_path / "legacy.npz"), sep)
+    sep3 = UnetAudioSeparator(mc)
+    Training.load_checkpoint(legacy, sep3, t_in)
+    assert torch.equal(sep3.params.cpu(), sep.params.cpu()) and torch.equal(sep3.adam_v.cpu(), sep.adam_v.cpu())
+    # Predict.py's loader (Evaluate.py:55-57: variables only) gives the same separation as the live separator
+    mix = np.random.default_rng(2).uniform(-0.5, 0.5, size=(300, 2)).astype(np.float32)
+    want = Evaluate.predict_track(mc, sep, mix)
+    got = Evaluate.produce_source_estimates(mc, path, mix)
+    for k in mc["source_names"]:
+        assert np.array_equal(got[k], want[k])
     v = Training.validation_loss(mc, sep, batches=2)
     assert np.isfinite(v) and v > 0
 

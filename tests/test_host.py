@@ -23,7 +23,7 @@ def mc(named=(), **kw):
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(REPO, "include", "wun.h")).read()
-    declared = set(re.findall(r"\b(wun_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(wun_[a-z0-9_]+)\s*\(", header))
     assert declared == set(wun.SYMBOLS), declared ^ set(wun.SYMBOLS)
     lib = ctypes.CDLL(wun.LIB_PATH)
     for s in declared:

@@ -259,3 +259,31 @@ def test_predict_track_tiling():
     short = audio[:T_in // 2]
     ps = O.predict_track(cfg, params, short, T_in, T_out)
     assert ps["vocals"].shape == short.shape
+
+
+def test_mask_flip_analysis_explains_exactly_the_flipped_elements():
+    """The checker used by __graft_entry__.smoke(): a gradient set computed with the LeakyReLU slope of a near-zero
+    pre-activation inverted (what a not-bit-identical forward does) is recognised as such; a scaled tensor is not."""
+    import Config
+    cfg = Config.build_config(["baseline_stereo"], dict(num_layers=4), experiment_id=0)["model_config"]
+    t_in, t_out = O.get_padding(cfg, 64)
+    params = O.init_params(cfg, seed=1337)
+    mix, targets = O.synthetic_batch(cfg, 2, t_in, t_out, seed=1)
+    near = O.near_zero_preactivations(cfg, params, mix, 1e-4)
+    assert near and near == sorted(near) and near[0][0] < 1e-6          # this seed has one within fp32 noise of zero
+    _, _, g0 = O.forward_backward(cfg, params, mix, targets)
+    flip = (near[0][1], near[0][2])
+    _, _, g1 = O.forward_backward_with_flips(cfg, params, mix, targets, [flip])
+    first = list(g0)[0]
+    e = np.linalg.norm(g1[first] - g0[first]) / np.linalg.norm(g0[first])
+    assert 1e-3 < e < 5e-2                                               # one element moves the first-layer kernel gradient by 6.6e-3
+    assert O.explain_gradient_mismatch(cfg, params, mix, targets, g0) == ((), 0.0)
+    flips, w = O.explain_gradient_mismatch(cfg, params, mix, targets, g1)
+    assert flips == (flip,) and w < 1e-6
+    bad = {k: v.copy() for k, v in g0.items()}
+    bad[first] *= 1.01
+    flips, w = O.explain_gradient_mismatch(cfg, params, mix, targets, bad)
+    assert flips is None and w > 5e-3
+    # the instrumentation leaves the oracle untouched
+    _, _, g2 = O.forward_backward(cfg, params, mix, targets)
+    assert all(np.array_equal(g2[k], g0[k]) for k in g0)

@@ -79,13 +79,13 @@ def predict_track(model_config, separator, mix_audio, batch_windows=16, device="
 
 def produce_source_estimates(model_config, load_model, mix_audio, separator=None):
     """Predict.py's work-horse (reference Evaluate.py:161-193 minus file I/O): builds the separator, loads variables
-    from `load_model` (a .npz written by Training.train) and separates `mix_audio`."""
+    from `load_model` (a TF-V2 checkpoint prefix - written by Training.train or by the reference - or a round-1 .npz;
+    reference restore: Evaluate.py:55-57) and separates `mix_audio`."""
     from Models.UnetAudioSeparator import UnetAudioSeparator
     if separator is None:
         separator = UnetAudioSeparator(model_config)
         in_shape, _ = separator.get_padding(np.array([1, model_config["num_frames"], 0]))
         if load_model is not None:
-            ckpt = np.load(load_model)
-            separator.load_variables({k: ckpt[k] for k in ckpt.files if k.startswith("separator/")},
-                                     input_frames=int(in_shape[1]))
+            import TFCheckpoint
+            TFCheckpoint.restore_separator(load_model, separator, int(in_shape[1]), with_optimizer=False)
     return predict_track(model_config, separator, mix_audio)

@@ -1,7 +1,8 @@
 """Prediction entry point (stand-in for /root/reference/Predict.py:1-17):
 
-    python Predict.py with cfg.full_44KHz model_path=checkpoints/123/123-2000.npz input_path=mix.npy [output_path=out]
+    python Predict.py with cfg.full_44KHz model_path=checkpoints/123/123-2000 input_path=mix.npy [output_path=out]
 
+model_path:  a TF-V2 checkpoint prefix (written by Training.py here or by the reference's Saver) or a round-1 .npz.
 input_path: a .npy float array [n_frames, n_channels] already at model_config["expected_sr"] (decoding / resampling
 audio files needs librosa + ffmpeg, which the reference uses at Evaluate.py:172 and which are out of scope here).
 Writes <output_path or input_path>_<source>.npy per source (reference writes _<source>.wav, Evaluate.py:193).

@@ -8,8 +8,8 @@ Keeps the reference's functions and command line (/root/reference/Training.py:24
 train()    one "epoch" of model_config["epoch_it"] steps (reference :103-109): every step is
            forward + MSE (:50-63) + backward + Adam(lr=init_sup_sep_lr) (:70-77), all inside libwun.so; with
            torch.distributed initialised the batch is sharded over the ranks and the flat gradient buffer is
-           all-reduced once per step (NCCL).  Saves an .npz checkpoint of the "separator/..." variables plus Adam
-           slots and global_step (reference Saver, :98,113).
+           all-reduced once per step (NCCL).  Saves a TensorFlow-V2-format checkpoint (TFCheckpoint.py) of the
+           "separator/..." variables, Adam slots and global_step, as the reference's Saver does (:98,113).
 optimise() early stopping on a validation loss + fine-tuning stage with doubled batch and lr 1e-5 (:123-150).
 
 The MUSDB/CCMixter TFRecord pipeline (Datasets.py) is out of scope; batches come from `batch_source`, by default the
@@ -23,6 +23,7 @@ import time
 import numpy as np
 
 import Config
+import TFCheckpoint
 from Models.UnetAudioSeparator import UnetAudioSeparator
 from wun import parallel
 
@@ -53,25 +54,16 @@ class SyntheticBatches(object):
 
 
 def save_checkpoint(path, sep):
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    blob = {n: v.detach().cpu().numpy() for n, v in sep.variables().items()}
-    if sep.adam_m is not None:
-        blob["separator_solver/adam_m"] = sep.adam_m.cpu().numpy()
-        blob["separator_solver/adam_v"] = sep.adam_v.cpu().numpy()
-    blob["global_step"] = np.int64(sep.global_step)
-    np.savez(path, **blob)
-    return path if path.endswith(".npz") else path + ".npz"
+    """saver.save (reference :98,113).  `path` is a TF-V2 checkpoint prefix (<dir>/<experiment_id>-<global_step>, written as
+    <prefix>.index + <prefix>.data-00000-of-00001 + the `checkpoint` state file); a path ending in .npz selects the
+    round-1 numpy container instead.  Returns the path to hand to load_checkpoint / Predict.py."""
+    return TFCheckpoint.save_separator(path, sep)
 
 
 def load_checkpoint(path, sep, input_frames):
-    import torch
-    ckpt = np.load(path)
-    sep.load_variables({k: ckpt[k] for k in ckpt.files if k.startswith("separator/")}, input_frames=input_frames)
-    sep.global_step = int(ckpt["global_step"]) if "global_step" in ckpt.files else 0
-    if "separator_solver/adam_m" in ckpt.files:
-        sep._ensure_training_state()
-        sep.adam_m.copy_(torch.from_numpy(ckpt["separator_solver/adam_m"]))
-        sep.adam_v.copy_(torch.from_numpy(ckpt["separator_solver/adam_v"]))
+    """restorer.restore (reference :92-96): variables, Adam slots and global_step - from a checkpoint written here or by
+    the reference's tf.train.Saver."""
+    TFCheckpoint.restore_separator(path, sep, input_frames, with_optimizer=True)
 
 
 def _to_device(batch, names, device):
@@ -120,7 +112,7 @@ def train(model_config, experiment_id, load_model=None, batch_source=None, sep=N
     path = None
     if rank == 0:
         path = save_checkpoint(os.path.join(model_config["model_base_dir"], str(experiment_id),
-                                            "%s-%d.npz" % (experiment_id, sep.global_step)), sep)
+                                            "%s-%d" % (experiment_id, sep.global_step)), sep)
     return path, sep
 
 

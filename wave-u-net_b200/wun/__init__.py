@@ -18,7 +18,7 @@ SYMBOLS = [
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
     "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step",
     "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
-    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv",
+    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_crc32c",
 ]
 
 
@@ -75,10 +75,21 @@ def _load():
     lib.wun_debug_run_conv.argtypes = [H, ctypes.c_int, ctypes.c_int, VP, VP, I64, VP, I64, VP, P(ctypes.c_double)]
     lib.wun_layer_kernel.argtypes = [H, ctypes.c_int, ctypes.c_int]
     lib.wun_layer_kernel.restype = ctypes.c_char_p
+    lib.wun_crc32c.argtypes = [ctypes.c_uint32, VP, ctypes.c_uint64]
+    lib.wun_crc32c.restype = ctypes.c_uint32
     return lib
 
 
 lib = _load()
+
+
+def crc32c(data, crc=0):
+    """CRC-32C of a bytes-like object / C-contiguous numpy array (host helper of the library, no GPU needed)."""
+    import numpy as np
+    a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    if a.size == 0:
+        return int(crc) & 0xffffffff
+    return int(lib.wun_crc32c(int(crc) & 0xffffffff, a.ctypes.data_as(ctypes.c_void_p), a.size))
 
 
 def check(rc):
