@@ -140,6 +140,10 @@ const char* wun_version(void);
 /* Human-readable plan (layer shapes, live windows, kernel choice per layer) into buf; returns the
  * number of bytes that the full text needs. */
 int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity);
+/* Plan audit (host only, no GPU needed): one text line per tensor-core launch of a forward+backward at `batch` with the
+ * tiling the planner picks (kernel variant, NPAD, tile height, TMEM columns, ring depth, dynamic shared memory, grid) -
+ * tests/test_host.py checks every preset against the hardware limits.  Returns the bytes the full text needs. */
+int64_t wun_debug_plan(const WunHandle* h, int64_t batch, char* buf, int64_t capacity);
 /* Where a saved activation / activation-gradient lives inside the caller's workspace (tests: per-layer parity).
  * Names: dec<i>, odd<i> (live even / odd rows of down block i), z (bottleneck), up<i>, and g_<name> twins. */
 int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,

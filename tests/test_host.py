@@ -130,3 +130,58 @@ def test_compute_entry_points_fail_loudly_without_gpu():
                              ctypes.addressof(buf), 1 << 40, None)
     assert rc == wun.WUN_E_NOGPU
     assert b"no CPU fallback" in wun.lib.wun_last_error()
+
+
+# ------------------------------------------------------------------------------------------------
+# plan audit: every tensor-core launch the planner would issue, against the hardware limits (no GPU needed)
+# ------------------------------------------------------------------------------------------------
+SMEM_LIMIT = {"dense2": 200 * 1024, "sparse4": 220 * 1024, "persistent": 220 * 1024}   # cudaFuncSetAttribute values in kernels_umma.cu
+
+
+def _audit(preset, batch, overrides=None):
+    from Models.UnetAudioSeparator import UnetAudioSeparator
+    mc = Config.build_config([preset], overrides or {}, experiment_id=0)["model_config"]
+    sep = UnetAudioSeparator(mc)
+    return sep.engine(num_frames=mc["num_frames"]).plan_audit(batch)
+
+
+@pytest.mark.parametrize("preset", ["baseline", "baseline_context", "baseline_stereo", "full", "full_multi_instrument", "full_44KHz"])
+@pytest.mark.parametrize("batch", [1, 2, 4, 16, 32])
+def test_planned_tcgen05_launches_respect_hardware_limits(preset, batch):
+    lines = _audit(preset, batch)
+    convs = [d for d in lines if d["op"] == "conv"]
+    wgs = [d for d in lines if d["op"] == "wgrad"]
+    assert convs and wgs
+    pow2 = lambda v: v >= 32 and (v & (v - 1)) == 0
+    for d in convs:
+        assert d["NPAD"] % 16 == 0 and 16 <= d["NPAD"] <= 256 and d["NPAD"] * d["nsplit"] >= d["N"], d
+        assert d["MT"] in (1, 2) and d["rows_alloc"] % 8 == 0 and d["rows_alloc"] >= d["MT"] * 128 + d["span"], d
+        need = d["MT"] * d["NPAD"] * (2 if d["kernel"] == "persistent" else 1) * (2 if d["fuse"] else 1)
+        assert pow2(d["tmem"]) and need <= d["tmem"] <= 512, d
+        if d["kernel"] == "dense2":
+            assert d["tmem"] <= 256, d                     # two CTAs per SM share the 512 TMEM columns
+        assert 1 <= d["TB"] <= 4 and 2 <= d["nbs"] <= 6, d
+        assert d["nteams"] == {"dense2": 2, "sparse4": 4}.get(d["kernel"], d["nteams"]) and d["nteams"] in (2, 3, 4), d
+        assert d["smem"] <= SMEM_LIMIT[d["kernel"]], d
+        assert d["tiles"] >= 1 and d["span"] <= 24, d
+    for d in wgs:
+        assert d["NT"] % 16 == 0 and 16 <= d["NT"] <= 128 and d["NT"] * d["ntiles"] >= min(d["Cp"], d["Cg"]), d
+        assert d["mtiles"] * 128 >= max(d["Cp"], d["Cg"]), d
+        assert d["taps_per_cta"] * d["tapsets"] >= d["ntaps"] and 1 <= d["taps_per_cta"] <= 8, d
+        assert pow2(d["tmem"]) and d["taps_per_cta"] * d["NT"] <= d["tmem"] <= 512, d
+        assert d["nstages"] in (2, 3) and d["smem"] <= 200 * 1024, d
+        gx, gy, gz = [int(v) for v in d["grid"].split("x")]
+        assert gx >= 1 and 1 <= gy <= 65535 and 1 <= gz <= 65535 and d["chunks_per_cta"] >= 1 and d["n_ctas_x"] <= gx, d
+
+
+def test_plan_audit_matches_the_measured_configuration():
+    """The tiling DESIGN.md / profiles/ describe for the benchmark (M4, batch 16): persistent 256-row tiles for down1-3,
+    two CTAs per SM in the middle, channel-split sparse launches for the deep layers."""
+    lines = _audit("baseline_stereo", 16)
+    fwd = {d["layer"]: d for d in lines if d["op"] == "conv" and d["pass"] == 0}
+    assert [fwd[i]["kernel"] for i in (1, 2, 3)] == ["persistent"] * 3
+    assert fwd[3]["NPAD"] == 96 and fwd[3]["MT"] == 2 and fwd[3]["tmem"] == 512 and fwd[3]["nteams"] == 3
+    assert fwd[4]["kernel"] == "dense2" and fwd[8]["kernel"] == "sparse4"
+    assert 0 not in fwd                                                       # the first layer (C_in = 2) is a CUDA-core kernel
+    assert len([d for d in lines if d["op"] == "conv"]) == 60                # the launch list of profiles/: 13 + 13 + 34
+    assert len({d["layer"] for d in lines if d["op"] == "wgrad"}) == 24

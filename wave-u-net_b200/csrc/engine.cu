@@ -75,6 +75,7 @@ struct WunHandle {
     size_t arena_sum = 0;                // total pack bytes of one forward+backward (dry run)
     cudaEvent_t packs_event = nullptr;
     bool packs_pending = false;          // main stream has not yet waited for the hoisted packs
+    std::vector<std::string>* audit = nullptr;   // dry runs: one line per tensor-core launch (wun_debug_plan)
     // per-call state
     bool dry = false;
     int64_t launches = 0;
@@ -220,7 +221,32 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
     if (use_umma) {
         if (h->phase != 1) h->launches += 2;    // weight pack + conv (counted once)
-        if (h->dry) { h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); h->arena_sum += ch.pack_bytes; return WUN_OK; }
+        if (h->dry) {
+            h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); h->arena_sum += ch.pack_bytes;
+            if (h->audit) {
+                long long tiles = 0; int max_rows = 0, span = 0;
+                for (int q = 0; q < L.ncls; ++q) {
+                    const int rows = L.cls[q].m_hi - L.cls[q].m_lo;
+                    tiles += (long long)((rows + ch.MT * 128 - 1) / (ch.MT * 128)) * ch.nsplit * L.batch;
+                    max_rows = std::max(max_rows, rows);
+                    int t = L.cls[q].term_begin;
+                    while (t < L.cls[q].term_end) {
+                        int t1 = t, dmin = L.terms[t].d, dmax = dmin;
+                        while (t1 < L.cls[q].term_end && L.terms[t1].plane == L.terms[t].plane) {
+                            dmin = std::min(dmin, L.terms[t1].d); dmax = std::max(dmax, L.terms[t1].d); ++t1; }
+                        span = std::max(span, dmax - dmin); t = t1;
+                    }
+                }
+                char line[512];
+                snprintf(line, sizeof(line), "conv layer=%d pass=%d kernel=%s N=%d NPAD=%d nsplit=%d MT=%d rows_alloc=%d span=%d tmem=%d "
+                         "TB=%d nbs=%d nteams=%d fuse=%d tiles=%lld max_rows=%d smem=%zu pack_bytes=%zu",
+                         h->cur_layer, h->cur_pass, ch.persistent ? "persistent" : (ch.nteams == 4 ? "sparse4" : "dense2"), L.N,
+                         ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, tiles,
+                         max_rows, umma_choice_smem_bytes(ch), ch.pack_bytes);
+                h->audit->push_back(line);
+            }
+            return WUN_OK;
+        }
         uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total) + h->arena_cur;
         h->arena_cur += ch.pack_bytes;
         UmmaLaunch U; UmmaPackLaunch PL;
@@ -389,6 +415,17 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     }
     const size_t slot = (size_t)h->cur_layer * 3 + 2;
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
+    if (h->dry && h->audit && use_umma) {
+        for (int g = 0; g < U.ngroups; ++g) {
+            const WgGroup& G = U.grp[g];
+            char line[512];
+            snprintf(line, sizeof(line), "wgrad layer=%d group=%d Cp=%d Cg=%d swap=%d NT=%d mtiles=%d ntiles=%d ntaps=%d taps_per_cta=%d "
+                     "tapsets=%d tmem=%d chunks_per_cta=%d n_ctas_x=%d grid=%dx%dx%d nstages=%d smem=%zu",
+                     h->cur_layer, g, G.P.C, G.G.C, G.swap, G.NT, G.n_mtiles, G.n_ntiles, G.ntaps, G.taps_per_cta, G.n_tapsets,
+                     G.tmem_cols, G.chunks_per_cta, G.n_ctas_x, U.grid_x, U.grid_y, U.grid_z, U.nstages, umma_wgrad_smem_bytes(U));
+            h->audit->push_back(line);
+        }
+    }
     if (h->phase == 1) return WUN_OK;
     if (use_umma) {
         ++h->launches;
@@ -743,6 +780,28 @@ int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity) {
     for (size_t i = 0; i + 2 < h->kernel_used.size(); i += 3)
         s += h->kernel_used[i] + "/" + h->kernel_used[i + 1] + "/" + h->kernel_used[i + 2] + " ";
     s += "\n";
+    if (buf && capacity > 0) {
+        int64_t n = std::min<int64_t>(capacity - 1, (int64_t)s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int64_t wun_debug_plan(const WunHandle* hc, int64_t batch, char* buf, int64_t capacity) {
+    WunHandle* h = const_cast<WunHandle*>(hc);
+    if (!h || batch < 1) return -1;
+    std::vector<std::string> lines;
+    const size_t keep_sum = h->arena_sum, keep_max = h->arena_bytes;
+    const std::vector<std::string> keep_used = h->kernel_used;
+    if (begin_call(h, nullptr, nullptr, batch, true, nullptr, 0, nullptr, true) != WUN_OK) return -1;
+    h->audit = &lines; h->phase = 0;
+    run_forward(h, nullptr, nullptr, nullptr, 1);
+    run_backward(h, nullptr, nullptr, 1.f);
+    h->audit = nullptr;
+    h->arena_sum = keep_sum; h->arena_bytes = keep_max; h->kernel_used = keep_used;
+    std::string s;
+    for (const auto& l : lines) { s += l; s += "\n"; }
     if (buf && capacity > 0) {
         int64_t n = std::min<int64_t>(capacity - 1, (int64_t)s.size());
         memcpy(buf, s.data(), n);

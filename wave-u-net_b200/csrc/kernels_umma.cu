@@ -1025,6 +1025,16 @@ static size_t wgrad_smem_bytes(const UmmaWgradLaunch& L) {
     return L.nstages * stage + (2 * kWgStagesMax + 1) * 8 + 16;
 }
 
+size_t umma_wgrad_smem_bytes(const UmmaWgradLaunch& L) { return wgrad_smem_bytes(L); }
+
+size_t umma_choice_smem_bytes(const UmmaChoice& ch) {
+    UmmaLaunch U;
+    memset(&U, 0, sizeof(U));
+    U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc; U.TB = ch.TB; U.nbs = ch.nbs;
+    U.nteams = ch.nteams; U.persistent = ch.persistent;
+    return ch.persistent ? umma_pers_smem_bytes(U) : umma_smem_bytes(U);
+}
+
 bool umma_plan_wgrad(UmmaWgradLaunch* L) {
     if (L->ngroups < 1 || L->ngroups > kWgMaxGroups) return false;
     long long work = 0;        // ~MMA work units of the launch, to size the K ranges

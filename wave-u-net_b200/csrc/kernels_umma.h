@@ -108,6 +108,9 @@ cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream);
 bool umma_plan_wgrad(UmmaWgradLaunch* L);
 
 size_t umma_smem_bytes(const UmmaLaunch& L);
+// dynamic shared memory the kernel variant chosen in `ch` is launched with / of a planned wgrad launch (plan audit)
+size_t umma_choice_smem_bytes(const UmmaChoice& ch);
+size_t umma_wgrad_smem_bytes(const UmmaWgradLaunch& L);
 cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream);
 cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream);
 // Decide whether / how a generic plane-convolution launch runs on tcgen05; false = not eligible (SIMT).

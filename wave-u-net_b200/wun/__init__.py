@@ -18,7 +18,7 @@ SYMBOLS = [
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
     "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step",
     "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
-    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_crc32c",
+    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_crc32c", "wun_debug_plan",
 ]
 
 
@@ -75,6 +75,8 @@ def _load():
     lib.wun_debug_run_conv.argtypes = [H, ctypes.c_int, ctypes.c_int, VP, VP, I64, VP, I64, VP, P(ctypes.c_double)]
     lib.wun_layer_kernel.argtypes = [H, ctypes.c_int, ctypes.c_int]
     lib.wun_layer_kernel.restype = ctypes.c_char_p
+    lib.wun_debug_plan.argtypes = [H, I64, ctypes.c_char_p, I64]
+    lib.wun_debug_plan.restype = I64
     lib.wun_crc32c.argtypes = [ctypes.c_uint32, VP, ctypes.c_uint64]
     lib.wun_crc32c.restype = ctypes.c_uint32
     return lib
@@ -177,6 +179,23 @@ class Engine(object):
         buf = ctypes.create_string_buffer(int(n))
         lib.wun_describe(self._h, buf, n)
         return buf.value.decode()
+
+    def plan_audit(self, batch):
+        """[dict] - one per tensor-core launch of a training step at `batch` (planner decisions; no GPU needed)."""
+        n = lib.wun_debug_plan(self._h, int(batch), None, 0)
+        if n < 0:
+            raise RuntimeError("wun_debug_plan failed: %s" % lib.wun_last_error().decode())
+        buf = ctypes.create_string_buffer(int(n))
+        lib.wun_debug_plan(self._h, int(batch), buf, n)
+        out = []
+        for line in buf.value.decode().splitlines():
+            parts = line.split()
+            d = {"op": parts[0]}
+            for kv in parts[1:]:
+                k, v = kv.split("=", 1)
+                d[k] = int(v) if v.lstrip("-").isdigit() else v
+            out.append(d)
+        return out
 
     def layer_kernel(self, layer, pass_):
         return lib.wun_layer_kernel(self._h, int(layer), int(pass_)).decode()
