@@ -224,24 +224,29 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
         if (h->dry) {
             h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); h->arena_sum += ch.pack_bytes;
             if (h->audit) {
-                long long tiles = 0; int max_rows = 0, span = 0;
+                long long tiles = 0, mmas = 0; int max_rows = 0, span = 0;
                 for (int q = 0; q < L.ncls; ++q) {
                     const int rows = L.cls[q].m_hi - L.cls[q].m_lo;
-                    tiles += (long long)((rows + ch.MT * 128 - 1) / (ch.MT * 128)) * ch.nsplit * L.batch;
+                    const long long tq = (long long)((rows + ch.MT * 128 - 1) / (ch.MT * 128)) * ch.nsplit * L.batch;
+                    tiles += tq;
                     max_rows = std::max(max_rows, rows);
                     int t = L.cls[q].term_begin;
+                    long long ksteps = 0;                       // (16-channel chunk, tap) pairs of one tile of this class
                     while (t < L.cls[q].term_end) {
                         int t1 = t, dmin = L.terms[t].d, dmax = dmin;
                         while (t1 < L.cls[q].term_end && L.terms[t1].plane == L.terms[t].plane) {
                             dmin = std::min(dmin, L.terms[t1].d); dmax = std::max(dmax, L.terms[t1].d); ++t1; }
-                        span = std::max(span, dmax - dmin); t = t1;
+                        span = std::max(span, dmax - dmin);
+                        ksteps += (long long)((L.planes[L.terms[t].plane].C + 15) / 16) * (t1 - t);
+                        t = t1;
                     }
+                    mmas += tq * ch.MT * ksteps * (ch.fuse ? 2 : 3);
                 }
                 char line[512];
                 snprintf(line, sizeof(line), "conv layer=%d pass=%d kernel=%s N=%d NPAD=%d nsplit=%d MT=%d rows_alloc=%d span=%d tmem=%d "
-                         "TB=%d nbs=%d nteams=%d fuse=%d tiles=%lld max_rows=%d smem=%zu pack_bytes=%zu",
+                         "TB=%d nbs=%d nteams=%d fuse=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu",
                          h->cur_layer, h->cur_pass, ch.persistent ? "persistent" : (ch.nteams == 4 ? "sparse4" : "dense2"), L.N,
-                         ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, tiles,
+                         ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, tiles, mmas,
                          max_rows, umma_choice_smem_bytes(ch), ch.pack_bytes);
                 h->audit->push_back(line);
             }
@@ -420,9 +425,9 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
             const WgGroup& G = U.grp[g];
             char line[512];
             snprintf(line, sizeof(line), "wgrad layer=%d group=%d Cp=%d Cg=%d swap=%d NT=%d mtiles=%d ntiles=%d ntaps=%d taps_per_cta=%d "
-                     "tapsets=%d tmem=%d chunks_per_cta=%d n_ctas_x=%d grid=%dx%dx%d nstages=%d smem=%zu",
+                     "tapsets=%d tmem=%d chunks_per_cta=%d n_ctas_x=%d chunks=%lld grid=%dx%dx%d nstages=%d smem=%zu",
                      h->cur_layer, g, G.P.C, G.G.C, G.swap, G.NT, G.n_mtiles, G.n_ntiles, G.ntaps, G.taps_per_cta, G.n_tapsets,
-                     G.tmem_cols, G.chunks_per_cta, G.n_ctas_x, U.grid_x, U.grid_y, U.grid_z, U.nstages, umma_wgrad_smem_bytes(U));
+                     G.tmem_cols, G.chunks_per_cta, G.n_ctas_x, (long long)U.batch * G.chunks_per_batch, U.grid_x, U.grid_y, U.grid_z, U.nstages, umma_wgrad_smem_bytes(U));
             h->audit->push_back(line);
         }
     }
