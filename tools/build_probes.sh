@@ -6,4 +6,5 @@ F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -diag-suppre
 nvcc $F -o tools/umma_probe tools/umma_probe.cu
 nvcc $F -DWUN_UMMA_TIMING -o tools/umma_probe_timing tools/umma_probe.cu
 nvcc $F -o tools/umma_layout_bench tools/umma_layout_bench.cu
+nvcc $F -o tools/presplit_probe tools/presplit_probe.cu
 echo probes built
