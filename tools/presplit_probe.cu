@@ -67,8 +67,19 @@ __global__ void split_plane_kernel(PlaneView P, int B, uint8_t* out, int nchunk,
 constexpr int kPsSlabStages = 4;
 constexpr int kPsThreads = 256;
 
+// split OUTPUT storage (what the next layer's slab loader wants): per class, row m of the class goes to parity plane m & 1
+// at index m >> 1:  [class][parity][batch][16-channel chunk][hi a0 | hi a1 | lo a0 | lo a1][row][16 B]
+struct SplitOut {
+    uint8_t* base[kMaxClasses][2];
+    long long bstride, cstride, pstride;
+};
+
+// SPLIT_OUT = false: fp32 row-major output through the engine's shared-memory staged epilogue.
+// SPLIT_OUT = true : thread = accumulator row writes hi/lo bf16 atoms straight from registers (no staging tile).
+template <bool SPLIT_OUT>
 __global__ void __launch_bounds__(kPsThreads, 1) presplit_conv_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles,
-                                                                          const __grid_constant__ SplitPlanes XS) {
+                                                                          const __grid_constant__ SplitPlanes XS,
+                                                                          const __grid_constant__ SplitOut YS) {
     constexpr int NS = kPsSlabStages;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -217,6 +228,37 @@ __global__ void __launch_bounds__(kPsThreads, 1) presplit_conv_persistent(const 
             const int n0 = tc.split * NPAD;
             mbar_wait(BAR(ACC_FULL + buf), (k >> 1) & 1);
             tc_fence_after();
+            if (SPLIT_OUT) {
+                for (int mt = 0; mt < L.MT; ++mt) {
+                    const int m = tc.m_base + mt * 128 + q4 * 32 + lane;
+                    const bool row_ok = m < K.out.m_hi;
+                    for (int cb = 0; cb < NPAD; cb += 16) {
+                        if (n0 + cb >= ((L.N + 15) & ~15)) break;
+                        __syncwarp();
+                        float v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)(mt * NPAD + cb), v);
+                        if (!row_ok) continue;
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float y0 = v[2 * j] + bias_s[n0 + cb + 2 * j], y1 = v[2 * j + 1] + bias_s[n0 + cb + 2 * j + 1];
+                            y0 = fmaxf(0.2f * y0, y0); y1 = fmaxf(0.2f * y1, y1);
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[j] = pack_bf16x2(y0 - __bfloat162float(h0), y1 - __bfloat162float(h1));
+                        }
+                        uint8_t* o = YS.base[tc.cls][m & 1] + (long long)tc.b * YS.bstride + (long long)((n0 + cb) >> 4) * YS.cstride +
+                                     (long long)(m >> 1) * 16;
+                        *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(o + YS.pstride) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<uint4*>(o + 2 * YS.pstride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(o + 3 * YS.pstride) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(BAR(ACC_EMPTY + buf));
+                continue;
+            }
             const int c0_last = min((NPAD - 1) / CW, (L.N - n0 - 1) / CW) * CW;
             for (int mt = 0; mt < L.MT; ++mt) {
                 for (int c0 = 0; c0 < NPAD; c0 += CW) {
@@ -379,15 +421,45 @@ static void run_case(const char* name, Problem p, bool check, int timing_iters) 
     for (int q = 0; q < LB.ncls; ++q) total += ((LB.cls[q].out.m_hi - LB.cls[q].out.m_lo + LB.MT * 128 - 1) / (LB.MT * 128)) * LB.batch;
     total *= LB.nsplit;
     const size_t smem_b = presplit_smem_bytes(LB);
-    CK(cudaFuncSetAttribute(presplit_conv_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CK(cudaFuncSetAttribute(presplit_conv_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     printf("[%s] bulk-fed variant: MT=%d rows_alloc=%d tmem=%d nbs=%d slab stages=%d smem=%zu tiles=%d\n", name, LB.MT, LB.rows_alloc,
            LB.tmem_cols, LB.nbs, kPsSlabStages, smem_b, total);
     const int grid = total < 148 ? total : 148;
+    // split output arrays (class q, parity): rows of class q = [m_lo, m_hi) -> index m >> 1
+    SplitOut YS;
+    memset(&YS, 0, sizeof(YS));
+    const int nchunk_o = (p.Cout + 15) / 16;
+    const int Rpad_o = (max(Td, mo_hi) + 1) / 2 + 8;
+    YS.pstride = (long long)Rpad_o * 16; YS.cstride = 4 * YS.pstride; YS.bstride = nchunk_o * YS.cstride;
+    const size_t ys_bytes = (size_t)p.B * YS.bstride;
+    for (int q = 0; q < 2; ++q)
+        for (int par = 0; par < 2; ++par) { CK(cudaMalloc(&YS.base[q][par], ys_bytes)); CK(cudaMemset(YS.base[q][par], 0, ys_bytes)); }
+    CK(cudaFuncSetAttribute(presplit_conv_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
 
-    auto check_outputs = [&](const char* which) {
+    auto check_outputs = [&](const char* which, bool from_split = false) {
         std::vector<float> dec((size_t)p.B * Td * p.Cout), odd((size_t)p.B * (n_odd + 1) * p.Cout);
-        CK(cudaMemcpy(dec.data(), ddec, dec.size() * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(odd.data(), dodd, odd.size() * 4, cudaMemcpyDeviceToHost));
+        if (!from_split) {
+            CK(cudaMemcpy(dec.data(), ddec, dec.size() * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(odd.data(), dodd, odd.size() * 4, cudaMemcpyDeviceToHost));
+        } else {
+            // rebuild fp32 rows from the hi/lo atom planes
+            std::vector<uint16_t> buf(ys_bytes / 2);
+            for (int q = 0; q < 2; ++q)
+                for (int par = 0; par < 2; ++par) {
+                    CK(cudaMemcpy(buf.data(), YS.base[q][par], ys_bytes, cudaMemcpyDeviceToHost));
+                    const int m_lo = (q == 0) ? 0 : mo_lo, m_hi = (q == 0) ? Td : mo_hi;
+                    for (int b = 0; b < p.B; ++b)
+                        for (int m = m_lo + ((m_lo & 1) != par); m < m_hi; m += 2)
+                            for (int n = 0; n < p.Cout; ++n) {
+                                const size_t e0 = ((size_t)b * YS.bstride + (size_t)(n >> 4) * YS.cstride) / 2;
+                                const size_t at = (size_t)((n >> 3) & 1) * (YS.pstride / 2) + (size_t)(m >> 1) * 8 + (n & 7);
+                                auto f = [&](uint16_t h) { uint32_t u = (uint32_t)h << 16; float r; memcpy(&r, &u, 4); return r; };
+                                const float val = f(buf[e0 + at]) + f(buf[e0 + 2 * (YS.pstride / 2) + at]);
+                                if (q == 0) dec[((size_t)b * Td + m) * p.Cout + n] = val;
+                                else odd[((size_t)b * n_odd + (m - mo_lo)) * p.Cout + n] = val;
+                            }
+                }
+        }
         std::vector<float> xh(x.size()), xl(x.size()), wh(w.size()), wl(w.size());
         for (size_t i = 0; i < x.size(); ++i) { xh[i] = bf16_round(x[i]); xl[i] = bf16_round(x[i] - xh[i]); }
         for (size_t i = 0; i < w.size(); ++i) { wh[i] = bf16_round(w[i]); wl[i] = bf16_round(w[i] - wh[i]); }
@@ -438,17 +510,24 @@ static void run_case(const char* name, Problem p, bool check, int timing_iters) 
     if (check) check_outputs("engine");
     // (b) bulk-fed
     CK(cudaMemset(ddec, 0xFF, dec_bytes)); CK(cudaMemset(dodd, 0xFF, odd_bytes));
-    presplit_conv_persistent<<<grid, kPsThreads, smem_b>>>(LB, total, XS);
+    presplit_conv_persistent<false><<<grid, kPsThreads, smem_b>>>(LB, total, XS, YS);
     { cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("[%s] bulk-fed KERNEL ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); } }
     if (check) check_outputs("bulk-fed");
+    // (c) bulk-fed + split-format epilogue
+    presplit_conv_persistent<true><<<grid, kPsThreads, smem_b>>>(LB, total, XS, YS);
+    { cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("[%s] bulk-fed/split-out KERNEL ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); } }
+    if (check) check_outputs("split-out", true);
     if (timing_iters > 0) {
         time_it("engine", [&]() { CK(launch_plane_conv_umma(L, 0)); });
-        time_it("bulk-fed", [&]() { presplit_conv_persistent<<<grid, kPsThreads, smem_b>>>(LB, total, XS); });
+        time_it("bulk-fed", [&]() { presplit_conv_persistent<false><<<grid, kPsThreads, smem_b>>>(LB, total, XS, YS); });
+        time_it("split-out", [&]() { presplit_conv_persistent<true><<<grid, kPsThreads, smem_b>>>(LB, total, XS, YS); });
         time_it("split x2", [&]() { for (int par = 0; par < 2; ++par) split_plane_kernel<<<148 * 8, 256>>>(CL.planes[par], p.B, dxs[par], nchunk, Rpad); });
     }
     cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(ddec); cudaFree(dodd); cudaFree(arena);
     for (int par = 0; par < 2; ++par) cudaFree(dxs[par]);
+    for (int q = 0; q < 2; ++q) for (int par = 0; par < 2; ++par) cudaFree(YS.base[q][par]);
 }
 
 int main(int argc, char** argv) {
