@@ -185,3 +185,22 @@ def test_plan_audit_matches_the_measured_configuration():
     assert 0 not in fwd                                                       # the first layer (C_in = 2) is a CUDA-core kernel
     assert len([d for d in lines if d["op"] == "conv"]) == 60                # the launch list of profiles/: 13 + 13 + 34
     assert len({d["layer"] for d in lines if d["op"] == "wgrad"}) == 24
+
+
+def test_long_window_mode_plans_and_amortises_the_context():
+    """any num_frames builds a plan (engines are cached per input length); the 131054-frame context of M4 is
+    paid once per window, so live FLOPs per OUTPUT frame fall as the window grows."""
+    from oracle import wave_unet_oracle as O
+    mc = Config.build_config(["baseline_stereo"], experiment_id=0)["model_config"]
+    per_frame = []
+    for nf in (16384, 65536, 262144):
+        t_in, t_out = wun.get_padding(wun.config_from_model_config(mc), nf)
+        assert (t_in, t_out) == O.get_padding(mc, nf)
+        assert t_in - t_out == 147443 - 16389                 # the context is independent of the window length
+        eng = wun.Engine(wun.config_from_model_config(mc), num_frames=nf)
+        assert eng.T_in == t_in and eng.T_out == t_out
+        per_frame.append(eng.forward_flops(1) / t_out)
+        audit = eng.plan_audit(2)
+        assert all(d["smem"] <= 220 * 1024 for d in audit)
+    assert per_frame[0] > 1.5 * per_frame[1] > 1.5 * per_frame[2] * 1.0
+    assert abs(per_frame[0] - 849e3) / 849e3 < 0.01           # SURVEY 8d: 849 kFLOP per output frame at the default window
