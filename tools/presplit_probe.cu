@@ -10,7 +10,8 @@
 //
 // The probe runs the SAME down-block shaped problem through (a) the engine's kernel (umma_run_conv path) and (b) the
 // bulk-fed variant below (same weight packs, same descriptors, same double-buffered-TMEM epilogue), checks both against
-// the CPU reference and prints both times.  Usage (under gpurun):   tools/presplit_probe [small|down1|down2|down3|down4]
+// the CPU reference and prints both times.  Usage (under gpurun):   tools/presplit_probe [all|small|down1..down4|wsmall|wdown1|wdown2|wdown3|wdown5]
+// (the w* cases do the same for the wgrad kernel: presplit_wgrad_kernel vs wgrad_umma_kernel)
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -530,6 +531,315 @@ static void run_case(const char* name, Problem p, bool check, int timing_iters) 
     for (int q = 0; q < 2; ++q) for (int par = 0; par < 2; ++par) cudaFree(YS.base[q][par]);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bulk-fed wgrad: the engine's wgrad_umma_kernel with the 8-12 converter warps replaced by ONE loader thread that pulls
+// the hi/lo atom planes of both operands from split storage (chunk of 64 reduction rows per stage).  Channel atoms past
+// the tensor's width are zero-filled in shared memory once.  MMA issue and the red.global epilogue are the engine's.
+//   warp 0 loader, warp 1 TMEM alloc + MMA issue, warps 4-11 epilogue (lane quarter = warp & 3, taps split by (warp-4)>>2)
+// ------------------------------------------------------------------------------------------------
+struct WgSplit {
+    const uint8_t* P[kWgMaxGroups];      // split storage of the activation plane of every group (plane row r at index r)
+    const uint8_t* G[kWgMaxGroups];      // split storage of the gradient plane (row m at index m)
+    long long p_bstride, p_cstride, p_pstride;
+    long long g_bstride[kWgMaxGroups], g_cstride[kWgMaxGroups], g_pstride[kWgMaxGroups];
+};
+
+constexpr int kPwThreads = 384;
+
+__global__ void __launch_bounds__(kPwThreads, 1) presplit_wgrad_kernel(const __grid_constant__ UmmaWgradLaunch L,
+                                                                       const __grid_constant__ WgSplit S) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int gi = 0;
+    while (gi + 1 < L.ngroups && (int)blockIdx.z >= L.grp[gi + 1].z0) ++gi;
+    const WgGroup& Gp = L.grp[gi];
+    const int tapset = blockIdx.z - Gp.z0;
+    if ((int)blockIdx.x >= Gp.n_ctas_x || (int)blockIdx.y >= Gp.n_mtiles * Gp.n_ntiles) return;
+    const int total_chunks = L.batch * Gp.chunks_per_batch;
+    const int g0 = blockIdx.x * Gp.chunks_per_cta;
+    const int g1 = min(g0 + Gp.chunks_per_cta, total_chunks);
+    if (g0 >= g1) return;
+    const int mtile = blockIdx.y / Gp.n_ntiles, ntile = blockIdx.y % Gp.n_ntiles;
+    const int tap0 = tapset * Gp.taps_per_cta;
+    const int ntap = min(Gp.taps_per_cta, Gp.ntaps - tap0);
+    const int NT = Gp.NT, swap = Gp.swap;
+    const PlaneView& SA = swap ? Gp.G : Gp.P;
+    const PlaneView& SB = swap ? Gp.P : Gp.G;
+    const int ca0 = mtile * 128, cb0 = ntile * NT;
+    const int rowsA = swap ? kWgRK : kWgRK + kWgSpan;
+    const int rowsB = swap ? kWgRK + kWgSpan : kWgRK;
+    const uint32_t planeA = 16u * rowsA, planeB = 16u * rowsB;
+    const int atomsA = 16, atomsB = NT / 8;
+    const uint32_t bytesA = 2u * atomsA * planeA, bytesB = 2u * atomsB * planeB;
+    const uint32_t stage_bytes = bytesA + bytesB;
+    int dmin = Gp.d[tap0];
+    for (int t = 1; t < ntap; ++t) dmin = min(dmin, Gp.d[tap0 + t]);
+
+    const int nst = L.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int FULL = 0, EMPTY = kWgStagesMax, ACC = 2 * kWgStagesMax;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC + 1);
+    if (tid == 0) {
+        for (int i = 0; i < kWgStagesMax; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+        mbar_init(BAR(ACC), 1);
+        fence_barrier_init();
+    }
+    // channel chunks the tensors really have inside this tile; the rest of the operand tile stays zero
+    const int chunksA = max(0, min(8, (SA.C - ca0 + 15) / 16)), chunksB = max(0, min(NT / 16, (SB.C - cb0 + 15) / 16));
+    for (uint32_t i = tid; i < (uint32_t)nst * stage_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    if (warp == 1) tmem_alloc(smem_u32(tmem_holder), Gp.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const int nchunks = g1 - g0;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint8_t* baseA = swap ? S.G[gi] : S.P[gi];
+            const uint8_t* baseB = swap ? S.P[gi] : S.G[gi];
+            const long long a_bs = swap ? S.g_bstride[gi] : S.p_bstride, a_cs = swap ? S.g_cstride[gi] : S.p_cstride,
+                            a_ps = swap ? S.g_pstride[gi] : S.p_pstride;
+            const long long b_bs = swap ? S.p_bstride : S.g_bstride[gi], b_cs = swap ? S.p_cstride : S.g_cstride[gi],
+                            b_ps = swap ? S.p_pstride : S.g_pstride[gi];
+            const uint32_t tx = (uint32_t)(chunksA * 4) * planeA + (uint32_t)(chunksB * 4) * planeB;
+            for (int ci = 0; ci < nchunks; ++ci) {
+                const int st = ci % nst;
+                const int gch = g0 + ci;
+                const int b = gch / Gp.chunks_per_batch;
+                const int rc = Gp.m_lo + (gch % Gp.chunks_per_batch) * kWgRK;      // first G row of the chunk
+                const int rowA = swap ? rc : rc + dmin, rowB = swap ? rc + dmin : rc;
+                mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + st), tx);
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
+                for (int g = 0; g < chunksA; ++g) {
+                    const uint8_t* src = baseA + (long long)b * a_bs + (long long)(ca0 / 16 + g) * a_cs + (long long)rowA * 16;
+                    bulk_g2s(sa + (uint32_t)(2 * g) * planeA, src, planeA, BAR(FULL + st));                               // hi atom 2g
+                    bulk_g2s(sa + (uint32_t)(2 * g + 1) * planeA, src + a_ps, planeA, BAR(FULL + st));                    // hi atom 2g+1
+                    bulk_g2s(sa + (uint32_t)(atomsA + 2 * g) * planeA, src + 2 * a_ps, planeA, BAR(FULL + st));           // lo atom 2g
+                    bulk_g2s(sa + (uint32_t)(atomsA + 2 * g + 1) * planeA, src + 3 * a_ps, planeA, BAR(FULL + st));       // lo atom 2g+1
+                }
+                for (int g = 0; g < chunksB; ++g) {
+                    const uint8_t* src = baseB + (long long)b * b_bs + (long long)(cb0 / 16 + g) * b_cs + (long long)rowB * 16;
+                    bulk_g2s(sb + (uint32_t)(2 * g) * planeB, src, planeB, BAR(FULL + st));
+                    bulk_g2s(sb + (uint32_t)(2 * g + 1) * planeB, src + b_ps, planeB, BAR(FULL + st));
+                    bulk_g2s(sb + (uint32_t)(atomsB + 2 * g) * planeB, src + 2 * b_ps, planeB, BAR(FULL + st));
+                    bulk_g2s(sb + (uint32_t)(atomsB + 2 * g + 1) * planeB, src + 3 * b_ps, planeB, BAR(FULL + st));
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t accum = 0;
+            for (int ci = 0; ci < nchunks; ++ci) {
+                const int st = ci % nst;
+                mbar_wait(BAR(FULL + st), (ci / nst) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
+                const uint64_t a_hi0 = umma_desc(sa, 128, planeA), a_lo0 = umma_desc(sa + atomsA * planeA, 128, planeA);
+                const uint64_t b_hi0 = umma_desc(sb, 128, planeB), b_lo0 = umma_desc(sb + atomsB * planeB, 128, planeB);
+                for (int t = 0; t < ntap; ++t) {
+                    const uint64_t shift = (uint64_t)(uint32_t)(Gp.d[tap0 + t] - dmin);
+                    const uint64_t sha = swap ? 0ull : shift, shb = swap ? shift : 0ull;
+                    const uint32_t td = tmem_base + (uint32_t)(t * NT);
+#pragma unroll
+                    for (int ks = 0; ks < kWgRK / 16; ++ks) {
+                        const uint64_t koff = (uint64_t)(16 * ks);
+                        const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
+                        const uint64_t b_hi = b_hi0 + shb + koff, b_lo = b_lo0 + shb + koff;
+                        umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
+                        umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                    }
+                }
+                accum = 1u;
+                umma_commit(BAR(EMPTY + st));
+            }
+            umma_commit(BAR(ACC));
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        mbar_wait(BAR(ACC), 0);
+        tc_fence_after();
+        const int q4 = warp & 3;
+        const int m = ca0 + q4 * 32 + lane;
+        const bool m_ok = m < SA.C;
+        const int sM = swap ? L.w_sg : L.w_sp, sN = swap ? L.w_sp : L.w_sg;
+        for (int t = (warp - 4) >> 2; t < ntap; t += 2) {
+            float* dst_t = L.dW + (long long)Gp.woff[tap0 + t] + (long long)m * sM;
+            for (int cb = 0; cb < NT; cb += 16) {
+                if (cb0 + cb >= SB.C) break;
+                __syncwarp();
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * NT + cb), v);
+                if (!m_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= L.scale;
+                float* dst = dst_t + (long long)(cb0 + cb) * sN;
+                if (sN == 1 && cb0 + cb + 16 <= SB.C && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (cb0 + cb + j < SB.C) atomicAdd(dst + (long long)j * sN, v[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Gp.tmem_cols);
+    }
+}
+
+static void run_wgrad(const char* name, Problem p, bool check, int timing_iters) {
+    const int To = p.T - p.fs + 1, Td = (To + 1) / 2;
+    const int mo_lo = p.cs / 2, mo_hi = (p.cs + p.U) / 2, n_odd = mo_hi - mo_lo;
+    std::vector<float> x((size_t)p.B * p.T * p.Cin), gdec((size_t)p.B * Td * p.Cout), godd((size_t)p.B * (n_odd + 1) * p.Cout);
+    unsigned s = 777u;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+    for (auto& v : x) v = rnd();
+    for (auto& v : gdec) v = rnd() * 1e-3f;
+    for (auto& v : godd) v = rnd() * 1e-3f;
+    float *dx, *dgd, *dgo, *ddw;
+    const size_t wn = (size_t)p.fs * p.Cin * p.Cout;
+    CK(cudaMalloc(&dx, x.size() * 4)); CK(cudaMalloc(&dgd, gdec.size() * 4)); CK(cudaMalloc(&dgo, godd.size() * 4)); CK(cudaMalloc(&ddw, wn * 4));
+    CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgd, gdec.data(), gdec.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgo, godd.data(), godd.size() * 4, cudaMemcpyHostToDevice));
+    UmmaWgradLaunch WL;
+    memset(&WL, 0, sizeof(WL));
+    WL.batch = p.B; WL.dW = ddw; WL.w_sp = p.Cout; WL.w_sg = 1; WL.scale = 1.f;
+    int grp_par[kWgMaxGroups], grp_q[kWgMaxGroups];
+    for (int q = 0; q < 2; ++q)
+        for (int par = 0; par < 2; ++par) {
+            WgGroup W;
+            memset(&W, 0, sizeof(W));
+            W.P.base = dx + par * p.Cin; W.P.bstride = (long long)p.T * p.Cin; W.P.rstride = 2 * p.Cin;
+            W.P.r_lo = 0; W.P.r_hi = (par == 0) ? (p.T + 1) / 2 : p.T / 2; W.P.C = p.Cin; W.P.kind = PLANE_DIRECT;
+            W.G.base = (q == 0) ? dgd : dgo - (long long)mo_lo * p.Cout;
+            W.G.bstride = (q == 0) ? (long long)Td * p.Cout : (long long)n_odd * p.Cout;
+            W.G.rstride = p.Cout; W.G.C = p.Cout; W.G.kind = PLANE_DIRECT;
+            W.m_lo = (q == 0) ? 0 : mo_lo; W.m_hi = (q == 0) ? Td : mo_hi;
+            W.G.r_lo = W.m_lo; W.G.r_hi = W.m_hi;
+            for (int j = 0; j < p.fs; ++j) {
+                int e = q + j;
+                if ((e & 1) != par) continue;
+                W.d[W.ntaps] = e >> 1; W.woff[W.ntaps] = j * p.Cin * p.Cout; ++W.ntaps;
+            }
+            if (W.m_hi <= W.m_lo || W.ntaps == 0) continue;
+            grp_par[WL.ngroups] = par; grp_q[WL.ngroups] = q;
+            WL.grp[WL.ngroups++] = W;
+        }
+    if (!umma_plan_wgrad(&WL)) { printf("[%s] wgrad not eligible\n", name); exit(4); }
+    const WgGroup& W0 = WL.grp[0];
+    printf("[%s] wgrad B=%d T=%d Cin=%d Cout=%d swap=%d NT=%d taps/cta=%d tapsets=%d chunks/cta=%d grid=(%d,%d,%d) stages=%d smem=%zu\n", name,
+           p.B, p.T, p.Cin, p.Cout, W0.swap, W0.NT, W0.taps_per_cta, W0.n_tapsets, W0.chunks_per_cta, WL.grid_x, WL.grid_y, WL.grid_z,
+           WL.nstages, umma_wgrad_smem_bytes(WL));
+
+    // split storage: P parity planes (shared by the two classes), G per class
+    WgSplit S;
+    memset(&S, 0, sizeof(S));
+    const int nchunkP = (p.Cin + 15) / 16, nchunkG = (p.Cout + 15) / 16;
+    const int RpadP = (p.T + 1) / 2 + kWgRK + kWgSpan + 64;
+    S.p_pstride = (long long)RpadP * 16; S.p_cstride = 4 * S.p_pstride; S.p_bstride = nchunkP * S.p_cstride;
+    uint8_t* dps[2];
+    uint8_t* dgs[2];
+    long long g_ps[2];
+    for (int par = 0; par < 2; ++par) {
+        CK(cudaMalloc(&dps[par], (size_t)p.B * S.p_bstride));
+        PlaneView P = WL.grp[0].P;
+        P.base = dx + par * p.Cin; P.r_hi = (par == 0) ? (p.T + 1) / 2 : p.T / 2;
+        split_plane_kernel<<<148 * 8, 256>>>(P, p.B, dps[par], nchunkP, RpadP);
+        CK(cudaGetLastError());
+    }
+    PlaneView Gv[2];
+    memset(Gv, 0, sizeof(Gv));
+    int RpadG[2];
+    for (int q = 0; q < 2; ++q) {
+        Gv[q].kind = PLANE_DIRECT;
+        Gv[q].base = (q == 0) ? dgd : dgo - (long long)mo_lo * p.Cout;
+        Gv[q].bstride = (q == 0) ? (long long)Td * p.Cout : (long long)n_odd * p.Cout;
+        Gv[q].rstride = p.Cout; Gv[q].C = p.Cout; Gv[q].r_lo = (q == 0) ? 0 : mo_lo; Gv[q].r_hi = (q == 0) ? Td : mo_hi;
+        Gv[q].blend = nullptr; Gv[q].xrows = 0; Gv[q].mid_mode = 0;
+        RpadG[q] = Gv[q].r_hi + kWgRK + 64;
+        g_ps[q] = (long long)RpadG[q] * 16;
+        CK(cudaMalloc(&dgs[q], (size_t)p.B * nchunkG * 4 * g_ps[q]));
+        split_plane_kernel<<<148 * 8, 256>>>(Gv[q], p.B, dgs[q], nchunkG, RpadG[q]);
+        CK(cudaGetLastError());
+    }
+    for (int g = 0; g < WL.ngroups; ++g) {
+        S.P[g] = dps[grp_par[g]];
+        S.G[g] = dgs[grp_q[g]];
+        S.g_pstride[g] = g_ps[grp_q[g]]; S.g_cstride[g] = 4 * S.g_pstride[g]; S.g_bstride[g] = nchunkG * S.g_cstride[g];
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaFuncSetAttribute(presplit_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid(WL.grid_x, WL.grid_y, WL.grid_z);
+    const size_t smem_b = umma_wgrad_smem_bytes(WL);
+
+    auto check_dw = [&](const char* which) {
+        std::vector<float> dw(wn);
+        CK(cudaMemcpy(dw.data(), ddw, wn * 4, cudaMemcpyDeviceToHost));
+        std::vector<double> ref(wn, 0.0);
+        auto split = [](float v, float* h, float* l) { *h = bf16_round(v); *l = bf16_round(v - *h); };
+        for (int b = 0; b < p.B; ++b)
+            for (int a = 0; a < To; ++a) {
+                const bool even = (a & 1) == 0;
+                if (!even && !(a >= p.cs && a < p.cs + p.U)) continue;
+                const float* g = even ? &gdec[((size_t)b * Td + a / 2) * p.Cout] : &godd[((size_t)b * n_odd + ((a - 1) / 2 - mo_lo)) * p.Cout];
+                for (int j = 0; j < p.fs; ++j)
+                    for (int c = 0; c < p.Cin; ++c) {
+                        float xh, xl; split(x[((size_t)b * p.T + a + j) * p.Cin + c], &xh, &xl);
+                        for (int n = 0; n < p.Cout; ++n) {
+                            float gh, gl; split(g[n], &gh, &gl);
+                            ref[((size_t)j * p.Cin + c) * p.Cout + n] += (double)xh * gh + (double)xl * gh + (double)xh * gl;
+                        }
+                    }
+            }
+        double num = 0, den = 0;
+        for (size_t i = 0; i < wn; ++i) { num += (dw[i] - ref[i]) * (dw[i] - ref[i]); den += ref[i] * ref[i]; }
+        const double rel = sqrt(num / den);
+        printf("[%s] wgrad %-9s %s rel_l2=%.3e\n", name, which, rel < 1e-4 ? "PASS" : "FAIL", rel);
+    };
+    auto time_it = [&](const char* which, auto launch) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        launch();
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < timing_iters; ++i) launch();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= timing_iters;
+        const double flops = 2.0 * p.B * ((double)Td + n_odd) * p.fs * p.Cin * p.Cout;
+        printf("[%s] wgrad %-9s time %.1f us  %.1f useful TFLOP/s\n", name, which, ms * 1e3, flops / (ms * 1e-3) * 1e-12);
+    };
+    CK(cudaMemset(ddw, 0, wn * 4));
+    CK(launch_wgrad_umma(WL, 0));
+    { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("[%s] engine WGRAD ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); } }
+    if (check) check_dw("engine");
+    CK(cudaMemset(ddw, 0, wn * 4));
+    presplit_wgrad_kernel<<<grid, kPwThreads, smem_b>>>(WL, S);
+    { cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("[%s] bulk-fed WGRAD ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); } }
+    if (check) check_dw("bulk-fed");
+    if (timing_iters > 0) {
+        time_it("engine", [&]() { CK(launch_wgrad_umma(WL, 0)); });
+        time_it("bulk-fed", [&]() { presplit_wgrad_kernel<<<grid, kPwThreads, smem_b>>>(WL, S); });
+    }
+    cudaFree(dx); cudaFree(dgd); cudaFree(dgo); cudaFree(ddw);
+    for (int i = 0; i < 2; ++i) { cudaFree(dps[i]); cudaFree(dgs[i]); }
+}
+
 int main(int argc, char** argv) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -547,5 +857,16 @@ int main(int argc, char** argv) {
     if (want("down2")) run_case("down2", {16, 36851, 48, 72, 15, 16366, 4105}, false, 20);
     if (want("down3")) run_case("down3", {16, 18419, 72, 96, 15, 8174, 2057}, false, 20);
     if (want("down4")) run_case("down4", {16, 9203, 96, 120, 15, 4078, 1033}, false, 20);
+    if (want("wsmall")) {
+        run_wgrad("wg_tiny",   { 1, 300,  16, 16,  3,  40, 101}, true, 0);
+        run_wgrad("wg_taps15", { 2, 1500, 32, 48, 15, 200, 401}, true, 0);
+        run_wgrad("wg_c72n96", { 2, 3000, 72, 96, 15, 500, 801}, true, 0);
+        run_wgrad("wg_c24",    { 2, 1500, 24, 48, 15, 200, 401}, true, 0);
+        run_wgrad("wg_wide",   { 2, 300, 264, 288, 15, 50, 101}, true, 0);
+    }
+    if (want("wdown1")) run_wgrad("wg_down1", {16, 73715, 24, 48, 15, 32750, 8201}, false, 10);
+    if (want("wdown2")) run_wgrad("wg_down2", {16, 36851, 48, 72, 15, 16366, 4105}, false, 10);
+    if (want("wdown3")) run_wgrad("wg_down3", {16, 18419, 72, 96, 15, 8174, 2057}, false, 10);
+    if (want("wdown5")) run_wgrad("wg_down5", {16, 4595, 120, 144, 15, 2030, 521}, false, 10);
     return 0;
 }
