@@ -269,6 +269,45 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([e2e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        e2e_seq_s = e2e_s
+
+        # ---- the same, with the package's input prefetcher: H2D of step i+1 overlaps the compute of step i, the step itself
+        # is the captured CUDA graph when there is one.  Every step still copies its inputs from pinned host memory and
+        # reads its loss back inside the timed region.  Any failure here leaves the sequential number standing.
+        e2e_pipe_s, pipe_err = None, None
+        try:
+            from wun.prefetch import DevicePrefetcher
+            pf = DevicePrefetcher([mix_d, tg_d])
+
+            def run_pipelined(n):
+                loss = None
+                pf.issue([mix_h, tg_h])
+                for i in range(n):
+                    if i + 1 < n:
+                        pf.issue([mix_h, tg_h])
+                    pf.consume()
+                    run_step()
+                    loss = float(sep._loss.item())
+                return loss
+
+            run_pipelined(max(2, min(3, args.warmup)))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            pipe_loss = run_pipelined(e_steps)
+            torch.cuda.synchronize()
+            e2e_pipe_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([e2e_pipe_s], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_pipe_s = float(t.item())
+            if not (pipe_loss == pipe_loss and 0.0 < pipe_loss < 10.0):      # finite, plausible MSE
+                raise RuntimeError("implausible loss %r from the pipelined loop" % (pipe_loss,))
+            if e2e_pipe_s < e2e_s:
+                e2e_s, last_loss = e2e_pipe_s, pipe_loss
+        except Exception as ex:                                               # noqa: BLE001 - keep the bench line alive
+            pipe_err = "%s: %s" % (type(ex).__name__, ex)
 
     ms_step = ms_total / args.steps
     frames = B * t_out * world
@@ -308,7 +347,11 @@ def run_ours(args, rank, world, local_rank):
                    "arithmetic": "fp32 in/out; tensor-core layers split every fp32 operand into bf16 hi+lo and issue "
                                  "3 bf16 MMAs per product (fp32 accumulate): 5e-6 rel. error vs the 1e-4 parity bar"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mix_h.numel() * 4 + tg_h.numel() * 4),
-                "d2h_bytes_per_step": 4, "steps": e_steps, "last_loss": last_loss},
+                "d2h_bytes_per_step": 4, "steps": e_steps, "last_loss": last_loss,
+                "sequential_value": frames / (e2e_seq_s / e_steps),
+                "prefetch_value": (frames / (e2e_pipe_s / e_steps)) if e2e_pipe_s else None,
+                "mode": "prefetch (wun.prefetch.DevicePrefetcher: H2D of step i+1 overlaps step i)"
+                        if (e2e_pipe_s and e2e_pipe_s <= e2e_seq_s) else "sequential", "prefetch_error": pipe_err},
         "gpu_launches": int((eng.launches(True) + 1) * args.steps),
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",

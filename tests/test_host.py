@@ -204,3 +204,55 @@ def test_long_window_mode_plans_and_amortises_the_context():
         assert all(d["smem"] <= 220 * 1024 for d in audit)
     assert per_frame[0] > 1.5 * per_frame[1] > 1.5 * per_frame[2] * 1.0
     assert abs(per_frame[0] - 849e3) / 849e3 < 0.01           # 849 kFLOP per output frame at the default window
+
+
+def test_device_prefetcher_slot_protocol(monkeypatch):
+    """wun.prefetch.DevicePrefetcher on fake streams / events: slots alternate, a slot is refilled only behind the `free`
+    event of the copy that drained it, is consumed only behind its `ready` event, and over-issuing is refused."""
+    import torch
+    from wun import prefetch
+    log = []
+
+    class FakeEvent(object):
+        n = 0
+        def __init__(self):
+            FakeEvent.n += 1; self.id = FakeEvent.n
+        def record(self, stream):
+            log.append(("record", self.id, stream.name))
+
+    class FakeStream(object):
+        def __init__(self, device=None, name="copy"):
+            self.name = name
+        def wait_event(self, ev):
+            log.append(("wait", ev.id, self.name))
+
+    class Ctx(object):
+        def __init__(self, s): self.s = s
+        def __enter__(self): log.append(("enter", self.s.name))
+        def __exit__(self, *a): log.append(("exit", self.s.name))
+
+    compute = FakeStream(name="compute")
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: Ctx(s))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: compute)
+    a, b = torch.zeros(4), torch.zeros(2, 3)
+    pf = prefetch.DevicePrefetcher([a, b])
+    ready, free = [e.id for e in pf.ready], [e.id for e in pf.free]
+    h = [[torch.full((4,), float(i)), torch.full((2, 3), 10.0 + i)] for i in range(3)]
+    with pytest.raises(RuntimeError):
+        pf.consume()
+    pf.issue(h[0]); pf.issue(h[1])
+    with pytest.raises(RuntimeError):
+        pf.issue(h[2])                                     # both staging slots in flight
+    pf.consume()
+    assert float(a[0]) == 0.0 and float(b[0, 0]) == 10.0
+    pf.issue(h[2])                                          # refills slot 0 ...
+    pf.consume(); assert float(a[0]) == 1.0
+    pf.consume(); assert float(a[0]) == 2.0 and float(b[1, 2]) == 12.0
+    ev = [x for x in log if x[0] in ("wait", "record")]
+    assert ev == [("wait", free[0], "copy"), ("record", ready[0], "copy"), ("wait", free[1], "copy"), ("record", ready[1], "copy"),
+                  ("wait", ready[0], "compute"), ("record", free[0], "compute"),
+                  ("wait", free[0], "copy"), ("record", ready[0], "copy"),      # ... only behind the copy that drained it
+                  ("wait", ready[1], "compute"), ("record", free[1], "compute"),
+                  ("wait", ready[0], "compute"), ("record", free[0], "compute")]
