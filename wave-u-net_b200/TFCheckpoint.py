@@ -367,7 +367,9 @@ def read_checkpoint(prefix, verify=True, names=None):
             raise CheckpointError("%s: size %d does not match shape %s" % (name, e["size"], e["shape"]))
         sid = e["shard_id"]
         if sid not in shards:
-            shards[sid] = np.memmap(_data_path(prefix, sid, num_shards), dtype=np.uint8, mode="r")
+            path = _data_path(prefix, sid, num_shards)
+            # (np.memmap refuses empty files - a bundle of empty tensors has a 0-byte data file)
+            shards[sid] = np.memmap(path, dtype=np.uint8, mode="r") if os.path.getsize(path) > 0 else np.zeros(0, np.uint8)
         raw = shards[sid][e["offset"]:e["offset"] + e["size"]]
         if raw.size != e["size"]:
             raise CheckpointError("%s: data file truncated" % name)
