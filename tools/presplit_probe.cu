@@ -68,6 +68,10 @@ __global__ void split_plane_kernel(PlaneView P, int B, uint8_t* out, int nchunk,
 constexpr int kPsSlabStages = 4;
 constexpr int kPsThreads = 256;
 
+// per-CTA cycle counters of the MMA-issuing thread (always compiled in: five clock64 reads per K chunk are noise):
+// [0] CTAs, [1] whole tile loop, [2] waiting for a slab, [3] waiting for weights, [4] waiting for a free accumulator
+__device__ unsigned long long g_ps_timing[8];
+
 // split OUTPUT storage (what the next layer's slab loader wants): per class, row m of the class goes to parity plane m & 1
 // at index m >> 1:  [class][parity][batch][16-channel chunk][hi a0 | hi a1 | lo a0 | lo a1][row][16 B]
 struct SplitOut {
@@ -173,11 +177,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) presplit_conv_persistent(const 
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t b_lbo = 32u * NPAD;
             int jg = 0, bg = 0, k = 0;
+            long long t_slab = 0, t_b = 0, t_acc = 0;
+            const long long t_loop0 = clock64();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
                 const TileCoord tc = decode_tile(L, t);
                 const UmmaClass& K = L.cls[tc.cls];
                 const int buf = k & 1;
-                mbar_wait(BAR(ACC_EMPTY + buf), ((k >> 1) & 1) ^ 1);
+                { const long long w0 = clock64(); mbar_wait(BAR(ACC_EMPTY + buf), ((k >> 1) & 1) ^ 1); t_acc += clock64() - w0; }
                 tc_fence_after();
                 uint32_t first = 0;
                 for (int g = 0; g < K.ngroups; ++g) {
@@ -185,13 +191,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) presplit_conv_persistent(const 
                     const int nchunk = (L.planes[G.plane].C + 15) >> 4;
                     for (int c = 0; c < nchunk; ++c, ++jg) {
                         const int st = jg % NS;
-                        mbar_wait(BAR(SLAB_FULL + st), (jg / NS) & 1);
+                        { const long long w0 = clock64(); mbar_wait(BAR(SLAB_FULL + st), (jg / NS) & 1); t_slab += clock64() - w0; }
                         tc_fence_after();
                         const uint32_t sa = smem_u32(slab0 + st * slab_bytes);
                         const uint64_t a_hi0 = umma_desc(sa, atom_stride, 128), a_lo0 = umma_desc(sa + 2 * atom_stride, atom_stride, 128);
                         for (int t0 = G.term_begin; t0 < G.term_end; t0 += TB, ++bg) {
                             const int bs = bg % nbs;
-                            mbar_wait(BAR(B_FULL + bs), (bg / nbs) & 1);
+                            { const long long w0 = clock64(); mbar_wait(BAR(B_FULL + bs), (bg / nbs) & 1); t_b += clock64() - w0; }
                             tc_fence_after();
                             const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
                             const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
@@ -216,6 +222,11 @@ __global__ void __launch_bounds__(kPsThreads, 1) presplit_conv_persistent(const 
                 }
                 umma_commit(BAR(ACC_FULL + buf));
             }
+            atomicAdd(&g_ps_timing[0], 1ull);
+            atomicAdd(&g_ps_timing[1], (unsigned long long)(clock64() - t_loop0));
+            atomicAdd(&g_ps_timing[2], (unsigned long long)t_slab);
+            atomicAdd(&g_ps_timing[3], (unsigned long long)t_b);
+            atomicAdd(&g_ps_timing[4], (unsigned long long)t_acc);
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -522,8 +533,20 @@ static void run_case(const char* name, Problem p, bool check, int timing_iters) 
     if (check) check_outputs("split-out", true);
     if (timing_iters > 0) {
         time_it("engine", [&]() { CK(launch_plane_conv_umma(L, 0)); });
+        { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; CK(cudaMemcpyToSymbol(g_ps_timing, z, sizeof(z))); }
         time_it("bulk-fed", [&]() { presplit_conv_persistent<false><<<grid, kPsThreads, smem_b>>>(LB, total, XS, YS); });
+        auto report = [&](const char* which) {
+            unsigned long long tt[8];
+            CK(cudaMemcpyFromSymbol(tt, g_ps_timing, sizeof(tt)));
+            const double n = (double)tt[0];
+            if (n > 0) printf("[%s] %-9s MMA thread per CTA: loop %.0f cycles = issue %.0f + wait slab %.0f + wait weights %.0f + wait accumulator %.0f\n",
+                              name, which, tt[1] / n, (tt[1] - tt[2] - tt[3] - tt[4]) / n, tt[2] / n, tt[3] / n, tt[4] / n);
+            memset(tt, 0, sizeof(tt));
+            CK(cudaMemcpyToSymbol(g_ps_timing, tt, sizeof(tt)));
+        };
+        report("bulk-fed");
         time_it("split-out", [&]() { presplit_conv_persistent<true><<<grid, kPsThreads, smem_b>>>(LB, total, XS, YS); });
+        report("split-out");
         time_it("split x2", [&]() { for (int par = 0; par < 2; ++par) split_plane_kernel<<<148 * 8, 256>>>(CL.planes[par], p.B, dxs[par], nchunk, Rpad); });
     }
     cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(ddec); cudaFree(dodd); cudaFree(arena);
