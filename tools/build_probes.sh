@@ -7,4 +7,5 @@ nvcc $F -o tools/umma_probe tools/umma_probe.cu
 nvcc $F -DWUN_UMMA_TIMING -o tools/umma_probe_timing tools/umma_probe.cu
 nvcc $F -o tools/umma_layout_bench tools/umma_layout_bench.cu
 nvcc $F -o tools/presplit_probe tools/presplit_probe.cu
+nvcc $F -o tools/first_layer_probe tools/first_layer_probe.cu
 echo probes built
