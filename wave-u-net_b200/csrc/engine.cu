@@ -67,6 +67,7 @@ struct WunHandle {
     cudaEvent_t join_event = nullptr;
     int fork_used = 0;
     bool use_side = true;                // WUN_SIDE_STREAM=0 disables
+    bool first_fast = false;             // WUN_FIRST_LAYER=1: dedicated first-layer kernels (kernels_first.cu; experimental)
     cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
     // weight packs are hoisted off the critical path: phase 1 enqueues every pack kernel of the step on the side stream
     // (they only depend on the parameters), phase 2 enqueues everything else; phase 0 = inline (inference, debug hook)
@@ -274,8 +275,49 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
     return WUN_OK;
 }
 
+// The first down block in the form kernels_first.cu wants, if the op has exactly the shape plan.cpp builds for it: input =
+// the caller's mix in two parity planes, class 0 = even full-rate rows -> dec0, class 1 = odd rows of the skip window -> odd0.
+static bool first_layer_desc(const WunHandle* h, const ConvOp& op, FirstLayer* F) {
+    if (!h->first_fast || op.planes.size() != 2 || op.classes.size() != 2) return false;
+    const ViewSpec& p0 = op.planes[0];
+    const ViewSpec& p1 = op.planes[1];
+    if (p0.tensor != TENSOR_MIX || p1.tensor != TENSOR_MIX || p0.row_step != 2 || p1.row_step != 2 || p0.row_offset != 0 ||
+        p1.row_offset != 1 || p0.kind != PLANE_DIRECT || p1.kind != PLANE_DIRECT) return false;
+    const int C = h->plan.cfg.num_channels;
+    if (op.cin_tot != C || !first_layer_supported(C, op.cout, op.k)) return false;
+    const ClassSpec& c0 = op.classes[0];
+    const ClassSpec& c1 = op.classes[1];
+    if (c0.out.row_step != 1 || c1.out.row_step != 1 || c0.out.row_offset != 0 || c1.out.row_offset != -c1.m_lo || c0.m_lo != 0) return false;
+    if ((int)c0.terms.size() != op.k || (int)c1.terms.size() != op.k) return false;
+    // tap j of class q reads full-rate x row 2m + q + j - pad:  2*d + plane = q + j - pad
+    int pad = 0;
+    for (const auto& t : c0.terms) if (t.tap == 0) pad = -(2 * t.d + t.plane);
+    for (int q = 0; q < 2; ++q)
+        for (const auto& t : op.classes[q].terms)
+            if (2 * t.d + t.plane != q + t.tap - pad || t.coff != 0) return false;
+    memset(F, 0, sizeof(*F));
+    F->x = h->mix; F->x_bstride = (long long)h->plan.T_in * C; F->T = (int)h->plan.T_in;
+    F->k = op.k; F->pad_left = pad;
+    F->dec = const_cast<float*>(tensor_ptr(h, c0.out.tensor)); F->dec_bstride = view_bstride(h, c0.out); F->Td = c0.m_hi;
+    F->odd = const_cast<float*>(tensor_ptr(h, c1.out.tensor)); F->odd_bstride = view_bstride(h, c1.out);
+    F->mo_lo = c1.m_lo; F->mo_hi = c1.m_hi;
+    F->W = h->params + h->plan.params[op.w_param].offset;
+    F->bias = h->params + h->plan.params[op.b_param].offset;
+    F->batch = h->batch;
+    return true;
+}
+
 static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
     h->cur_layer = layer_index; h->cur_pass = 0;
+    if (layer_index == 0) {
+        FirstLayer F;
+        if (first_layer_desc(h, op, &F)) {
+            if (h->phase == 1) return WUN_OK;
+            ++h->launches;
+            if (!h->dry) launch_first_fwd(F, h->plan.cfg.num_channels, op.cout, h->stream);
+            return WUN_OK;
+        }
+    }
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
     L.nplanes = (int)op.planes.size();
@@ -376,6 +418,22 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
 static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale, int layer_index) {
     const Plan& P = h->plan;
     h->cur_layer = layer_index;
+    if (layer_index == 0) {
+        FirstWgrad FW;
+        if (first_layer_desc(h, op, &FW.L)) {          // one launch: dW and db of both classes
+            if (h->phase == 1) return WUN_OK;
+            ++h->launches;
+            if (!h->dry) {
+                FW.L.dec = const_cast<float*>(tensor_ptr(h, P.grad_twin[op.classes[0].out.tensor]));
+                FW.L.odd = const_cast<float*>(tensor_ptr(h, P.grad_twin[op.classes[1].out.tensor]));
+                FW.dW = grads + P.params[op.w_param].offset;
+                FW.db = grads + P.params[op.b_param].offset;
+                FW.scale = scale; FW.rows_per_cta = 0;
+                launch_first_wgrad(FW, P.cfg.num_channels, op.cout, h->wstream);
+            }
+            return WUN_OK;
+        }
+    }
     // collect (class, plane) groups
     std::vector<WgradLaunch> groups;
     for (const auto& c : op.classes) {
@@ -626,6 +684,7 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* names[3] = {"WUN_UMMA_FWD", "WUN_UMMA_DGRAD", "WUN_UMMA_WGRAD"};
       for (int i = 0; i < 3; ++i) { const char* v = getenv(names[i]); h->umma_pass[i] = !(v && v[0] == '0'); } }
     { const char* v = getenv("WUN_SIDE_STREAM"); h->use_side = !(v && v[0] == '0'); }
+    { const char* v = getenv("WUN_FIRST_LAYER"); h->first_fast = (v && v[0] == '1'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);

@@ -43,7 +43,30 @@ struct UpsampleBwdLaunch {
     int rows_per_cta;
 };
 
+// First down block (kernels_first.cu).  Class 0: full-rate rows a = 2m, m in [0, Td) -> dec[b][m][n];
+// class 1: rows a = 2m+1, m in [mo_lo, mo_hi) -> odd[b][m - mo_lo][n].  x row of (row a, tap j) = a + j - pad_left.
+struct FirstLayer {
+    const float* x; long long x_bstride; int T;     // x[b][t][c], c < C
+    int k, pad_left;                                // taps; 0 for valid (context) convs, (k-1)/2 for same
+    float* dec; long long dec_bstride; int Td;
+    float* odd; long long odd_bstride; int mo_lo, mo_hi;
+    const float* W;                                 // [k][C][N]
+    const float* bias;                              // [N]
+    int batch;
+};
+
+struct FirstWgrad {
+    FirstLayer L;                 // x, geometry; dec / odd here are the GRADIENT tensors g_dec / g_odd (read only)
+    float* dW;                    // [k][C][N]
+    float* db;                    // [N] or null
+    float scale;
+    int rows_per_cta;             // class rows one CTA reduces (multiple of 128; set by the launcher)
+};
+
 void launch_plane_conv_simt(const ConvLaunch& L, cudaStream_t stream);
+bool first_layer_supported(int C, int N, int k);
+void launch_first_fwd(const FirstLayer& L, int C, int N, cudaStream_t stream);
+void launch_first_wgrad(FirstWgrad P, int C, int N, cudaStream_t stream);
 void launch_plane_wgrad_simt(WgradLaunch L, cudaStream_t stream);
 void launch_colsum(const PlaneView& V, int batch, float scale, float* out, cudaStream_t stream);
 void launch_output_fwd(const OutputLaunch& L, cudaStream_t stream);
