@@ -76,6 +76,11 @@ struct WunHandle {
     size_t arena_sum = 0;                // total pack bytes of one forward+backward (dry run)
     cudaEvent_t packs_event = nullptr;
     bool packs_pending = false;          // main stream has not yet waited for the hoisted packs
+    // WUN_PACK_EVENTS=1 (experimental): one event per FORWARD weight pack, so that forward conv i waits for pack i only
+    // instead of for all ~60 packs of the step (the backward convs still wait for the single packs_event)
+    bool pack_events_on = false;
+    std::vector<cudaEvent_t> pack_events;
+    int pack_idx = 0;                    // forward tensor-core conv counter of the current phase
     std::vector<std::string>* audit = nullptr;   // dry runs: one line per tensor-core launch (wun_debug_plan)
     // per-call state
     bool dry = false;
@@ -258,8 +263,19 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
         UmmaLaunch U; UmmaPackLaunch PL;
         cudaError_t e = umma_build(L, ch, arena, &U, &PL);
         if (e == cudaSuccess && h->phase != 2) e = launch_umma_pack(PL, (h->phase == 1) ? h->side : h->stream);
+        const bool per_pack = h->pack_events_on && h->cur_pass == 0 && h->phase != 0;
+        if (per_pack) {
+            const int idx = h->pack_idx++;
+            while ((int)h->pack_events.size() <= idx && e == cudaSuccess) {
+                cudaEvent_t ev;
+                e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) h->pack_events.push_back(ev);
+            }
+            if (e == cudaSuccess && h->phase == 1) e = cudaEventRecord(h->pack_events[idx], h->side);
+            if (e == cudaSuccess && h->phase == 2) e = cudaStreamWaitEvent(h->stream, h->pack_events[idx], 0);
+        }
         if (e == cudaSuccess && h->phase != 1) {
-            if (h->packs_pending) {             // first tensor-core conv of the step: the hoisted packs must have landed
+            if (h->packs_pending && !per_pack) {   // first conv that needs ALL hoisted packs (with per-pack events: the first dgrad)
                 e = cudaStreamWaitEvent(h->stream, h->packs_event, 0);
                 h->packs_pending = false;
             }
@@ -685,6 +701,7 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
       for (int i = 0; i < 3; ++i) { const char* v = getenv(names[i]); h->umma_pass[i] = !(v && v[0] == '0'); } }
     { const char* v = getenv("WUN_SIDE_STREAM"); h->use_side = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_FIRST_LAYER"); h->first_fast = (v && v[0] == '1'); }
+    { const char* v = getenv("WUN_PACK_EVENTS"); h->pack_events_on = (v && v[0] == '1'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);
@@ -706,6 +723,7 @@ int wun_destroy(WunHandle* h) {
         for (auto e : h->fork_events) cudaEventDestroy(e);
         if (h->join_event) cudaEventDestroy(h->join_event);
         if (h->packs_event) cudaEventDestroy(h->packs_event);
+        for (auto e : h->pack_events) cudaEventDestroy(e);
         if (h->side) cudaStreamDestroy(h->side);
         delete h;
     }
@@ -781,7 +799,7 @@ int wun_forward_backward(WunHandle* h, const float* params, const float* mix, co
         if (h->fork_events.empty()) { cudaEvent_t e; WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->fork_events.push_back(e); }
         WUN_CUDA_OK(cudaEventRecord(h->fork_events[0], h->stream));
         WUN_CUDA_OK(cudaStreamWaitEvent(h->side, h->fork_events[0], 0));
-        h->phase = 1; h->arena_cur = 0;
+        h->phase = 1; h->arena_cur = 0; h->pack_idx = 0;
         rc = run_forward(h, targets, outputs, loss, 1);
         if (rc == WUN_OK) rc = run_backward(h, targets, grads, grad_scale);
         h->phase = 0;
@@ -790,7 +808,7 @@ int wun_forward_backward(WunHandle* h, const float* params, const float* mix, co
         h->packs_pending = true;
         h->phase = 2;
     }
-    h->arena_cur = 0;
+    h->arena_cur = 0; h->pack_idx = 0;
     rc = run_forward(h, targets, outputs, loss, 1);
     if (rc == WUN_OK) rc = run_backward(h, targets, grads, grad_scale);
     h->phase = 0;
