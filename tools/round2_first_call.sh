@@ -4,6 +4,7 @@
 # 1. are the bulk-copy-fed tcgen05 kernels (tools/presplit_probe.cu) correct, and how much faster than the converter-fed ones?
 # 2. are the dedicated first-layer kernels (kernels_first.cu) correct and faster?  (probe, then the parity tests with the switch)
 # 3. does WUN_PACK_EVENTS=1 help, and does the prefetch leg of bench.py's e2e work?
+# 4. WUN_BULK_WGRAD=1: split pass + bulk-copy-fed wgrad inside the engine (parity, step time)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "=== presplit probe (correctness on small cases, then the M4 down3 layer)"
@@ -18,8 +19,10 @@ timeout 120 stdbuf -oL tools/first_layer_probe small 2>&1 | grep -v "^$"
 timeout 120 stdbuf -oL tools/first_layer_probe m4 2>&1 | grep -v "^$"
 echo "=== parity tests with the experimental switches"
 WUN_FIRST_LAYER=1 WUN_PACK_EVENTS=1 timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-echo "=== bench: defaults / first layer / + pack events"
-for cfg in "X=0" "WUN_FIRST_LAYER=1" "WUN_FIRST_LAYER=1 WUN_PACK_EVENTS=1"; do
+echo "=== parity tests with the bulk-copy-fed wgrad"
+WUN_BULK_WGRAD=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -4
+echo "=== bench: defaults / first layer / + pack events / + bulk wgrad"
+for cfg in "X=0" "WUN_FIRST_LAYER=1" "WUN_FIRST_LAYER=1 WUN_PACK_EVENTS=1" "WUN_BULK_WGRAD=1" "WUN_FIRST_LAYER=1 WUN_PACK_EVENTS=1 WUN_BULK_WGRAD=1"; do
   echo -n "$cfg  "
   env $cfg timeout 150 python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys

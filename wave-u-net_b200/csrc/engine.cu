@@ -68,6 +68,8 @@ struct WunHandle {
     int fork_used = 0;
     bool use_side = true;                // WUN_SIDE_STREAM=0 disables
     bool first_fast = false;             // WUN_FIRST_LAYER=1: dedicated first-layer kernels (kernels_first.cu; experimental)
+    bool bulk_wgrad = false;             // WUN_BULK_WGRAD=1: split pass + bulk-copy-fed tcgen05 wgrad (experimental)
+    size_t split_item_bytes = 0;         // per batch item: largest split arena any layer's wgrad needs (dry run)
     cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
     // weight packs are hoisted off the critical path: phase 1 enqueues every pack kernel of the step on the side stream
     // (they only depend on the parameters), phase 2 enqueues everything else; phase 0 = inline (inference, debug hook)
@@ -431,6 +433,56 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
     return WUN_OK;
 }
 
+// Split arena of one layer's bulk-fed wgrad: one array per DISTINCT plane view the groups read (activation planes are shared
+// by the classes, class gradients by the planes), covering the union of the row ranges the CTAs touch.  Returns the bytes
+// needed at `batch` (arrays 256-B aligned); fills the jobs / operand table when `arena` is not null.
+static size_t plan_wgrad_split(const UmmaWgradLaunch& U, int batch, uint8_t* arena, WgSplit* S, SplitJobs* J) {
+    struct Slot { PlaneView V; int lo, hi; size_t off; };
+    std::vector<Slot> slots;
+    int p_slot[kWgMaxGroups], g_slot[kWgMaxGroups];
+    auto find = [&](const PlaneView& V, int lo, int hi) {
+        for (size_t i = 0; i < slots.size(); ++i)
+            if (memcmp(&slots[i].V, &V, sizeof(PlaneView)) == 0) {
+                slots[i].lo = std::min(slots[i].lo, lo); slots[i].hi = std::max(slots[i].hi, hi);
+                return (int)i;
+            }
+        slots.push_back({V, lo, hi, 0});
+        return (int)slots.size() - 1;
+    };
+    for (int g = 0; g < U.ngroups; ++g) {
+        const WgGroup& G = U.grp[g];
+        int dmin = G.d[0], dmax = G.d[0];
+        for (int t = 1; t < G.ntaps; ++t) { dmin = std::min(dmin, G.d[t]); dmax = std::max(dmax, G.d[t]); }
+        p_slot[g] = find(G.P, G.m_lo + dmin, G.m_hi + dmax + kWgOverreachP);
+        g_slot[g] = find(G.G, G.m_lo, G.m_hi + kWgOverreachG);
+    }
+    if ((int)slots.size() > kSplitMaxJobs) return 0;
+    size_t cur = 0;
+    for (auto& sl : slots) {
+        const int nchunk = (sl.V.C + 15) / 16, rows = (sl.hi - sl.lo + 7) / 8 * 8;
+        cur = (cur + 255) / 256 * 256;
+        sl.off = cur;
+        cur += (size_t)batch * nchunk * 4 * rows * 16;
+    }
+    if (arena) {
+        memset(S, 0, sizeof(*S));
+        memset(J, 0, sizeof(*J));
+        J->batch = batch; J->njobs = (int)slots.size();
+        for (size_t i = 0; i < slots.size(); ++i) {
+            SplitJob& job = J->job[i];
+            job.V = slots[i].V; job.out = arena + slots[i].off;
+            job.nchunk = (slots[i].V.C + 15) / 16; job.rows = (slots[i].hi - slots[i].lo + 7) / 8 * 8; job.row0 = slots[i].lo;
+        }
+        for (int g = 0; g < U.ngroups; ++g) {
+            const SplitJob& jp = J->job[p_slot[g]];
+            const SplitJob& jg = J->job[g_slot[g]];
+            S->P[g] = jp.out; S->p_pstride[g] = (long long)jp.rows * 16; S->p_nchunk[g] = jp.nchunk; S->p_row0[g] = jp.row0;
+            S->G[g] = jg.out; S->g_pstride[g] = (long long)jg.rows * 16; S->g_nchunk[g] = jg.nchunk; S->g_row0[g] = jg.row0;
+        }
+    }
+    return cur + 256;
+}
+
 static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale, int layer_index) {
     const Plan& P = h->plan;
     h->cur_layer = layer_index;
@@ -508,8 +560,21 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     if (h->phase == 1) return WUN_OK;
     if (use_umma) {
         ++h->launches;
+        const size_t split_need = h->bulk_wgrad ? plan_wgrad_split(U, 1, nullptr, nullptr, nullptr) : 0;
+        const bool bulk = split_need > 0;                 // 0: too many distinct views for one split pass -> converter-fed kernel
+        if (bulk) { ++h->launches; if (h->dry) h->split_item_bytes = std::max(h->split_item_bytes, split_need); }
         if (!h->dry) {
-            cudaError_t e = launch_wgrad_umma(U, h->wstream);
+            cudaError_t e;
+            if (bulk) {
+                uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total) + h->arena_sum;
+                arena += (256 - (reinterpret_cast<uintptr_t>(arena) & 255)) & 255;
+                WgSplit S; SplitJobs J;
+                plan_wgrad_split(U, h->batch, arena, &S, &J);
+                e = launch_split_views(J, h->wstream);      // same stream as the wgrad: the arena is reused layer after layer
+                if (e == cudaSuccess) e = launch_wgrad_umma_bulk(U, S, h->wstream);
+            } else {
+                e = launch_wgrad_umma(U, h->wstream);
+            }
             if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 wgrad launch: ") + cudaGetErrorString(e));
         }
         return WUN_OK;
@@ -654,6 +719,11 @@ static int check_device() {
     return WUN_OK;
 }
 
+// bytes of the split arena behind the weight packs (bulk-fed wgrad only; per-item size from the dry run at create time)
+static int64_t split_arena_bytes(const WunHandle* h, int64_t batch) {
+    return (h && h->bulk_wgrad && h->split_item_bytes) ? (int64_t)h->split_item_bytes * batch + 256 * (kSplitMaxJobs + 1) : 0;
+}
+
 static int begin_call(WunHandle* h, const float* params, const float* mix, int64_t batch, bool training, void* ws,
                       int64_t ws_bytes, void* stream, bool dry) {
     if (!h) return set_err(WUN_E_INVALID, "null handle");
@@ -665,7 +735,7 @@ static int begin_call(WunHandle* h, const float* params, const float* mix, int64
     if (dry) return WUN_OK;
     { int rc0 = check_device(); if (rc0 != WUN_OK) return rc0; }
     if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
-    if (ws_bytes < h->lay.total * (int64_t)sizeof(float) + (int64_t)h->arena_sum)
+    if (ws_bytes < h->lay.total * (int64_t)sizeof(float) + (int64_t)h->arena_sum + (training ? split_arena_bytes(h, batch) : 0))
         return set_err(WUN_E_INVALID, "workspace too small");
     if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return set_err(WUN_E_INVALID, "workspace must be 256-byte aligned");
     h->params = params; h->mix = mix; h->ws = (float*)ws; h->stream = (cudaStream_t)stream;
@@ -702,6 +772,7 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* v = getenv("WUN_SIDE_STREAM"); h->use_side = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_FIRST_LAYER"); h->first_fast = (v && v[0] == '1'); }
     { const char* v = getenv("WUN_PACK_EVENTS"); h->pack_events_on = (v && v[0] == '1'); }
+    { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = (v && v[0] == '1'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);
@@ -745,7 +816,7 @@ int wun_param_table(const WunHandle* h, WunParamInfo* out, int64_t capacity) {
 int64_t wun_workspace_bytes(const WunHandle* h, int64_t batch, int training) {
     if (!h || batch < 1) return -1;
     Layout l = make_layout(h->plan, batch, training != 0);
-    return l.total * (int64_t)sizeof(float) + (int64_t)h->arena_sum + 256;
+    return l.total * (int64_t)sizeof(float) + (int64_t)h->arena_sum + 256 + (training ? split_arena_bytes(h, batch) : 0);
 }
 
 double wun_forward_flops(const WunHandle* h, int64_t batch) { return h ? h->plan.fwd_flops_per_item * batch : 0; }

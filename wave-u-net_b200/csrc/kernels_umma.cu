@@ -1121,6 +1121,220 @@ cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (WUN_BULK_WGRAD=1, engine.cu; validated by tools/presplit_probe first): wgrad fed by bulk copies.
+// A batched "split pass" materialises every plane view the layer's wgrad groups read (activation planes incl. interpolated
+// MID planes, and the class gradients) as hi/lo bf16 atom planes  [batch][16-ch chunk][hi a0|hi a1|lo a0|lo a1][row][16 B]
+// with zero rows around the valid range; the wgrad kernel then fills its stages with cp.async.bulk issued by ONE thread
+// instead of 12 converter warps re-converting the same rows in every (class, plane, tap-set) CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_views_kernel(const __grid_constant__ SplitJobs J) {
+    const SplitJob& job = J.job[blockIdx.y];
+    const long long total = (long long)J.batch * job.nchunk * job.rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % job.rows);
+        const int c = (int)((i / job.rows) % job.nchunk);
+        const int b = (int)(i / ((long long)job.rows * job.nchunk));
+        float x[16];
+        load_row16(job.V, b, job.row0 + r, c * 16, x);      // zero outside the valid rows / channels; MID planes blended here
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * k]), h1 = __float2bfloat16_rn(x[2 * k + 1]);
+            hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[k] = pack_bf16x2(x[2 * k] - __bfloat162float(h0), x[2 * k + 1] - __bfloat162float(h1));
+        }
+        const long long ps = (long long)job.rows * 16;
+        uint8_t* o = job.out + (((long long)b * job.nchunk + c) * 4) * ps + (long long)r * 16;
+        *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(o + ps) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(o + 2 * ps) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(o + 3 * ps) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+}
+
+cudaError_t launch_split_views(const SplitJobs& J, cudaStream_t stream) {
+    if (J.njobs <= 0) return cudaSuccess;
+    long long most = 0;
+    for (int j = 0; j < J.njobs; ++j) most = max(most, (long long)J.batch * J.job[j].nchunk * J.job[j].rows);
+    long long blocks = (most + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    split_views_kernel<<<dim3((unsigned)blocks, J.njobs), 256, 0, stream>>>(J);
+    return cudaGetLastError();
+}
+
+constexpr int kWgBulkThreads = 384;   // warp 0 loader, warp 1 TMEM alloc + MMA issue, warps 4-11 epilogue
+
+
+
+__global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(const __grid_constant__ UmmaWgradLaunch L,
+                                                                       const __grid_constant__ WgSplit S) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int gi = 0;
+    while (gi + 1 < L.ngroups && (int)blockIdx.z >= L.grp[gi + 1].z0) ++gi;
+    const WgGroup& Gp = L.grp[gi];
+    const int tapset = blockIdx.z - Gp.z0;
+    if ((int)blockIdx.x >= Gp.n_ctas_x || (int)blockIdx.y >= Gp.n_mtiles * Gp.n_ntiles) return;
+    const int total_chunks = L.batch * Gp.chunks_per_batch;
+    const int g0 = blockIdx.x * Gp.chunks_per_cta;
+    const int g1 = min(g0 + Gp.chunks_per_cta, total_chunks);
+    if (g0 >= g1) return;
+    const int mtile = blockIdx.y / Gp.n_ntiles, ntile = blockIdx.y % Gp.n_ntiles;
+    const int tap0 = tapset * Gp.taps_per_cta;
+    const int ntap = min(Gp.taps_per_cta, Gp.ntaps - tap0);
+    const int NT = Gp.NT, swap = Gp.swap;
+    const PlaneView& SA = swap ? Gp.G : Gp.P;
+    const PlaneView& SB = swap ? Gp.P : Gp.G;
+    const int ca0 = mtile * 128, cb0 = ntile * NT;
+    const int rowsA = swap ? kWgRK : kWgRK + kWgSpan;
+    const int rowsB = swap ? kWgRK + kWgSpan : kWgRK;
+    const uint32_t planeA = 16u * rowsA, planeB = 16u * rowsB;
+    const int atomsA = 16, atomsB = NT / 8;
+    const uint32_t bytesA = 2u * atomsA * planeA, bytesB = 2u * atomsB * planeB;
+    const uint32_t stage_bytes = bytesA + bytesB;
+    int dmin = Gp.d[tap0];
+    for (int t = 1; t < ntap; ++t) dmin = min(dmin, Gp.d[tap0 + t]);
+
+    const int nst = L.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int FULL = 0, EMPTY = kWgStagesMax, ACC = 2 * kWgStagesMax;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC + 1);
+    if (tid == 0) {
+        for (int i = 0; i < kWgStagesMax; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+        mbar_init(BAR(ACC), 1);
+        fence_barrier_init();
+    }
+    // channel chunks the tensors really have inside this tile; the rest of the operand tile stays zero
+    const int chunksA = max(0, min(8, (SA.C - ca0 + 15) / 16)), chunksB = max(0, min(NT / 16, (SB.C - cb0 + 15) / 16));
+    for (uint32_t i = tid; i < (uint32_t)nst * stage_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    if (warp == 1) tmem_alloc(smem_u32(tmem_holder), Gp.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const int nchunks = g1 - g0;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint8_t* baseA = swap ? S.G[gi] : S.P[gi];
+            const uint8_t* baseB = swap ? S.P[gi] : S.G[gi];
+            const long long a_ps = swap ? S.g_pstride[gi] : S.p_pstride[gi], b_ps = swap ? S.p_pstride[gi] : S.g_pstride[gi];
+            const long long a_cs = 4 * a_ps, b_cs = 4 * b_ps;
+            const long long a_bs = (swap ? S.g_nchunk[gi] : S.p_nchunk[gi]) * a_cs, b_bs = (swap ? S.p_nchunk[gi] : S.g_nchunk[gi]) * b_cs;
+            const int a_row0 = swap ? S.g_row0[gi] : S.p_row0[gi], b_row0 = swap ? S.p_row0[gi] : S.g_row0[gi];
+            const uint32_t tx = (uint32_t)(chunksA * 4) * planeA + (uint32_t)(chunksB * 4) * planeB;
+            for (int ci = 0; ci < nchunks; ++ci) {
+                const int st = ci % nst;
+                const int gch = g0 + ci;
+                const int b = gch / Gp.chunks_per_batch;
+                const int rc = Gp.m_lo + (gch % Gp.chunks_per_batch) * kWgRK;      // first G row of the chunk
+                const int rowA = (swap ? rc : rc + dmin) - a_row0, rowB = (swap ? rc + dmin : rc) - b_row0;   // array indices
+                mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + st), tx);
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
+                for (int g = 0; g < chunksA; ++g) {
+                    const uint8_t* src = baseA + (long long)b * a_bs + (long long)(ca0 / 16 + g) * a_cs + (long long)rowA * 16;
+                    bulk_g2s(sa + (uint32_t)(2 * g) * planeA, src, planeA, BAR(FULL + st));                               // hi atom 2g
+                    bulk_g2s(sa + (uint32_t)(2 * g + 1) * planeA, src + a_ps, planeA, BAR(FULL + st));                    // hi atom 2g+1
+                    bulk_g2s(sa + (uint32_t)(atomsA + 2 * g) * planeA, src + 2 * a_ps, planeA, BAR(FULL + st));           // lo atom 2g
+                    bulk_g2s(sa + (uint32_t)(atomsA + 2 * g + 1) * planeA, src + 3 * a_ps, planeA, BAR(FULL + st));       // lo atom 2g+1
+                }
+                for (int g = 0; g < chunksB; ++g) {
+                    const uint8_t* src = baseB + (long long)b * b_bs + (long long)(cb0 / 16 + g) * b_cs + (long long)rowB * 16;
+                    bulk_g2s(sb + (uint32_t)(2 * g) * planeB, src, planeB, BAR(FULL + st));
+                    bulk_g2s(sb + (uint32_t)(2 * g + 1) * planeB, src + b_ps, planeB, BAR(FULL + st));
+                    bulk_g2s(sb + (uint32_t)(atomsB + 2 * g) * planeB, src + 2 * b_ps, planeB, BAR(FULL + st));
+                    bulk_g2s(sb + (uint32_t)(atomsB + 2 * g + 1) * planeB, src + 3 * b_ps, planeB, BAR(FULL + st));
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t accum = 0;
+            for (int ci = 0; ci < nchunks; ++ci) {
+                const int st = ci % nst;
+                mbar_wait(BAR(FULL + st), (ci / nst) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
+                const uint64_t a_hi0 = umma_desc(sa, 128, planeA), a_lo0 = umma_desc(sa + atomsA * planeA, 128, planeA);
+                const uint64_t b_hi0 = umma_desc(sb, 128, planeB), b_lo0 = umma_desc(sb + atomsB * planeB, 128, planeB);
+                for (int t = 0; t < ntap; ++t) {
+                    const uint64_t shift = (uint64_t)(uint32_t)(Gp.d[tap0 + t] - dmin);
+                    const uint64_t sha = swap ? 0ull : shift, shb = swap ? shift : 0ull;
+                    const uint32_t td = tmem_base + (uint32_t)(t * NT);
+#pragma unroll
+                    for (int ks = 0; ks < kWgRK / 16; ++ks) {
+                        const uint64_t koff = (uint64_t)(16 * ks);
+                        const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
+                        const uint64_t b_hi = b_hi0 + shb + koff, b_lo = b_lo0 + shb + koff;
+                        umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
+                        umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                    }
+                }
+                accum = 1u;
+                umma_commit(BAR(EMPTY + st));
+            }
+            umma_commit(BAR(ACC));
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        mbar_wait(BAR(ACC), 0);
+        tc_fence_after();
+        const int q4 = warp & 3;
+        const int m = ca0 + q4 * 32 + lane;
+        const bool m_ok = m < SA.C;
+        const int sM = swap ? L.w_sg : L.w_sp, sN = swap ? L.w_sp : L.w_sg;
+        for (int t = (warp - 4) >> 2; t < ntap; t += 2) {
+            float* dst_t = L.dW + (long long)Gp.woff[tap0 + t] + (long long)m * sM;
+            for (int cb = 0; cb < NT; cb += 16) {
+                if (cb0 + cb >= SB.C) break;
+                __syncwarp();
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * NT + cb), v);
+                if (!m_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= L.scale;
+                float* dst = dst_t + (long long)(cb0 + cb) * sN;
+                if (sN == 1 && cb0 + cb + 16 <= SB.C && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (cb0 + cb + j < SB.C) atomicAdd(dst + (long long)j * sN, v[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Gp.tmem_cols);
+    }
+}
+
+
+cudaError_t launch_wgrad_umma_bulk(const UmmaWgradLaunch& L, const WgSplit& S, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_umma_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(L.grid_x, L.grid_y, L.grid_z);
+    wgrad_umma_bulk_kernel<<<grid, kWgBulkThreads, wgrad_smem_bytes(L), stream>>>(L, S);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight pre-pack: fp32 W -> hi/lo bf16 blocks in K-step streaming order.  blockIdx.y = job (class, split);
 // one thread per (block, n, k) element.  Block bi = ((group, chunk), term) in the kernel's loop order; element
 // (a, n, kk) of the hi half sits at byte a*32*NPAD + (n/8)*128 + (n%8)*16 + kk*2, the lo half 16*NPAD bytes later:

@@ -104,6 +104,33 @@ struct UmmaWgradLaunch {
 };
 
 cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream);
+// ---- bulk-copy-fed wgrad (experimental, WUN_BULK_WGRAD=1) --------------------------------------------------------
+constexpr int kSplitMaxJobs = 2 * kWgMaxGroups;
+
+struct SplitJob {           // materialise plane rows [row0, row0 + rows) of V as hi/lo bf16 atom planes at `out`
+    PlaneView V;
+    uint8_t* out;           // [batch][nchunk][4][rows][16 B]
+    int nchunk, rows, row0;
+};
+
+struct SplitJobs {
+    SplitJob job[kSplitMaxJobs];
+    int njobs, batch;
+};
+
+struct WgSplit {            // where the wgrad groups find their operands (filled next to the SplitJobs)
+    const uint8_t* P[kWgMaxGroups];
+    const uint8_t* G[kWgMaxGroups];
+    long long p_pstride[kWgMaxGroups], g_pstride[kWgMaxGroups];   // bytes between the 4 sub-planes of a chunk (= rows * 16)
+    int p_nchunk[kWgMaxGroups], g_nchunk[kWgMaxGroups];
+    int p_row0[kWgMaxGroups], g_row0[kWgMaxGroups];               // plane row stored at array index 0
+};
+
+cudaError_t launch_split_views(const SplitJobs& J, cudaStream_t stream);
+cudaError_t launch_wgrad_umma_bulk(const UmmaWgradLaunch& L, const WgSplit& S, cudaStream_t stream);
+// rows one wgrad CTA can read past the last valid row of a group: G side / P side (chunk rounding + tap span)
+constexpr int kWgOverreachG = 64, kWgOverreachP = 64 + 16;
+
 // fills the tiling fields (groups' P, G, taps and the common fields already set); false = not eligible
 bool umma_plan_wgrad(UmmaWgradLaunch* L);
 
