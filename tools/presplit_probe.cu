@@ -556,174 +556,9 @@ static void run_case(const char* name, Problem p, bool check, int timing_iters) 
 
 
 // ------------------------------------------------------------------------------------------------
-// bulk-fed wgrad: the engine's wgrad_umma_kernel with the 8-12 converter warps replaced by ONE loader thread that pulls
-// the hi/lo atom planes of both operands from split storage (chunk of 64 reduction rows per stage).  Channel atoms past
-// the tensor's width are zero-filled in shared memory once.  MMA issue and the red.global epilogue are the engine's.
-//   warp 0 loader, warp 1 TMEM alloc + MMA issue, warps 4-11 epilogue (lane quarter = warp & 3, taps split by (warp-4)>>2)
+// bulk-fed wgrad: the LIBRARY's split pass + wgrad_umma_bulk_kernel (kernels_umma.cu, engine switch WUN_BULK_WGRAD=1)
+// next to the converter-fed wgrad_umma_kernel on the same launch description.
 // ------------------------------------------------------------------------------------------------
-struct WgSplit {
-    const uint8_t* P[kWgMaxGroups];      // split storage of the activation plane of every group (plane row r at index r)
-    const uint8_t* G[kWgMaxGroups];      // split storage of the gradient plane (row m at index m)
-    long long p_bstride, p_cstride, p_pstride;
-    long long g_bstride[kWgMaxGroups], g_cstride[kWgMaxGroups], g_pstride[kWgMaxGroups];
-};
-
-constexpr int kPwThreads = 384;
-
-__global__ void __launch_bounds__(kPwThreads, 1) presplit_wgrad_kernel(const __grid_constant__ UmmaWgradLaunch L,
-                                                                       const __grid_constant__ WgSplit S) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int gi = 0;
-    while (gi + 1 < L.ngroups && (int)blockIdx.z >= L.grp[gi + 1].z0) ++gi;
-    const WgGroup& Gp = L.grp[gi];
-    const int tapset = blockIdx.z - Gp.z0;
-    if ((int)blockIdx.x >= Gp.n_ctas_x || (int)blockIdx.y >= Gp.n_mtiles * Gp.n_ntiles) return;
-    const int total_chunks = L.batch * Gp.chunks_per_batch;
-    const int g0 = blockIdx.x * Gp.chunks_per_cta;
-    const int g1 = min(g0 + Gp.chunks_per_cta, total_chunks);
-    if (g0 >= g1) return;
-    const int mtile = blockIdx.y / Gp.n_ntiles, ntile = blockIdx.y % Gp.n_ntiles;
-    const int tap0 = tapset * Gp.taps_per_cta;
-    const int ntap = min(Gp.taps_per_cta, Gp.ntaps - tap0);
-    const int NT = Gp.NT, swap = Gp.swap;
-    const PlaneView& SA = swap ? Gp.G : Gp.P;
-    const PlaneView& SB = swap ? Gp.P : Gp.G;
-    const int ca0 = mtile * 128, cb0 = ntile * NT;
-    const int rowsA = swap ? kWgRK : kWgRK + kWgSpan;
-    const int rowsB = swap ? kWgRK + kWgSpan : kWgRK;
-    const uint32_t planeA = 16u * rowsA, planeB = 16u * rowsB;
-    const int atomsA = 16, atomsB = NT / 8;
-    const uint32_t bytesA = 2u * atomsA * planeA, bytesB = 2u * atomsB * planeB;
-    const uint32_t stage_bytes = bytesA + bytesB;
-    int dmin = Gp.d[tap0];
-    for (int t = 1; t < ntap; ++t) dmin = min(dmin, Gp.d[tap0 + t]);
-
-    const int nst = L.nstages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
-    const uint32_t bar0 = smem_u32(bars);
-    auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int FULL = 0, EMPTY = kWgStagesMax, ACC = 2 * kWgStagesMax;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC + 1);
-    if (tid == 0) {
-        for (int i = 0; i < kWgStagesMax; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
-        mbar_init(BAR(ACC), 1);
-        fence_barrier_init();
-    }
-    // channel chunks the tensors really have inside this tile; the rest of the operand tile stays zero
-    const int chunksA = max(0, min(8, (SA.C - ca0 + 15) / 16)), chunksB = max(0, min(NT / 16, (SB.C - cb0 + 15) / 16));
-    for (uint32_t i = tid; i < (uint32_t)nst * stage_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();
-    if (warp == 1) tmem_alloc(smem_u32(tmem_holder), Gp.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const int nchunks = g1 - g0;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            const uint8_t* baseA = swap ? S.G[gi] : S.P[gi];
-            const uint8_t* baseB = swap ? S.P[gi] : S.G[gi];
-            const long long a_bs = swap ? S.g_bstride[gi] : S.p_bstride, a_cs = swap ? S.g_cstride[gi] : S.p_cstride,
-                            a_ps = swap ? S.g_pstride[gi] : S.p_pstride;
-            const long long b_bs = swap ? S.p_bstride : S.g_bstride[gi], b_cs = swap ? S.p_cstride : S.g_cstride[gi],
-                            b_ps = swap ? S.p_pstride : S.g_pstride[gi];
-            const uint32_t tx = (uint32_t)(chunksA * 4) * planeA + (uint32_t)(chunksB * 4) * planeB;
-            for (int ci = 0; ci < nchunks; ++ci) {
-                const int st = ci % nst;
-                const int gch = g0 + ci;
-                const int b = gch / Gp.chunks_per_batch;
-                const int rc = Gp.m_lo + (gch % Gp.chunks_per_batch) * kWgRK;      // first G row of the chunk
-                const int rowA = swap ? rc : rc + dmin, rowB = swap ? rc + dmin : rc;
-                mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
-                mbar_arrive_expect_tx(BAR(FULL + st), tx);
-                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
-                for (int g = 0; g < chunksA; ++g) {
-                    const uint8_t* src = baseA + (long long)b * a_bs + (long long)(ca0 / 16 + g) * a_cs + (long long)rowA * 16;
-                    bulk_g2s(sa + (uint32_t)(2 * g) * planeA, src, planeA, BAR(FULL + st));                               // hi atom 2g
-                    bulk_g2s(sa + (uint32_t)(2 * g + 1) * planeA, src + a_ps, planeA, BAR(FULL + st));                    // hi atom 2g+1
-                    bulk_g2s(sa + (uint32_t)(atomsA + 2 * g) * planeA, src + 2 * a_ps, planeA, BAR(FULL + st));           // lo atom 2g
-                    bulk_g2s(sa + (uint32_t)(atomsA + 2 * g + 1) * planeA, src + 3 * a_ps, planeA, BAR(FULL + st));       // lo atom 2g+1
-                }
-                for (int g = 0; g < chunksB; ++g) {
-                    const uint8_t* src = baseB + (long long)b * b_bs + (long long)(cb0 / 16 + g) * b_cs + (long long)rowB * 16;
-                    bulk_g2s(sb + (uint32_t)(2 * g) * planeB, src, planeB, BAR(FULL + st));
-                    bulk_g2s(sb + (uint32_t)(2 * g + 1) * planeB, src + b_ps, planeB, BAR(FULL + st));
-                    bulk_g2s(sb + (uint32_t)(atomsB + 2 * g) * planeB, src + 2 * b_ps, planeB, BAR(FULL + st));
-                    bulk_g2s(sb + (uint32_t)(atomsB + 2 * g + 1) * planeB, src + 3 * b_ps, planeB, BAR(FULL + st));
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (elect_one()) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t accum = 0;
-            for (int ci = 0; ci < nchunks; ++ci) {
-                const int st = ci % nst;
-                mbar_wait(BAR(FULL + st), (ci / nst) & 1);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
-                const uint64_t a_hi0 = umma_desc(sa, 128, planeA), a_lo0 = umma_desc(sa + atomsA * planeA, 128, planeA);
-                const uint64_t b_hi0 = umma_desc(sb, 128, planeB), b_lo0 = umma_desc(sb + atomsB * planeB, 128, planeB);
-                for (int t = 0; t < ntap; ++t) {
-                    const uint64_t shift = (uint64_t)(uint32_t)(Gp.d[tap0 + t] - dmin);
-                    const uint64_t sha = swap ? 0ull : shift, shb = swap ? shift : 0ull;
-                    const uint32_t td = tmem_base + (uint32_t)(t * NT);
-#pragma unroll
-                    for (int ks = 0; ks < kWgRK / 16; ++ks) {
-                        const uint64_t koff = (uint64_t)(16 * ks);
-                        const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
-                        const uint64_t b_hi = b_hi0 + shb + koff, b_lo = b_lo0 + shb + koff;
-                        umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
-                        umma_bf16(td, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(td, a_hi, b_hi, idesc, 1u);
-                    }
-                }
-                accum = 1u;
-                umma_commit(BAR(EMPTY + st));
-            }
-            umma_commit(BAR(ACC));
-        }
-        __syncwarp();
-    } else if (warp >= 4) {
-        mbar_wait(BAR(ACC), 0);
-        tc_fence_after();
-        const int q4 = warp & 3;
-        const int m = ca0 + q4 * 32 + lane;
-        const bool m_ok = m < SA.C;
-        const int sM = swap ? L.w_sg : L.w_sp, sN = swap ? L.w_sp : L.w_sg;
-        for (int t = (warp - 4) >> 2; t < ntap; t += 2) {
-            float* dst_t = L.dW + (long long)Gp.woff[tap0 + t] + (long long)m * sM;
-            for (int cb = 0; cb < NT; cb += 16) {
-                if (cb0 + cb >= SB.C) break;
-                __syncwarp();
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * NT + cb), v);
-                if (!m_ok) continue;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= L.scale;
-                float* dst = dst_t + (long long)(cb0 + cb) * sN;
-                if (sN == 1 && cb0 + cb + 16 <= SB.C && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (cb0 + cb + j < SB.C) atomicAdd(dst + (long long)j * sN, v[j]);
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, Gp.tmem_cols);
-    }
-}
-
 static void run_wgrad(const char* name, Problem p, bool check, int timing_iters) {
     const int To = p.T - p.fs + 1, Td = (To + 1) / 2;
     const int mo_lo = p.cs / 2, mo_hi = (p.cs + p.U) / 2, n_odd = mo_hi - mo_lo;
@@ -742,7 +577,6 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
     UmmaWgradLaunch WL;
     memset(&WL, 0, sizeof(WL));
     WL.batch = p.B; WL.dW = ddw; WL.w_sp = p.Cout; WL.w_sg = 1; WL.scale = 1.f;
-    int grp_par[kWgMaxGroups], grp_q[kWgMaxGroups];
     for (int q = 0; q < 2; ++q)
         for (int par = 0; par < 2; ++par) {
             WgGroup W;
@@ -760,7 +594,6 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
                 W.d[W.ntaps] = e >> 1; W.woff[W.ntaps] = j * p.Cin * p.Cout; ++W.ntaps;
             }
             if (W.m_hi <= W.m_lo || W.ntaps == 0) continue;
-            grp_par[WL.ngroups] = par; grp_q[WL.ngroups] = q;
             WL.grp[WL.ngroups++] = W;
         }
     if (!umma_plan_wgrad(&WL)) { printf("[%s] wgrad not eligible\n", name); exit(4); }
@@ -769,46 +602,17 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
            p.B, p.T, p.Cin, p.Cout, W0.swap, W0.NT, W0.taps_per_cta, W0.n_tapsets, W0.chunks_per_cta, WL.grid_x, WL.grid_y, WL.grid_z,
            WL.nstages, umma_wgrad_smem_bytes(WL));
 
-    // split storage: P parity planes (shared by the two classes), G per class
+    // split arena exactly as the engine builds it: one array per distinct plane view, one batched split pass
+    const size_t arena_bytes = umma_plan_wgrad_split(WL, p.B, nullptr, nullptr, nullptr);
+    if (!arena_bytes) { printf("[%s] too many distinct views for one split pass\n", name); return; }
+    uint8_t* arena;
+    CK(cudaMalloc(&arena, arena_bytes));
     WgSplit S;
-    memset(&S, 0, sizeof(S));
-    const int nchunkP = (p.Cin + 15) / 16, nchunkG = (p.Cout + 15) / 16;
-    const int RpadP = (p.T + 1) / 2 + kWgRK + kWgSpan + 64;
-    S.p_pstride = (long long)RpadP * 16; S.p_cstride = 4 * S.p_pstride; S.p_bstride = nchunkP * S.p_cstride;
-    uint8_t* dps[2];
-    uint8_t* dgs[2];
-    long long g_ps[2];
-    for (int par = 0; par < 2; ++par) {
-        CK(cudaMalloc(&dps[par], (size_t)p.B * S.p_bstride));
-        PlaneView P = WL.grp[0].P;
-        P.base = dx + par * p.Cin; P.r_hi = (par == 0) ? (p.T + 1) / 2 : p.T / 2;
-        split_plane_kernel<<<148 * 8, 256>>>(P, p.B, dps[par], nchunkP, RpadP);
-        CK(cudaGetLastError());
-    }
-    PlaneView Gv[2];
-    memset(Gv, 0, sizeof(Gv));
-    int RpadG[2];
-    for (int q = 0; q < 2; ++q) {
-        Gv[q].kind = PLANE_DIRECT;
-        Gv[q].base = (q == 0) ? dgd : dgo - (long long)mo_lo * p.Cout;
-        Gv[q].bstride = (q == 0) ? (long long)Td * p.Cout : (long long)n_odd * p.Cout;
-        Gv[q].rstride = p.Cout; Gv[q].C = p.Cout; Gv[q].r_lo = (q == 0) ? 0 : mo_lo; Gv[q].r_hi = (q == 0) ? Td : mo_hi;
-        Gv[q].blend = nullptr; Gv[q].xrows = 0; Gv[q].mid_mode = 0;
-        RpadG[q] = Gv[q].r_hi + kWgRK + 64;
-        g_ps[q] = (long long)RpadG[q] * 16;
-        CK(cudaMalloc(&dgs[q], (size_t)p.B * nchunkG * 4 * g_ps[q]));
-        split_plane_kernel<<<148 * 8, 256>>>(Gv[q], p.B, dgs[q], nchunkG, RpadG[q]);
-        CK(cudaGetLastError());
-    }
-    for (int g = 0; g < WL.ngroups; ++g) {
-        S.P[g] = dps[grp_par[g]];
-        S.G[g] = dgs[grp_q[g]];
-        S.g_pstride[g] = g_ps[grp_q[g]]; S.g_cstride[g] = 4 * S.g_pstride[g]; S.g_bstride[g] = nchunkG * S.g_cstride[g];
-    }
+    SplitJobs J;
+    umma_plan_wgrad_split(WL, p.B, arena, &S, &J);
+    printf("[%s] split arena %.1f MB in %d arrays\n", name, arena_bytes / 1e6, J.njobs);
+    CK(launch_split_views(J, 0));
     CK(cudaDeviceSynchronize());
-    CK(cudaFuncSetAttribute(presplit_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    dim3 grid(WL.grid_x, WL.grid_y, WL.grid_z);
-    const size_t smem_b = umma_wgrad_smem_bytes(WL);
 
     auto check_dw = [&](const char* which) {
         std::vector<float> dw(wn);
@@ -851,16 +655,16 @@ static void run_wgrad(const char* name, Problem p, bool check, int timing_iters)
     { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("[%s] engine WGRAD ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); } }
     if (check) check_dw("engine");
     CK(cudaMemset(ddw, 0, wn * 4));
-    presplit_wgrad_kernel<<<grid, kPwThreads, smem_b>>>(WL, S);
-    { cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    CK(launch_wgrad_umma_bulk(WL, S, 0));
+    { cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("[%s] bulk-fed WGRAD ERROR: %s\n", name, cudaGetErrorString(e)); exit(3); } }
     if (check) check_dw("bulk-fed");
     if (timing_iters > 0) {
         time_it("engine", [&]() { CK(launch_wgrad_umma(WL, 0)); });
-        time_it("bulk-fed", [&]() { presplit_wgrad_kernel<<<grid, kPwThreads, smem_b>>>(WL, S); });
+        time_it("bulk-fed", [&]() { CK(launch_wgrad_umma_bulk(WL, S, 0)); });
+        time_it("split pass", [&]() { CK(launch_split_views(J, 0)); });
     }
-    cudaFree(dx); cudaFree(dgd); cudaFree(dgo); cudaFree(ddw);
-    for (int i = 0; i < 2; ++i) { cudaFree(dps[i]); cudaFree(dgs[i]); }
+    cudaFree(dx); cudaFree(dgd); cudaFree(dgo); cudaFree(ddw); cudaFree(arena);
 }
 
 int main(int argc, char** argv) {

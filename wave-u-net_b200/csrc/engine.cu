@@ -433,56 +433,6 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
     return WUN_OK;
 }
 
-// Split arena of one layer's bulk-fed wgrad: one array per DISTINCT plane view the groups read (activation planes are shared
-// by the classes, class gradients by the planes), covering the union of the row ranges the CTAs touch.  Returns the bytes
-// needed at `batch` (arrays 256-B aligned); fills the jobs / operand table when `arena` is not null.
-static size_t plan_wgrad_split(const UmmaWgradLaunch& U, int batch, uint8_t* arena, WgSplit* S, SplitJobs* J) {
-    struct Slot { PlaneView V; int lo, hi; size_t off; };
-    std::vector<Slot> slots;
-    int p_slot[kWgMaxGroups], g_slot[kWgMaxGroups];
-    auto find = [&](const PlaneView& V, int lo, int hi) {
-        for (size_t i = 0; i < slots.size(); ++i)
-            if (memcmp(&slots[i].V, &V, sizeof(PlaneView)) == 0) {
-                slots[i].lo = std::min(slots[i].lo, lo); slots[i].hi = std::max(slots[i].hi, hi);
-                return (int)i;
-            }
-        slots.push_back({V, lo, hi, 0});
-        return (int)slots.size() - 1;
-    };
-    for (int g = 0; g < U.ngroups; ++g) {
-        const WgGroup& G = U.grp[g];
-        int dmin = G.d[0], dmax = G.d[0];
-        for (int t = 1; t < G.ntaps; ++t) { dmin = std::min(dmin, G.d[t]); dmax = std::max(dmax, G.d[t]); }
-        p_slot[g] = find(G.P, G.m_lo + dmin, G.m_hi + dmax + kWgOverreachP);
-        g_slot[g] = find(G.G, G.m_lo, G.m_hi + kWgOverreachG);
-    }
-    if ((int)slots.size() > kSplitMaxJobs) return 0;
-    size_t cur = 0;
-    for (auto& sl : slots) {
-        const int nchunk = (sl.V.C + 15) / 16, rows = (sl.hi - sl.lo + 7) / 8 * 8;
-        cur = (cur + 255) / 256 * 256;
-        sl.off = cur;
-        cur += (size_t)batch * nchunk * 4 * rows * 16;
-    }
-    if (arena) {
-        memset(S, 0, sizeof(*S));
-        memset(J, 0, sizeof(*J));
-        J->batch = batch; J->njobs = (int)slots.size();
-        for (size_t i = 0; i < slots.size(); ++i) {
-            SplitJob& job = J->job[i];
-            job.V = slots[i].V; job.out = arena + slots[i].off;
-            job.nchunk = (slots[i].V.C + 15) / 16; job.rows = (slots[i].hi - slots[i].lo + 7) / 8 * 8; job.row0 = slots[i].lo;
-        }
-        for (int g = 0; g < U.ngroups; ++g) {
-            const SplitJob& jp = J->job[p_slot[g]];
-            const SplitJob& jg = J->job[g_slot[g]];
-            S->P[g] = jp.out; S->p_pstride[g] = (long long)jp.rows * 16; S->p_nchunk[g] = jp.nchunk; S->p_row0[g] = jp.row0;
-            S->G[g] = jg.out; S->g_pstride[g] = (long long)jg.rows * 16; S->g_nchunk[g] = jg.nchunk; S->g_row0[g] = jg.row0;
-        }
-    }
-    return cur + 256;
-}
-
 static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale, int layer_index) {
     const Plan& P = h->plan;
     h->cur_layer = layer_index;
@@ -560,7 +510,7 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
     if (h->phase == 1) return WUN_OK;
     if (use_umma) {
         ++h->launches;
-        const size_t split_need = h->bulk_wgrad ? plan_wgrad_split(U, 1, nullptr, nullptr, nullptr) : 0;
+        const size_t split_need = h->bulk_wgrad ? umma_plan_wgrad_split(U, 1, nullptr, nullptr, nullptr) : 0;
         const bool bulk = split_need > 0;                 // 0: too many distinct views for one split pass -> converter-fed kernel
         if (bulk) { ++h->launches; if (h->dry) h->split_item_bytes = std::max(h->split_item_bytes, split_need); }
         if (!h->dry) {
@@ -569,7 +519,7 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
                 uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total) + h->arena_sum;
                 arena += (256 - (reinterpret_cast<uintptr_t>(arena) & 255)) & 255;
                 WgSplit S; SplitJobs J;
-                plan_wgrad_split(U, h->batch, arena, &S, &J);
+                umma_plan_wgrad_split(U, h->batch, arena, &S, &J);
                 e = launch_split_views(J, h->wstream);      // same stream as the wgrad: the arena is reused layer after layer
                 if (e == cudaSuccess) e = launch_wgrad_umma_bulk(U, S, h->wstream);
             } else {

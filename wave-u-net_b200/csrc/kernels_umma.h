@@ -126,6 +126,9 @@ struct WgSplit {            // where the wgrad groups find their operands (fille
     int p_row0[kWgMaxGroups], g_row0[kWgMaxGroups];               // plane row stored at array index 0
 };
 
+// Split arena of one layer's wgrad at `batch`: bytes needed (0 = too many distinct views); fills the jobs / operand table
+// when `arena` (256-B aligned, that many bytes) is given.
+size_t umma_plan_wgrad_split(const UmmaWgradLaunch& U, int batch, uint8_t* arena, WgSplit* S, SplitJobs* J);
 cudaError_t launch_split_views(const SplitJobs& J, cudaStream_t stream);
 cudaError_t launch_wgrad_umma_bulk(const UmmaWgradLaunch& L, const WgSplit& S, cudaStream_t stream);
 // rows one wgrad CTA can read past the last valid row of a group: G side / P side (chunk rounding + tap span)
