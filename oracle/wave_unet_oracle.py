@@ -24,7 +24,7 @@ pins this oracle instead:
     definitions; outputs AND autograd gradients are committed as fixtures.
   * the TF leaf-op semantics themselves (SAME-padding split, legacy resize_bilinear, Maximum
     sub-gradient, Adam epsilon placement) are restated from the TF-1.8 op definitions; they are made
-    observable by hand-computed micro cases in tests/test_oracle_micro.py.
+    observable by hand-computed micro cases in tests/test_oracle.py.
 So: wiring pinned by the reference's code, leaf kernels restated => "parity pinned at graph level,
 leaf ops unpinned".
 
@@ -317,7 +317,7 @@ def forward_backward(cfg, params_np, mix_np, targets_np, dtype=torch.float32, tr
 # tensors of a small net by ~1e-2 although every kernel is exact (measured: tools/grad_diag.py).  The two
 # helpers below let a checker PROVE that a gradient mismatch is exactly that: list the pre-activations near zero, redo
 # the backward with some of their slopes flipped, and compare again.
-_FLIP_STATE = {"active": False, "call": 0, "flips": (), "record": None, "tol": 0.0}
+_FLIP_STATE = {"active": False, "call": 0, "flips": (), "record": None, "tol": 0.0, "masks": None, "mask_report": None}
 
 
 def _leaky_relu_instrumented(x):
@@ -330,6 +330,22 @@ def _leaky_relu_instrumented(x):
             rel = (x.abs() / rms).reshape(-1)
             for flat in torch.nonzero(rel < st["tol"]).reshape(-1).tolist():
                 st["record"].append((float(rel[flat]), idx, int(flat)))
+    if st["masks"] is not None:
+        # slopes dictated by another implementation at the rows it keeps (forward_backward_with_masks)
+        mask = x.detach() > 0
+        for rows, given in st["masks"].get(idx, ()):
+            rows = torch.as_tensor(rows, dtype=torch.long)
+            given = torch.as_tensor(given, dtype=torch.bool)
+            own = mask[:, rows, :]
+            diff = own != given
+            n = int(diff.sum())
+            worst = 0.0
+            if n:
+                rms = float(x.detach().pow(2).mean().sqrt().clamp_min(1e-30))
+                worst = float((x.detach()[:, rows, :].abs() * diff).max()) / rms
+            st["mask_report"].append((idx, n, worst))
+            mask[:, rows, :] = given
+        return torch.where(mask, x, LEAK * x)
     mine = [f for c, f in st["flips"] if c == idx]
     if not mine:
         return F.leaky_relu(x, LEAK)
@@ -339,16 +355,16 @@ def _leaky_relu_instrumented(x):
     return torch.where(mask.reshape(x.shape), x, LEAK * x)
 
 
-def _run_instrumented(fn, flips=(), record=None, tol=0.0):
+def _run_instrumented(fn, flips=(), record=None, tol=0.0, masks=None, mask_report=None):
     global leaky_relu
     saved = leaky_relu
-    _FLIP_STATE.update(active=True, call=0, flips=tuple(flips), record=record, tol=tol)
+    _FLIP_STATE.update(active=True, call=0, flips=tuple(flips), record=record, tol=tol, masks=masks, mask_report=mask_report)
     leaky_relu = _leaky_relu_instrumented
     try:
         return fn()
     finally:
         leaky_relu = saved
-        _FLIP_STATE.update(active=False, call=0, flips=(), record=None, tol=0.0)
+        _FLIP_STATE.update(active=False, call=0, flips=(), record=None, tol=0.0, masks=None, mask_report=None)
 
 
 def near_zero_preactivations(cfg, params_np, mix_np, tol=1e-4, dtype=torch.float64):
@@ -364,6 +380,19 @@ def near_zero_preactivations(cfg, params_np, mix_np, tol=1e-4, dtype=torch.float
 def forward_backward_with_flips(cfg, params_np, mix_np, targets_np, flips, dtype=torch.float32):
     """forward_backward with the LeakyReLU slope of the listed (call index, flat index) elements inverted."""
     return _run_instrumented(lambda: forward_backward(cfg, params_np, mix_np, targets_np, dtype), flips=flips)
+
+
+def forward_backward_with_masks(cfg, params_np, mix_np, targets_np, masks, dtype=torch.float32):
+    """forward_backward where the LeakyReLU slope at given rows is DICTATED: masks = {call index: [(rows, bool[B,len(rows),C])]}
+    (True = slope 1).  Used to prove that an implementation's gradients are exact for ITS OWN activation signs: the caller
+    passes sign(saved activation) of every row the implementation keeps (rows it never computes get no gradient anyway).
+    Returns (loss, outputs, grads, report) with report = [(call index, #elements whose slope differs from the oracle's own,
+    largest |pre-activation| / layer rms among those)] - a faithful implementation differs only where the pre-activation
+    is within forward rounding noise of zero."""
+    report = []
+    loss, outs, grads = _run_instrumented(lambda: forward_backward(cfg, params_np, mix_np, targets_np, dtype),
+                                          masks=masks, mask_report=report)
+    return loss, outs, grads, report
 
 
 def explain_gradient_mismatch(cfg, params_np, mix_np, targets_np, grads_got, tol=1e-3, margin=1e-4, max_candidates=4):

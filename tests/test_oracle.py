@@ -287,3 +287,39 @@ def test_mask_flip_analysis_explains_exactly_the_flipped_elements():
     # the instrumentation leaves the oracle untouched
     _, _, g2 = O.forward_backward(cfg, params, mix, targets)
     assert all(np.array_equal(g2[k], g0[k]) for k in g0)
+
+
+def test_backward_with_dictated_slopes_and_live_rows():
+    """forward_backward_with_masks (the GPU gradient tests' proof step): with the oracle's OWN signs at the rows the
+    engine keeps (tests/helpers.live_rows) the gradients are unchanged and no slope differs; with one sign inverted the
+    report names it and the gradients move."""
+    import Config
+    from helpers import live_rows
+    for named, ov, nf in ((["full"], dict(num_layers=3, num_initial_filters=6), 40),
+                          (["baseline"], dict(num_layers=3, num_initial_filters=6), 64)):
+        cfg = Config.build_config(named, ov, experiment_id=0)["model_config"]
+        t_in, t_out = O.get_padding(cfg, nf)
+        params = O.init_params(cfg, seed=3)
+        mix, targets = O.synthetic_batch(cfg, 2, t_in, t_out, seed=4)
+        with torch.no_grad():
+            _, inter = O.forward(cfg, O._as_torch(params, torch.float32, False), torch.from_numpy(mix), True,
+                                 return_intermediates=True)
+        L = cfg["num_layers"]
+        tensors = [inter["down%d" % i] for i in range(L)] + [inter["bottleneck"]] + [inter["up%d" % i] for i in range(L)]
+        rows = live_rows(cfg, t_in)
+        assert sorted(rows) == list(range(2 * L + 1))
+        masks = {}
+        for idx, views in rows.items():
+            assert all(r.max() < tensors[idx].shape[1] for _, r in views if len(r))
+            if idx >= L:
+                assert len(views[0][1]) == tensors[idx].shape[1]
+            masks[idx] = [(r, (tensors[idx][:, r, :] > 0).numpy()) for _, r in views]
+        loss0, _, g0 = O.forward_backward(cfg, params, mix, targets)
+        loss1, _, g1, rep = O.forward_backward_with_masks(cfg, params, mix, targets, masks)
+        assert loss0 == loss1 and all(r[1] == 0 for r in rep)
+        for n in g0:
+            np.testing.assert_array_equal(g0[n], g1[n])
+        masks[L][0][1][0, 0, 0] ^= True
+        _, _, g2, rep = O.forward_backward_with_masks(cfg, params, mix, targets, masks)
+        assert [r for r in rep if r[0] == L][0][1] == 1          # (later layers see the changed forward value too)
+        assert any(np.abs(g2[n] - g0[n]).max() > 0 for n in g0)

@@ -152,6 +152,7 @@ class Engine(object):
         self.param_table = [(a.name.decode(), tuple(a.shape[:a.ndim]), int(a.offset), int(a.numel)) for a in arr]
         self.param_numel = lib.wun_param_numel(self._h)
         self._ws = {}
+        self._ws_last = None
 
     def __del__(self):
         try:
@@ -205,7 +206,7 @@ class Engine(object):
         off, rows, ch = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
         check(lib.wun_debug_tensor(self._h, name.encode(), int(batch), 1 if training else 0, ctypes.byref(off),
                                    ctypes.byref(rows), ctypes.byref(ch)))
-        ws = next(iter(self._ws.values()))
+        ws = next((w for k, w in self._ws.items() if k[:2] == (int(batch), bool(training))), self._ws_last)
         n = int(batch) * rows.value * ch.value
         return ws[off.value:off.value + n].view(int(batch), rows.value, ch.value)
 
@@ -222,13 +223,21 @@ class Engine(object):
     # ---- device calls (torch tensors supply memory and the stream) --------------------------------
     def _workspace(self, batch, training, device):
         import torch
+        # One workspace per (batch, mode, device), never freed while the engine lives: a captured CUDA graph bakes the
+        # raw pointer in, and Training.optimise alternates training steps with forward-only validation.
         key = (int(batch), bool(training), str(device))
         ws = self._ws.get(key)
         if ws is None:
             nbytes = self.workspace_bytes(batch, training)
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
-            self._ws = {key: ws}          # keep one workspace alive (the latest shape)
+            self._ws[key] = ws
+        self._ws_last = ws
         return ws
+
+    def release_workspaces(self):
+        """Drop every cached workspace (only safe when no captured graph refers to them)."""
+        self._ws = {}
+        self._ws_last = None
 
     @staticmethod
     def _stream():
