@@ -123,6 +123,22 @@ int wun_forward_backward(WunHandle* h, const float* params, const float* mix, co
  * `step` = t >= 1.  One fused pass over the flat buffers. */
 int wun_adam_step(WunHandle* h, float* params, const float* grads, float* m, float* v, int64_t step,
                   float lr, float beta1, float beta2, float eps, void* stream);
+/* The same update with the step-dependent part on the device, as TF keeps it (variables beta1_power / beta2_power):
+ * `state` = DEVICE float[3] {beta1_power, beta2_power, step}, initialised by the caller to {beta1, beta2, 0};
+ * lr_t = lr * sqrt(1 - state[1]) / (1 - state[0]) is computed inside the kernel and the accumulators advance
+ * ({*beta1, *beta2, +1}) after the update.  Nothing step-dependent is a launch argument, so a captured CUDA graph of a
+ * whole training step replays correctly (wun_adam_step would freeze lr_t at its capture-time value). */
+int wun_adam_step_device(WunHandle* h, float* params, const float* grads, float* m, float* v, float* state,
+                         float lr, float beta1, float beta2, float eps, void* stream);
+
+/* Data-parallel overlap (the one collective of the path): the gradient is produced from the END of the flat buffer
+ * (output layer) towards offset 0 (first down block).  Declare n buckets by their first flat offset, strictly descending, the
+ * last one 0; every later wun_forward_backward records an internal event per bucket as soon as all gradients at offsets >=
+ * first_offset[k] are final, and wun_stream_wait_grad_bucket makes `stream` (the caller's communication stream) wait for it -
+ * so bucket k's all-reduce runs while the rest of the backward pass still computes.  Works inside CUDA-graph capture (plain
+ * event record / wait).  n = 0 removes the buckets. */
+int wun_set_grad_buckets(WunHandle* h, int n, const int64_t* first_offset);
+int wun_stream_wait_grad_bucket(WunHandle* h, int k, void* stream);
 
 /* Evaluate.predict_track (Evaluate.py:117-143) device side: cut `n_windows` windows
  * [T_in, C] starting at frame positions `starts[i]` (DEVICE array, int64) out of the already padded mixture
@@ -154,6 +170,14 @@ int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int tr
  * events for the dominant-kernel roofline. */
 int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, const float* mix, int64_t batch,
                        void* workspace, int64_t workspace_bytes, void* stream, double* flops_per_launch);
+/* The same for any pass of a conv layer: pass 0 = forward, 1 = dgrad (every launch of the layer's input-gradient step; needs the
+ * activation gradients a previous wun_forward_backward left in `workspace`), 2 = wgrad + bias gradient (accumulated into
+ * `grads_scratch`, a flat buffer laid out like the parameters).  Each iteration repeats the layer's launches for that pass,
+ * weight packs included for pass 1.  *flops_per_launch = the layer's algorithmic FLOPs for that pass at this batch.
+ * bench.py uses it for the per-layer / per-family roofline table. */
+int wun_debug_run_layer(WunHandle* h, int layer, int pass, int iters, const float* params, const float* mix,
+                        float* grads_scratch, int64_t batch, void* workspace, int64_t workspace_bytes, void* stream,
+                        double* flops_per_launch);
 /* Which kernel family a conv layer uses: "simt" or "umma".  layer: 0..L-1 down, L bottleneck,
  * L+1..2L up.  pass: 0 fwd, 1 dgrad, 2 wgrad. */
 const char* wun_layer_kernel(const WunHandle* h, int layer, int pass);

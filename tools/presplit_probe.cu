@@ -684,6 +684,11 @@ int main(int argc, char** argv) {
     if (want("down2")) run_case("down2", {16, 36851, 48, 72, 15, 16366, 4105}, false, 20);
     if (want("down3")) run_case("down3", {16, 18419, 72, 96, 15, 8174, 2057}, false, 20);
     if (want("down4")) run_case("down4", {16, 9203, 96, 120, 15, 4078, 1033}, false, 20);
+    // deep (sparse, fewer tiles than SMs) layers: is the converter the limiter there?
+    if (want("down5")) run_case("down5", {16, 4595, 120, 144, 15, 2030, 521}, false, 20);
+    if (want("down7")) run_case("down7", {16, 1139, 168, 192, 15, 494, 137}, false, 20);
+    if (want("down9")) run_case("down9", {16, 275, 216, 240, 15, 110, 41}, false, 20);
+    if (want("down11")) run_case("down11", {16, 59, 264, 288, 15, 14, 17}, false, 20);
     if (want("wsmall")) {
         run_wgrad("wg_tiny",   { 1, 300,  16, 16,  3,  40, 101}, true, 0);
         run_wgrad("wg_taps15", { 2, 1500, 32, 48, 15, 200, 401}, true, 0);

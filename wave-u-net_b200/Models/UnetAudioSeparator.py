@@ -48,9 +48,32 @@ class UnetAudioSeparator:
         self.grads = None
         self.adam_m = None
         self.adam_v = None
-        self.global_step = 0
+        self._adam_state = None     # device float32[3] {beta1_power, beta2_power, step}: TF's beta*_power variables
+        self._betas = (0.9, 0.999)
+        self._step0 = 0
         self._loss = None
         self.seed = 1337            # Training.py:22
+
+    # global_step lives on the device next to Adam's beta-power accumulators, so that a CUDA-graph replay of a whole
+    # training step (bench.py, wun/prefetch.py) advances it and uses the right bias correction every replay.
+    @property
+    def global_step(self):
+        if self._adam_state is None:
+            return self._step0
+        return int(round(float(self._adam_state[2].item())))
+
+    @global_step.setter
+    def global_step(self, n):
+        self._step0 = int(n)
+        if self._adam_state is not None:
+            self._write_adam_state()
+
+    def _write_adam_state(self):
+        import torch
+        b1, b2 = self._betas
+        n = self._step0
+        vals = torch.tensor([b1 ** (n + 1), b2 ** (n + 1), float(n)], dtype=torch.float32)
+        self._adam_state.copy_(vals.to(self._adam_state.device))
 
     # ------------------------------------------------------------------------------------------
     # reference API
@@ -123,9 +146,12 @@ class UnetAudioSeparator:
         eng = next(iter(self._engines.values()))
         return OrderedDict((n, self.grads[o:o + c].view(*s)) for n, s, o, c in eng.param_table)
 
-    def load_variables(self, values, device="cuda", num_frames=None, input_frames=None):
-        """values: mapping TF-name -> array (e.g. read from a checkpoint); all variables required."""
+    def load_variables(self, values, device=None, num_frames=None, input_frames=None):
+        """values: mapping TF-name -> array (e.g. read from a checkpoint); all variables required.  device: where the
+        flat buffer goes - default: where the current variables live, else the current CUDA device."""
         import torch
+        if device is None:
+            device = self.params.device if self.params is not None else torch.device("cuda", torch.cuda.current_device())
         eng = self.engine(num_frames, input_frames) if (num_frames or input_frames) else \
             next(iter(self._engines.values()))
         flat = np.zeros(eng.param_numel, np.float32)
@@ -135,6 +161,9 @@ class UnetAudioSeparator:
             flat[off:off + numel] = a.reshape(-1)
         self.params = torch.from_numpy(flat).to(device)
         self.grads = self.adam_m = self.adam_v = None
+        if self._adam_state is not None:
+            self._step0 = self.global_step
+            self._adam_state = None
 
     # ------------------------------------------------------------------------------------------
     # the training half of the graph (Training.py:50-77)
@@ -146,6 +175,8 @@ class UnetAudioSeparator:
             self.adam_m = torch.zeros_like(self.params)
             self.adam_v = torch.zeros_like(self.params)
             self._loss = torch.zeros(1, dtype=torch.float32, device=self.params.device)
+            self._adam_state = torch.zeros(3, dtype=torch.float32, device=self.params.device)
+            self._write_adam_state()
 
     def stack_targets(self, batch):
         """dict name -> [B,T_out,C]  ->  [K,B,T_out,C] in source_names order."""
@@ -168,6 +199,9 @@ class UnetAudioSeparator:
     def adam_step(self, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
         """tf.train.AdamOptimizer(learning_rate).minimize step on the separator variables (:77)."""
         eng = next(iter(self._engines.values()))
-        self.global_step += 1
-        eng.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.global_step, learning_rate, beta1,
-                      beta2, epsilon)
+        if (beta1, beta2) != self._betas:
+            self._step0 = self.global_step
+            self._betas = (beta1, beta2)
+            self._write_adam_state()
+        eng.adam_step_device(self.params, self.grads, self.adam_m, self.adam_v, self._adam_state, learning_rate, beta1,
+                             beta2, epsilon)

@@ -98,12 +98,17 @@ def train(model_config, experiment_id, load_model=None, batch_source=None, sep=N
     lr = model_config["init_sup_sep_lr"]
     global_batch = int(in_shape[0])
     running, t0 = 0.0, time.time()
+    # N > 1: the gradient all-reduce runs bucketed on a communication stream while backward still computes
+    overlap = parallel.BucketedAllReduce(eng, sep.grads) if (world > 1 and sep.grads.is_cuda) else None
     for it in range(model_config["epoch_it"]):                      # :103
         mix, tg = _to_device(next(batch_source), names, device)
         mix_l = parallel.shard_batch(mix, rank, world).contiguous()
         tg_l = parallel.shard_batch(tg, rank, world, dim=1).contiguous()
         loss = sep.loss_and_gradients(mix_l, tg_l, grad_scale=parallel.grad_scale_for(mix_l.shape[0], global_batch))
-        parallel.allreduce_gradients(sep.grads)
+        if overlap is not None:
+            overlap.run()
+        else:
+            parallel.allreduce_gradients(sep.grads)
         sep.adam_step(lr)
         if log_every and (it + 1) % log_every == 0 and rank == 0:
             running = float(loss.item())

@@ -67,8 +67,8 @@ struct WunHandle {
     cudaEvent_t join_event = nullptr;
     int fork_used = 0;
     bool use_side = true;                // WUN_SIDE_STREAM=0 disables
-    bool first_fast = false;             // WUN_FIRST_LAYER=1: dedicated first-layer kernels (kernels_first.cu; experimental)
-    bool bulk_wgrad = false;             // WUN_BULK_WGRAD=1: split pass + bulk-copy-fed tcgen05 wgrad (experimental)
+    bool first_fast = true;              // dedicated first-layer kernels (kernels_first.cu); WUN_FIRST_LAYER=0 = generic path
+    bool bulk_wgrad = true;              // split pass + bulk-copy-fed tcgen05 wgrad; WUN_BULK_WGRAD=0 = converter-fed kernel
     size_t split_item_bytes = 0;         // per batch item: largest split arena any layer's wgrad needs (dry run)
     cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
     // weight packs are hoisted off the critical path: phase 1 enqueues every pack kernel of the step on the side stream
@@ -78,12 +78,17 @@ struct WunHandle {
     size_t arena_sum = 0;                // total pack bytes of one forward+backward (dry run)
     cudaEvent_t packs_event = nullptr;
     bool packs_pending = false;          // main stream has not yet waited for the hoisted packs
-    // WUN_PACK_EVENTS=1 (experimental): one event per FORWARD weight pack, so that forward conv i waits for pack i only
-    // instead of for all ~60 packs of the step (the backward convs still wait for the single packs_event)
-    bool pack_events_on = false;
+    // one event per FORWARD weight pack, so that forward conv i waits for pack i only instead of for all ~60 packs of the
+    // step (the backward convs still wait for the single packs_event); WUN_PACK_EVENTS=0 disables
+    bool pack_events_on = true;
     std::vector<cudaEvent_t> pack_events;
     int pack_idx = 0;                    // forward tensor-core conv counter of the current phase
     std::vector<std::string>* audit = nullptr;   // dry runs: one line per tensor-core launch (wun_debug_plan)
+    // data-parallel overlap: gradient buckets in PRODUCTION order (output layer first, down0 last); bucket k = flat offsets
+    // >= bucket_first[k] (and below bucket k-1's).  bucket_events[k] is recorded once every gradient of the bucket is final.
+    std::vector<int64_t> bucket_first;
+    std::vector<cudaEvent_t> bucket_events;
+    int bucket_next = 0;
     // per-call state
     bool dry = false;
     int64_t launches = 0;
@@ -559,6 +564,23 @@ static int fork_side(WunHandle* h) {
     return WUN_OK;
 }
 
+// Every gradient at a flat offset >= `ready_from` has been enqueued (side-stream work in order, main-stream work up to the
+// last fork): record the events of the buckets this completes.  Called right after a fork (side waits for main) or at the end.
+static int mark_grads_ready(WunHandle* h, int64_t ready_from, cudaStream_t on) {
+    if (h->dry || h->phase == 1) return WUN_OK;
+    while (h->bucket_next < (int)h->bucket_first.size() && h->bucket_first[h->bucket_next] >= ready_from) {
+        WUN_CUDA_OK(cudaEventRecord(h->bucket_events[h->bucket_next], on));
+        ++h->bucket_next;
+    }
+    return WUN_OK;
+}
+
+static int64_t op_first_offset(const Plan& P, const ConvOp& op, const UpsampleSpec* us) {
+    int64_t o = std::min(P.params[op.w_param].offset, P.params[op.b_param].offset);
+    if (us && us->interp_param >= 0) o = std::min<int64_t>(o, P.params[us->interp_param].offset);
+    return o;
+}
+
 static void fill_output_launch(const WunHandle* h, OutputLaunch* O, const float* targets, float* outputs, float* loss,
                                int training) {
     const Plan& P = h->plan;
@@ -626,9 +648,14 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         launch_output_wgrad(O, grads, scale, h->stream);
         launch_output_dgrad(O, const_cast<float*>(tensor_ptr(h, P.grad_twin[P.t_feat])), h->stream);
     }
+    if (h->phase != 1) h->bucket_next = 0;
+    int64_t ready_from = h->plan.param_numel;      // lowest flat offset whose gradient is complete once the next fork is passed
+    if (P.nconv > 0) ready_from = std::min<int64_t>(P.params[P.out_w_param[0]].offset, P.params[P.out_b_param[0]].offset);
     for (int i = L - 1; i >= 0; --i) {
         const ConvOp& op = P.up[i];
         if ((rc = fork_side(h)) != WUN_OK) return rc;
+        if ((rc = mark_grads_ready(h, ready_from, h->wstream)) != WUN_OK) return rc;
+        ready_from = std::min(ready_from, op_first_offset(P, op, &P.ups[i]));
         if ((rc = conv_wgrad(h, op, grads, scale, L + 1 + i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, op, h->bwd_up[i], L + 1 + i)) != WUN_OK) return rc;
         const UpsampleSpec& us = P.ups[i];
@@ -645,10 +672,14 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         if (!h->dry && h->phase != 1) launch_upsample_bwd(U, h->stream);
     }
     if ((rc = fork_side(h)) != WUN_OK) return rc;
+    if ((rc = mark_grads_ready(h, ready_from, h->wstream)) != WUN_OK) return rc;
+    ready_from = std::min(ready_from, op_first_offset(P, P.bottleneck, nullptr));
     if ((rc = conv_wgrad(h, P.bottleneck, grads, scale, L)) != WUN_OK) return rc;
     if ((rc = conv_dgrad(h, P.bottleneck, h->bwd_bottleneck, L)) != WUN_OK) return rc;
     for (int i = L - 1; i >= 0; --i) {
         if ((rc = fork_side(h)) != WUN_OK) return rc;
+        if ((rc = mark_grads_ready(h, ready_from, h->wstream)) != WUN_OK) return rc;
+        ready_from = std::min(ready_from, op_first_offset(P, P.down[i], nullptr));
         if ((rc = conv_wgrad(h, P.down[i], grads, scale, i)) != WUN_OK) return rc;
         if ((rc = conv_dgrad(h, P.down[i], h->bwd_down[i], i)) != WUN_OK) return rc;
     }
@@ -656,6 +687,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
         WUN_CUDA_OK(cudaEventRecord(h->join_event, h->side));
         WUN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->join_event, 0));
     }
+    if ((rc = mark_grads_ready(h, 0, h->stream)) != WUN_OK) return rc;    // whatever is left: final after the join
     return WUN_OK;
 }
 
@@ -720,9 +752,11 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* names[3] = {"WUN_UMMA_FWD", "WUN_UMMA_DGRAD", "WUN_UMMA_WGRAD"};
       for (int i = 0; i < 3; ++i) { const char* v = getenv(names[i]); h->umma_pass[i] = !(v && v[0] == '0'); } }
     { const char* v = getenv("WUN_SIDE_STREAM"); h->use_side = !(v && v[0] == '0'); }
-    { const char* v = getenv("WUN_FIRST_LAYER"); h->first_fast = (v && v[0] == '1'); }
-    { const char* v = getenv("WUN_PACK_EVENTS"); h->pack_events_on = (v && v[0] == '1'); }
-    { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = (v && v[0] == '1'); }
+    // default ON since round 2 (validated on B200: probes + the GPU parity suite with each switch; step 8.51 -> 7.39 ms);
+    // "=0" selects the round-1 path for A/B runs
+    { const char* v = getenv("WUN_FIRST_LAYER"); h->first_fast = !(v && v[0] == '0'); }
+    { const char* v = getenv("WUN_PACK_EVENTS"); h->pack_events_on = !(v && v[0] == '0'); }
+    { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = !(v && v[0] == '0'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);
@@ -745,6 +779,7 @@ int wun_destroy(WunHandle* h) {
         if (h->join_event) cudaEventDestroy(h->join_event);
         if (h->packs_event) cudaEventDestroy(h->packs_event);
         for (auto e : h->pack_events) cudaEventDestroy(e);
+        for (auto e : h->bucket_events) cudaEventDestroy(e);
         if (h->side) cudaStreamDestroy(h->side);
         delete h;
     }
@@ -849,8 +884,42 @@ int wun_adam_step(WunHandle* h, float* params, const float* grads, float* m, flo
     int rc = check_device();
     if (rc != WUN_OK) return rc;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    launch_adam(params, grads, m, v, h->plan.param_numel, (float)lr_t, beta1, beta2, eps, (cudaStream_t)stream);
+    launch_adam(params, grads, m, v, h->plan.param_numel, (float)lr_t, beta1, beta2, eps, nullptr, (cudaStream_t)stream);
     WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_adam_step_device(WunHandle* h, float* params, const float* grads, float* m, float* v, float* state, float lr,
+                         float beta1, float beta2, float eps, void* stream) {
+    if (!h || !params || !grads || !m || !v || !state) return set_err(WUN_E_INVALID, "null argument");
+    int rc = check_device();
+    if (rc != WUN_OK) return rc;
+    launch_adam(params, grads, m, v, h->plan.param_numel, lr, beta1, beta2, eps, state, (cudaStream_t)stream);
+    WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_set_grad_buckets(WunHandle* h, int n, const int64_t* first_offset) {
+    if (!h || n < 0 || (n > 0 && !first_offset)) return set_err(WUN_E_INVALID, "bad argument");
+    for (int k = 0; k < n; ++k) {
+        if (first_offset[k] < 0 || first_offset[k] >= h->plan.param_numel || (k > 0 && first_offset[k] >= first_offset[k - 1]))
+            return set_err(WUN_E_INVALID, "bucket offsets must be strictly descending (production order) inside the flat buffer");
+    }
+    if (n > 0 && first_offset[n - 1] != 0) return set_err(WUN_E_INVALID, "the last bucket must start at offset 0");
+    if (n > 0) { int rc = check_device(); if (rc != WUN_OK) return rc; }
+    while ((int)h->bucket_events.size() < n) {
+        cudaEvent_t e;
+        WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->bucket_events.push_back(e);
+    }
+    h->bucket_first.assign(first_offset, first_offset + n);
+    h->bucket_next = 0;
+    return WUN_OK;
+}
+
+int wun_stream_wait_grad_bucket(WunHandle* h, int k, void* stream) {
+    if (!h || k < 0 || k >= (int)h->bucket_first.size()) return set_err(WUN_E_INVALID, "no such gradient bucket");
+    WUN_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, h->bucket_events[k], 0));
     return WUN_OK;
 }
 
@@ -913,30 +982,60 @@ int64_t wun_debug_plan(const WunHandle* hc, int64_t batch, char* buf, int64_t ca
     return (int64_t)s.size() + 1;
 }
 
-int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, const float* mix, int64_t batch,
-                       void* workspace, int64_t workspace_bytes, void* stream, double* flops_per_launch) {
-    if (!h || iters < 1) return set_err(WUN_E_INVALID, "bad argument");
+static double op_forward_flops(const ConvOp& op, int64_t batch) {
+    double f = 0;
+    for (const auto& c : op.classes) {
+        double ks = 0;
+        for (const auto& t : c.terms) ks += op.planes[t.plane].C;
+        f += 2.0 * std::max(0, c.m_hi - c.m_lo) * ks * op.cout;
+    }
+    return f * batch;
+}
+
+int wun_debug_run_layer(WunHandle* h, int layer, int pass, int iters, const float* params, const float* mix, float* grads_scratch,
+                        int64_t batch, void* workspace, int64_t workspace_bytes, void* stream, double* flops_per_launch) {
+    if (!h || iters < 1 || pass < 0 || pass > 2) return set_err(WUN_E_INVALID, "bad argument");
     const int L = h->plan.cfg.num_layers;
     if (layer < 0 || layer > 2 * L) return set_err(WUN_E_INVALID, "layer out of range");
+    if (pass == 2 && !grads_scratch) return set_err(WUN_E_INVALID, "wgrad pass needs a gradient scratch buffer");
     int rc = begin_call(h, params, mix, batch, true, workspace, workspace_bytes, stream, false);
     if (rc != WUN_OK) return rc;
     const ConvOp& op = (layer < L) ? h->plan.down[layer] : (layer == L ? h->plan.bottleneck : h->plan.up[layer - L - 1]);
+    const OpBackward& ob = (layer < L) ? h->bwd_down[layer] : (layer == L ? h->bwd_bottleneck : h->bwd_up[layer - L - 1]);
     if (flops_per_launch) {
-        double f = 0;
-        for (const auto& c : op.classes) {
-            double ks = 0;
-            for (const auto& t : c.terms) ks += op.planes[t.plane].C;
-            f += 2.0 * std::max(0, c.m_hi - c.m_lo) * ks * op.cout;
+        // algorithmic (live-position) FLOPs: dgrad = the forward MACs of the planes that need a gradient, wgrad = all of them
+        double f = op_forward_flops(op, batch);
+        if (pass == 1) {
+            double keep = 0, all = 0;
+            for (const auto& c : op.classes)
+                for (const auto& t : c.terms) {
+                    const double w = (double)std::max(0, c.m_hi - c.m_lo) * op.planes[t.plane].C;
+                    all += w;
+                    if (op.plane_grad_tensor[t.plane] != -2) keep += w;
+                }
+            f = (all > 0) ? f * keep / all : 0;
         }
-        *flops_per_launch = f * batch;
+        *flops_per_launch = f;
     }
-    h->debug_iters = iters;
-    h->phase = 0; h->arena_cur = 0;
-    rc = conv_forward(h, op, layer);
-    h->debug_iters = 0;
+    h->phase = 0; h->arena_cur = 0; h->wstream = h->stream;
+    if (pass == 0) {
+        h->debug_iters = iters;
+        rc = conv_forward(h, op, layer);
+        h->debug_iters = 0;
+    } else {
+        for (int i = 0; i < iters && rc == WUN_OK; ++i) {
+            h->arena_cur = 0;
+            rc = (pass == 1) ? conv_dgrad(h, op, ob, layer) : conv_wgrad(h, op, grads_scratch, 1.f, layer);
+        }
+    }
     if (rc != WUN_OK) return rc;
     WUN_CUDA_OK(cudaGetLastError());
     return WUN_OK;
+}
+
+int wun_debug_run_conv(WunHandle* h, int layer, int iters, const float* params, const float* mix, int64_t batch,
+                       void* workspace, int64_t workspace_bytes, void* stream, double* flops_per_launch) {
+    return wun_debug_run_layer(h, layer, 0, iters, params, mix, nullptr, batch, workspace, workspace_bytes, stream, flops_per_launch);
 }
 
 int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,

@@ -75,7 +75,7 @@ void launch_output_wgrad(const OutputLaunch& L, float* grads, float scale, cudaS
 void launch_upsample_bwd(UpsampleBwdLaunch L, cudaStream_t stream);
 void launch_sigmoid(const float* x, float* y, int n, cudaStream_t stream);
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
-                 float eps, cudaStream_t stream);
+                 float eps, float* state, cudaStream_t stream);
 void launch_gather_windows(const float* padded, long long n_padded, const long long* starts, int n_windows,
                            int T_in, int C, float* out, cudaStream_t stream);
 void launch_scatter_windows(const float* outs, const long long* starts, int n_windows, int n_sources, int T_out,

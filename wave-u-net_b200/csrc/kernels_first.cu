@@ -1,7 +1,8 @@
 // kernels_first.cu - dedicated CUDA-core kernels for the first down block (C_in = 1 | 2 waveform channels;
 // UnetAudioSeparator.py:97-100 with i = 0): forward and weight (+ bias) gradient.  Memory-shaped work (AI 13 FLOP/B) that
-// stays off the tensor cores; the generic plane kernels cost 6 % of the M4 step on it.  EXPERIMENTAL: enabled with
-// WUN_FIRST_LAYER=1 (engine.cu), validated by tools/first_layer_probe before it becomes the default.
+// stays off the tensor cores; the generic plane kernels cost 6 % of the M4 step on it.  Default since round 2
+// (tools/first_layer_probe on B200, M4 B=16: forward 202 -> 71 us, weight + bias gradient 446 -> 220 us); WUN_FIRST_LAYER=0
+// selects the generic plane kernels.
 //   first_fwd_kernel   thread = 2 output rows x all N filters in registers; x staged de-interleaved by parity so that the
 //                      stride-2 row reads are conflict-free; weights read as warp-broadcast float4 from shared memory
 //   first_wgrad_kernel 16 thread groups take the rows of a chunk round-robin; thread = 6 (tap, channel) x 8 filter

@@ -638,10 +638,16 @@ void launch_sigmoid(const float* x, float* y, int n, cudaStream_t stream) {
     sigmoid_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, y, n);
 }
 
-// tf.train.AdamOptimizer: p -= lr_t * m / (sqrt(v) + eps), lr_t folded on the host (Training.py:77)
+// tf.train.AdamOptimizer: p -= lr_t * m / (sqrt(v) + eps) (Training.py:77).  lr_t comes either folded on the host
+// (state == nullptr) or from the device-resident accumulators state = {beta1_power, beta2_power, step} that TF keeps as
+// the variables beta1_power / beta2_power: lr_t = lr * sqrt(1 - beta2_power) / (1 - beta1_power).  The second form is
+// what a CUDA-graph replay needs - nothing step-dependent is baked into the launch; adam_advance_kernel moves the
+// accumulators after the update, like TF's _finish().
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, long long n,
-                                                    float lr_t, float b1, float b2, float eps) {
+                                                    float lr_t, float b1, float b2, float eps,
+                                                    const float* __restrict__ state) {
+    if (state) lr_t = lr_t * sqrtf(1.f - state[1]) / (1.f - state[0]);
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 3 < n) {
@@ -668,12 +674,18 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         }
     }
 }
+__global__ void adam_advance_kernel(float* state, float b1, float b2) {
+    state[0] *= b1;
+    state[1] *= b2;
+    state[2] += 1.f;
+}
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
-                 float eps, cudaStream_t stream) {
+                 float eps, float* state, cudaStream_t stream) {
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, lr_t, b1, b2, eps);
+    adam_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, lr_t, b1, b2, eps, state);
+    if (state) adam_advance_kernel<<<1, 1, 0, stream>>>(state, b1, b2);
 }
 
 // Evaluate.py:131-132 (gather) and :138-139 (scatter, plain overwrite; later windows win because

@@ -1123,7 +1123,8 @@ cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (WUN_BULK_WGRAD=1, engine.cu; validated by tools/presplit_probe first): wgrad fed by bulk copies.
+// Bulk-copy-fed wgrad (default; WUN_BULK_WGRAD=0 selects the converter-fed kernel above).  Validated on B200 by
+// tools/presplit_probe (down3: 241 -> 137 us) and the GPU parity suite.
 // A batched "split pass" materialises every plane view the layer's wgrad groups read (activation planes incl. interpolated
 // MID planes, and the class gradients) as hi/lo bf16 atom planes  [batch][16-ch chunk][hi a0|hi a1|lo a0|lo a1][row][16 B]
 // with zero rows around the valid range; the wgrad kernel then fills its stages with cp.async.bulk issued by ONE thread

@@ -16,9 +16,9 @@ SYMBOLS = [
     "wun_get_padding", "wun_create", "wun_create_for_input", "wun_destroy", "wun_input_frames",
     "wun_output_frames", "wun_param_count", "wun_param_numel", "wun_param_table", "wun_workspace_bytes",
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
-    "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step",
+    "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step", "wun_adam_step_device", "wun_set_grad_buckets", "wun_stream_wait_grad_bucket",
     "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
-    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_crc32c", "wun_debug_plan",
+    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_debug_run_layer", "wun_crc32c", "wun_debug_plan",
 ]
 
 
@@ -65,6 +65,9 @@ def _load():
     lib.wun_forward.argtypes = [H, VP, VP, I64, ctypes.c_int, VP, VP, I64, VP]
     lib.wun_forward_backward.argtypes = [H, VP, VP, VP, I64, VP, VP, VP, F, VP, I64, VP]
     lib.wun_adam_step.argtypes = [H, VP, VP, VP, VP, I64, F, F, F, F, VP]
+    lib.wun_adam_step_device.argtypes = [H, VP, VP, VP, VP, VP, F, F, F, F, VP]
+    lib.wun_set_grad_buckets.argtypes = [H, ctypes.c_int, P(I64)]
+    lib.wun_stream_wait_grad_bucket.argtypes = [H, ctypes.c_int, VP]
     lib.wun_gather_windows.argtypes = [H, VP, I64, VP, I64, VP, VP]
     lib.wun_scatter_windows.argtypes = [H, VP, VP, I64, VP, I64, VP]
     lib.wun_last_error.restype = ctypes.c_char_p
@@ -73,6 +76,8 @@ def _load():
     lib.wun_describe.restype = I64
     lib.wun_debug_tensor.argtypes = [H, ctypes.c_char_p, I64, ctypes.c_int, P(I64), P(I64), P(ctypes.c_int32)]
     lib.wun_debug_run_conv.argtypes = [H, ctypes.c_int, ctypes.c_int, VP, VP, I64, VP, I64, VP, P(ctypes.c_double)]
+    lib.wun_debug_run_layer.argtypes = [H, ctypes.c_int, ctypes.c_int, ctypes.c_int, VP, VP, VP, I64, VP, I64, VP,
+                                        P(ctypes.c_double)]
     lib.wun_layer_kernel.argtypes = [H, ctypes.c_int, ctypes.c_int]
     lib.wun_layer_kernel.restype = ctypes.c_char_p
     lib.wun_debug_plan.argtypes = [H, I64, ctypes.c_char_p, I64]
@@ -217,7 +222,19 @@ class Engine(object):
         ws = self._workspace(B, True, mix.device)
         fl = ctypes.c_double()
         check(lib.wun_debug_run_conv(self._h, int(layer), int(iters), params.data_ptr(), mix.data_ptr(), B,
-                                     ws.data_ptr(), ws.numel() * 4, self._stream(), ctypes.byref(fl)))
+                                     ws.data_ptr(), ws.numel() * 4, self._stream(mix.device), ctypes.byref(fl)))
+        return fl.value
+
+    def run_layer_pass(self, layer, pass_, iters, params, mix, grads_scratch=None):
+        """Benchmark hook: enqueue every launch of one pass (0 fwd, 1 dgrad, 2 wgrad) of conv layer `layer` `iters` times
+        on the current stream, on the tensors a previous training step left in the workspace.  Returns the pass's
+        algorithmic FLOPs per iteration."""
+        B = mix.shape[0]
+        ws = self._workspace(B, True, mix.device)
+        fl = ctypes.c_double()
+        check(lib.wun_debug_run_layer(self._h, int(layer), int(pass_), int(iters), params.data_ptr(), mix.data_ptr(),
+                                      grads_scratch.data_ptr() if grads_scratch is not None else None, B,
+                                      ws.data_ptr(), ws.numel() * 4, self._stream(mix.device), ctypes.byref(fl)))
         return fl.value
 
     # ---- device calls (torch tensors supply memory and the stream) --------------------------------
@@ -240,40 +257,79 @@ class Engine(object):
         self._ws_last = None
 
     @staticmethod
-    def _stream():
+    def _stream(device=None):
+        """The current torch stream of the tensors' device (not of whatever device happens to be current)."""
         import torch
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def _check_io(self, mix, targets=None, out=None, flat=()):
+        import torch
+        B = mix.shape[0]
+        K, C = self.cfg.num_sources, self.cfg.num_channels
+        assert mix.is_cuda and mix.dtype == torch.float32 and mix.is_contiguous(), "mix must be a contiguous float32 CUDA tensor"
+        assert tuple(mix.shape[1:]) == (self.T_in, C), ("mix shape", tuple(mix.shape), "expected [B, %d, %d]" % (self.T_in, C))
+        for name, t in (("targets", targets), ("outputs", out)):
+            if t is None:
+                continue
+            assert t.is_cuda and t.device == mix.device and t.dtype == torch.float32 and t.is_contiguous(), name
+            assert tuple(t.shape) == (K, B, self.T_out, C), (name, tuple(t.shape), "expected", (K, B, self.T_out, C))
+        for t in flat:
+            assert t.is_cuda and t.device == mix.device and t.dtype == torch.float32 and t.is_contiguous()
+            assert t.numel() >= self.param_numel, ("flat buffer too small", t.numel(), self.param_numel)
 
     def forward(self, params, mix, training, out=None):
         import torch
         B = mix.shape[0]
         K, C = self.cfg.num_sources, self.cfg.num_channels
-        assert mix.is_cuda and mix.dtype == torch.float32 and mix.is_contiguous()
-        assert tuple(mix.shape[1:]) == (self.T_in, C), (tuple(mix.shape), self.T_in, C)
         if out is None:
             out = torch.empty((K, B, self.T_out, C), dtype=torch.float32, device=mix.device)
+        self._check_io(mix, out=out, flat=(params,))
         ws = self._workspace(B, False, mix.device)
-        check(lib.wun_forward(self._h, params.data_ptr(), mix.data_ptr(), B, 1 if training else 0, out.data_ptr(),
-                              ws.data_ptr(), ws.numel() * 4, self._stream()))
+        with torch.cuda.device(mix.device):
+            check(lib.wun_forward(self._h, params.data_ptr(), mix.data_ptr(), B, 1 if training else 0, out.data_ptr(),
+                                  ws.data_ptr(), ws.numel() * 4, self._stream(mix.device)))
         return out
 
     def forward_backward(self, params, mix, targets, grads, loss, grad_scale=1.0, out=None):
+        import torch
         B = mix.shape[0]
+        self._check_io(mix, targets=targets, out=out, flat=(params, grads))
         ws = self._workspace(B, True, mix.device)
-        check(lib.wun_forward_backward(self._h, params.data_ptr(), mix.data_ptr(), targets.data_ptr(), B,
-                                       out.data_ptr() if out is not None else None, loss.data_ptr(),
-                                       grads.data_ptr(), float(grad_scale), ws.data_ptr(), ws.numel() * 4,
-                                       self._stream()))
+        with torch.cuda.device(mix.device):
+            check(lib.wun_forward_backward(self._h, params.data_ptr(), mix.data_ptr(), targets.data_ptr(), B,
+                                           out.data_ptr() if out is not None else None, loss.data_ptr(),
+                                           grads.data_ptr(), float(grad_scale), ws.data_ptr(), ws.numel() * 4,
+                                           self._stream(mix.device)))
         return loss
 
     def adam_step(self, params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
-        check(lib.wun_adam_step(self._h, params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), int(step),
-                                float(lr), float(beta1), float(beta2), float(eps), self._stream()))
+        import torch
+        with torch.cuda.device(params.device):
+            check(lib.wun_adam_step(self._h, params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), int(step),
+                                    float(lr), float(beta1), float(beta2), float(eps), self._stream(params.device)))
+
+    def adam_step_device(self, params, grads, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        """Graph-safe Adam: `state` = device float32[3] {beta1_power, beta2_power, step} (include/wun.h)."""
+        import torch
+        with torch.cuda.device(params.device):
+            check(lib.wun_adam_step_device(self._h, params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                           state.data_ptr(), float(lr), float(beta1), float(beta2), float(eps),
+                                           self._stream(params.device)))
+
+    def set_grad_buckets(self, first_offsets):
+        """Gradient buckets in production order (include/wun.h): strictly descending first flat offsets, the last one 0."""
+        arr = (ctypes.c_int64 * len(first_offsets))(*[int(o) for o in first_offsets])
+        check(lib.wun_set_grad_buckets(self._h, len(first_offsets), arr))
+        self.grad_buckets = [int(o) for o in first_offsets]
+
+    def stream_wait_grad_bucket(self, k, stream):
+        """Make torch stream `stream` wait until bucket k of the last enqueued forward_backward is final."""
+        check(lib.wun_stream_wait_grad_bucket(self._h, int(k), ctypes.c_void_p(stream.cuda_stream)))
 
     def gather_windows(self, padded, starts, mix_batch):
         check(lib.wun_gather_windows(self._h, padded.data_ptr(), padded.shape[0], starts.data_ptr(),
-                                     starts.numel(), mix_batch.data_ptr(), self._stream()))
+                                     starts.numel(), mix_batch.data_ptr(), self._stream(padded.device)))
 
     def scatter_windows(self, outputs, starts, preds):
         check(lib.wun_scatter_windows(self._h, outputs.data_ptr(), starts.data_ptr(), starts.numel(),
-                                      preds.data_ptr(), preds.shape[1], self._stream()))
+                                      preds.data_ptr(), preds.shape[1], self._stream(preds.device)))

@@ -44,6 +44,67 @@ def allreduce_gradients(flat_grads, group=None):
     return flat_grads
 
 
+def bucket_offsets(param_table, n_buckets=4):
+    """First flat offsets of `n_buckets` gradient buckets in PRODUCTION order (descending, last = 0) for
+    Engine.set_grad_buckets.  Backward produces gradients from the end of the flat buffer (output convs, up blocks) to its
+    start (first down block), layer by layer; buckets are cut at layer boundaries (a layer = consecutive table entries
+    up to and including a '/bias'), with about the same number of layers each."""
+    starts, cur = [], None
+    for name, _, off, _ in param_table:
+        if cur is None:
+            cur = off
+        if name.endswith("/bias"):
+            starts.append(cur)
+            cur = None
+    if cur is not None:
+        starts.append(cur)
+    starts = sorted(set(starts), reverse=True)            # production order: highest offsets first
+    n = max(1, min(int(n_buckets), len(starts)))
+    per = len(starts) / float(n)
+    firsts = []
+    for k in range(1, n + 1):
+        idx = min(len(starts) - 1, int(round(k * per)) - 1)
+        o = 0 if k == n else starts[idx]
+        if not firsts or o < firsts[-1]:
+            firsts.append(o)
+    if firsts[-1] != 0:
+        firsts.append(0)
+    return firsts
+
+
+class BucketedAllReduce(object):
+    """The step's single collective, overlapped with backward: the flat gradient buffer is all-reduced (sum) in buckets on
+    a communication stream, each bucket as soon as the engine reports its gradients final (Engine.set_grad_buckets /
+    stream_wait_grad_bucket), while the remaining backward kernels keep running on the compute stream.
+
+        ar = BucketedAllReduce(engine, sep.grads)
+        sep.loss_and_gradients(mix, targets, grad_scale=1/world)     # enqueue forward + backward
+        ar.run()                                                     # enqueue the bucket all-reduces + the join
+        sep.adam_step(lr)
+
+    Plain stream / event ordering only, so the whole step (NCCL included) can be captured in one CUDA graph."""
+
+    def __init__(self, engine, flat_grads, n_buckets=4, group=None):
+        self.engine, self.grads, self.group = engine, flat_grads, group
+        firsts = bucket_offsets(engine.param_table, n_buckets)
+        engine.set_grad_buckets(firsts)
+        his = [engine.param_numel] + firsts[:-1]
+        self.views = [flat_grads[lo:hi] for lo, hi in zip(firsts, his)]
+        self.comm = torch.cuda.Stream(device=flat_grads.device)
+        self.done = torch.cuda.Event()
+
+    def run(self):
+        import torch.distributed as dist
+        dev = self.grads.device
+        cur = torch.cuda.current_stream(dev)
+        for k, view in enumerate(self.views):
+            self.engine.stream_wait_grad_bucket(k, self.comm)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        self.done.record(self.comm)
+        cur.wait_event(self.done)
+
+
 def broadcast_parameters(flat_params, src=0, group=None):
     """Make every replica start from rank `src`'s variables (the DP invariant)."""
     import torch.distributed as dist
