@@ -150,6 +150,24 @@ int wun_gather_windows(WunHandle* h, const float* padded, int64_t n_padded, cons
 int wun_scatter_windows(WunHandle* h, const float* outputs, const int64_t* starts, int64_t n_windows,
                         float* preds, int64_t n_frames, void* stream);
 
+/* Training-batch construction on the device: replaces the tf.data input pipeline of the reference for the training
+ * partition (Datasets.py:16-19 take_random_snippets, :196-214 map / shuffle / batch; Utils.py:26-36 random_amplify,
+ * :38-42 crop_sample) with ONE kernel over a track pool that is resident in HBM.
+ *   pool          [num_sources + 1][total_frames][C] float32 (device): every source in source_names order, then the
+ *                 recorded mixture; the tracks are laid end to end along the frame axis
+ *   track_offset  [n_tracks] int64 (device): first pool frame of each track;  track_length [n_tracks]: its frames
+ *   step_state    int64[1] (device): batch counter; read by the kernel, advanced by one by this call (on the stream), so
+ *                 the call can sit inside a captured CUDA graph and still draw a new batch on every replay
+ * Per example b: track = hash(seed, step, b, 0) mod n_tracks, start = hash(.., 1) mod (length - T_in) [tf.random_uniform
+ * maxval is exclusive]; with `augmentation` every source is scaled by its own gain in [0.7, 1.0) and the mix is the sum of
+ * the scaled sources in source order, otherwise the recorded mix is copied; the targets keep the centre T_out frames.
+ * Outputs: mix_out [batch, T_in, C], targets_out [num_sources][batch, T_out, C] (the layout wun_forward_backward takes);
+ * `chosen` (optional, int64 [batch][2]) receives (track, start) of every example.  Bit-exact against
+ * oracle/feeder_oracle.py.  T_in / T_out / C / num_sources are the handle's. */
+int wun_feed_batch(WunHandle* h, const float* pool, int64_t total_frames, const int64_t* track_offset,
+                   const int64_t* track_length, int64_t n_tracks, int64_t batch, int augmentation, uint64_t seed,
+                   int64_t* step_state, float* mix_out, float* targets_out, int64_t* chosen, void* stream);
+
 /* --- diagnostics -------------------------------------------------------------------------------- */
 const char* wun_last_error(void);
 const char* wun_version(void);

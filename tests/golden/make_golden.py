@@ -149,7 +149,44 @@ def padding_table():
     print("padding.json: %d rows" % len(rows))
 
 
+def feeder_case():
+    """Utils.random_amplify + Utils.crop_sample (the reference's own functions, fp32 here: the feeder is byte movement plus
+    one multiply and one sum per sample, and parity is bit-exact) on fixed snippets and fixed gains."""
+    import collections
+    import Utils as RefUtils                                   # /root/reference/Utils.py, unmodified
+    rng = np.random.default_rng(4242)
+    rec = {}
+    for ci, (names, C, t_in, t_out) in enumerate([(["accompaniment", "vocals"], 2, 40, 12),
+                                                  (["bass", "drums", "other", "vocals"], 1, 33, 33),
+                                                  (["bass", "drums", "other", "vocals"], 2, 57, 21)]):
+        tf_shim.STATE.reset(dtype=torch.float32)
+        gains = rng.uniform(0.7, 1.0, size=len(names)).astype(np.float32)
+        snips = collections.OrderedDict((n, rng.uniform(-1, 1, size=(t_in, C)).astype(np.float32)) for n in names)
+        sample = collections.OrderedDict((n, tf_shim.T(torch.tensor(v))) for n, v in snips.items())
+        sample["mix"] = tf_shim.T(torch.zeros((t_in, C)))      # overwritten by random_amplify
+        tf_shim.STATE.uniform_queue = [float(g) for g in gains]
+        out = RefUtils.random_amplify(sample)
+        out = RefUtils.crop_sample(out, (t_in - t_out) // 2)
+        rec["c%d/names" % ci] = np.array(names)
+        rec["c%d/gains" % ci] = gains
+        rec["c%d/t_out" % ci] = np.int64(t_out)
+        for n in names:
+            rec["c%d/in/%s" % (ci, n)] = snips[n]
+            rec["c%d/out/%s" % (ci, n)] = out[n].t.numpy()
+        rec["c%d/out/mix" % ci] = out["mix"].t.numpy()
+        # without augmentation only crop_sample runs (Datasets.py:204-208)
+        sample2 = collections.OrderedDict((n, tf_shim.T(torch.tensor(v))) for n, v in snips.items())
+        sample2["mix"] = tf_shim.T(torch.tensor(sum(snips.values()).astype(np.float32)))
+        out2 = RefUtils.crop_sample(sample2, (t_in - t_out) // 2)
+        for n in names:
+            rec["c%d/out_noaug/%s" % (ci, n)] = out2[n].t.numpy()
+        rec["c%d/out_noaug/mix" % ci] = out2["mix"].t.numpy()
+    np.savez_compressed(os.path.join(HERE, "feeder.npz"), **rec)
+    print("feeder.npz: 3 cases (reference Utils.random_amplify / crop_sample)")
+
+
 if __name__ == "__main__":
+    feeder_case()
     padding_table()
     for name, (named, ov, b, nf) in CASES.items():
         run_case(name, named, ov, b, nf)

@@ -34,7 +34,7 @@ class T:
     def get_shape(self):
         return Shape(self.t.shape)
 
-    def __getitem__(self, idx):
+    def __getitem__(self, idx):  # noqa: E301
         return T(self.t[idx])
 
     def _v(self, o):
@@ -60,6 +60,7 @@ class _State:
         self.rng = np.random.default_rng(seed)
         self.dtype = dtype
         self.preset = None      # optional dict name -> np array to use instead of random init
+        self.uniform_queue = []  # values tf.random_uniform returns, in call order (Utils.random_amplify)
 
 
 STATE = _State()
@@ -210,6 +211,16 @@ def install():
     nn.conv2d = _conv2d
     tf.nn = nn
     tf.trainable_variables = lambda: []
+    # data pipeline ops used by Utils.random_amplify (Utils.py:33-35): the "random" gains are popped from a queue the
+    # fixture generator fills (TF's stateful RNG cannot be reproduced; the values are inputs of the fixture instead)
+    tf.random_uniform = lambda shape, minval=0.0, maxval=1.0, **kw: T(torch.as_tensor(STATE.uniform_queue.pop(0), dtype=STATE.dtype))
+
+    def _add_n(vals):
+        acc = vals[0].t if isinstance(vals[0], T) else torch.as_tensor(vals[0])
+        for v in vals[1:]:
+            acc = acc + (v.t if isinstance(v, T) else torch.as_tensor(v))      # left to right, like the kernel
+        return T(acc)
+    tf.add_n = _add_n
     sys.modules["tensorflow"] = tf
     sys.modules["tensorflow.layers"] = layers
     sys.modules["tensorflow.image"] = image

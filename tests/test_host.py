@@ -135,7 +135,7 @@ def test_compute_entry_points_fail_loudly_without_gpu():
 # ------------------------------------------------------------------------------------------------
 # plan audit: every tensor-core launch the planner would issue, against the hardware limits (no GPU needed)
 # ------------------------------------------------------------------------------------------------
-SMEM_LIMIT = {"dense2": 200 * 1024, "sparse4": 220 * 1024, "persistent": 220 * 1024}   # cudaFuncSetAttribute values in kernels_umma.cu
+SMEM_LIMIT = {"dense2": 200 * 1024, "sparse4": 220 * 1024, "persistent": 220 * 1024, "fold": 220 * 1024}   # cudaFuncSetAttribute values in kernels_umma.cu
 
 
 def _audit(preset, batch, overrides=None):
@@ -164,6 +164,12 @@ def test_planned_tcgen05_launches_respect_hardware_limits(preset, batch):
         assert d["nteams"] == {"dense2": 2, "sparse4": 4}.get(d["kernel"], d["nteams"]) and d["nteams"] in (2, 3, 4), d
         assert d["smem"] <= SMEM_LIMIT[d["kernel"]], d
         assert d["tiles"] >= 1 and d["span"] <= 24, d
+        if d["kernel"] == "fold":                          # cluster of ksplit CTAs per tile: portable size, one wave of clusters
+            assert 1 <= d["ksplit"] <= 8 and d["tiles"] <= [0, 148, 74, 45, 33, 26, 22, 15, 15][d["ksplit"]], d   # tools/cluster_probe on B200
+            assert d["nteams"] == 4 and not d["fuse"], d
+            assert d["MT"] * 128 * (d["NPAD"] + 4) * 4 <= d["smem"], d      # the partial-accumulator tile aliases the pipeline memory
+        else:
+            assert d["ksplit"] == 0, d
     for d in wgs:
         assert d["NT"] % 16 == 0 and 16 <= d["NT"] <= 128 and d["NT"] * d["ntiles"] >= min(d["Cp"], d["Cg"]), d
         assert d["mtiles"] * 128 >= max(d["Cp"], d["Cg"]), d
@@ -176,12 +182,13 @@ def test_planned_tcgen05_launches_respect_hardware_limits(preset, batch):
 
 def test_plan_audit_matches_the_measured_configuration():
     """The tiling DESIGN.md / profiles/ describe for the benchmark (M4, batch 16): persistent 256-row tiles for down1-3,
-    two CTAs per SM in the middle, channel-split sparse launches for the deep layers."""
+    two CTAs per SM in the middle, batch-folded cluster split-K launches for the deep layers."""
     lines = _audit("baseline_stereo", 16)
     fwd = {d["layer"]: d for d in lines if d["op"] == "conv" and d["pass"] == 0}
     assert [fwd[i]["kernel"] for i in (1, 2, 3)] == ["persistent"] * 3
     assert fwd[3]["NPAD"] == 96 and fwd[3]["MT"] == 2 and fwd[3]["tmem"] == 512 and fwd[3]["nteams"] == 3
-    assert fwd[4]["kernel"] == "dense2" and fwd[8]["kernel"] == "sparse4"
+    assert fwd[4]["kernel"] == "dense2" and fwd[8]["kernel"] == "fold" and fwd[8]["ksplit"] == 3
+    assert fwd[12]["kernel"] == "fold" and fwd[12]["ksplit"] == 8 and fwd[12]["nsplit"] == 2     # bottleneck: 8 tiles x 8-CTA clusters
     assert 0 not in fwd                                                       # the first layer (C_in = 2) is a CUDA-core kernel
     assert len([d for d in lines if d["op"] == "conv"]) == 60                # the launch list of profiles/: 13 + 13 + 34
     assert len({d["layer"] for d in lines if d["op"] == "wgrad"}) == 24

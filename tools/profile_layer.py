@@ -11,14 +11,12 @@ import bench
 
 layer = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-cfg = Config.build_config([bench.PRESET], experiment_id=0)["model_config"]
-t_in, t_out, mix, tg = bench.build_problem(cfg, bench.BATCH_PER_GPU, 1337)
-sep = UnetAudioSeparator(cfg)
-eng = sep.engine(input_frames=t_in)
-sep._ensure_params(eng, torch.device("cuda"), create=True)
-mix_d, tg_d = torch.from_numpy(mix).cuda(), torch.from_numpy(tg).cuda()
-sep.loss_and_gradients(mix_d, tg_d)
-torch.cuda.synchronize()
+dev = torch.device("cuda:0")
+run = bench.TrainingRun(bench.PRESET, bench.BATCH_PER_GPU, bench.BATCH_PER_GPU, 0, 1, dev, None)
+with torch.cuda.stream(run.stream):
+    run.step()
+run.stream.synchronize()
+eng, sep, mix_d = run.eng, run.sep, run.mix_d
 torch.cuda.profiler.start()          # ncu --profile-from-start off: only the launches below are profiled
 fl = eng.run_conv_layer(layer, iters, sep.params, mix_d)
 torch.cuda.synchronize()

@@ -53,6 +53,8 @@ class UnetAudioSeparator:
         self._step0 = 0
         self._loss = None
         self.seed = 1337            # Training.py:22
+        self.last_feeder = None     # wun.feeder.DeviceFeeder Training.train built for this separator (device-side input pipeline)
+        self.last_feeder_tracks = None
 
     # global_step lives on the device next to Adam's beta-power accumulators, so that a CUDA-graph replay of a whole
     # training step (bench.py, wun/prefetch.py) advances it and uses the right bias correction every replay.

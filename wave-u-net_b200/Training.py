@@ -73,8 +73,26 @@ def _to_device(batch, names, device):
     return mix, tg
 
 
-def train(model_config, experiment_id, load_model=None, batch_source=None, sep=None, device=None, log_every=100):
-    """One epoch (reference train(), :24-121).  Returns (checkpoint path, separator)."""
+def _device_feeder(model_config, sep, eng, device, rank, world, local_batch):
+    """The training data source when none is given: synthetic tracks resident in HBM + wun.feeder.DeviceFeeder (snippet
+    sampling, random_amplify, centre crop in ONE kernel per batch: Datasets.py:196-214 / Utils.py:26-42 on the device).
+    Built once per separator and input length, re-used by every later epoch; rank r draws its own shard of the batch."""
+    from wun.feeder import DeviceFeeder, synthetic_tracks
+    key = (eng.T_in, local_batch, str(device), bool(model_config["augmentation"]))
+    if getattr(sep, "_feeder_key", None) != key:
+        tracks = synthetic_tracks(model_config["source_names"], model_config["num_channels"], 8,
+                                  (eng.T_in + 1 + eng.T_in // 4, 2 * eng.T_in), seed=4321)
+        sep.last_feeder_tracks = tracks
+        sep.last_feeder = DeviceFeeder(eng, tracks, model_config["source_names"], local_batch,
+                                       augmentation=model_config["augmentation"], seed=1337 + 7919 * rank, device=device)
+        sep._feeder_key = key
+    return sep.last_feeder
+
+
+def train(model_config, experiment_id, load_model=None, batch_source=None, sep=None, device=None, log_every=100, feeder=None):
+    """One epoch (reference train(), :24-121).  Returns (checkpoint path, separator).
+    Data: `batch_source` (an iterator of host numpy batches, e.g. SyntheticBatches) if given; otherwise, on a CUDA device,
+    the device-side feeder (`feeder="device"`, the default there); `feeder="host"` forces the numpy generator."""
     import torch
     rank, world = parallel.world()
     if device is None:
@@ -92,18 +110,26 @@ def train(model_config, experiment_id, load_model=None, batch_source=None, sep=N
     sep._ensure_params(eng, device, create=True)
     sep._ensure_training_state()
     parallel.broadcast_parameters(sep.params)
-    if batch_source is None:
-        batch_source = SyntheticBatches(model_config, in_shape, out_shape, seed=1337 + sep.global_step)
     names = model_config["source_names"]
     lr = model_config["init_sup_sep_lr"]
     global_batch = int(in_shape[0])
+    dev_feeder = None
+    if batch_source is None and feeder != "host" and device.type == "cuda":
+        lo, hi = parallel.shard_range(global_batch, rank, world)
+        local_batch = hi - lo
+        dev_feeder = _device_feeder(model_config, sep, eng, device, rank, world, local_batch)
+    elif batch_source is None:
+        batch_source = SyntheticBatches(model_config, in_shape, out_shape, seed=1337 + sep.global_step)
     running, t0 = 0.0, time.time()
     # N > 1: the gradient all-reduce runs bucketed on a communication stream while backward still computes
     overlap = parallel.BucketedAllReduce(eng, sep.grads) if (world > 1 and sep.grads.is_cuda) else None
     for it in range(model_config["epoch_it"]):                      # :103
-        mix, tg = _to_device(next(batch_source), names, device)
-        mix_l = parallel.shard_batch(mix, rank, world).contiguous()
-        tg_l = parallel.shard_batch(tg, rank, world, dim=1).contiguous()
+        if dev_feeder is not None:
+            mix_l, tg_l = dev_feeder.next_batch()                   # this rank's shard, built on the device
+        else:
+            mix, tg = _to_device(next(batch_source), names, device)
+            mix_l = parallel.shard_batch(mix, rank, world).contiguous()
+            tg_l = parallel.shard_batch(tg, rank, world, dim=1).contiguous()
         loss = sep.loss_and_gradients(mix_l, tg_l, grad_scale=parallel.grad_scale_for(mix_l.shape[0], global_batch))
         if overlap is not None:
             overlap.run()

@@ -240,7 +240,13 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
                 long long tiles = 0, mmas = 0; int max_rows = 0, span = 0;
                 for (int q = 0; q < L.ncls; ++q) {
                     const int rows = L.cls[q].m_hi - L.cls[q].m_lo;
-                    const long long tq = (long long)((rows + ch.MT * 128 - 1) / (ch.MT * 128)) * ch.nsplit * L.batch;
+                    int qspan = 0;                              // widest tap span of the class (folded tiling)
+                    for (int ta = L.cls[q].term_begin; ta < L.cls[q].term_end; ++ta)
+                        for (int tb = ta; tb < L.cls[q].term_end && L.terms[tb].plane == L.terms[ta].plane; ++tb)
+                            qspan = std::max(qspan, std::abs(L.terms[tb].d - L.terms[ta].d));
+                    const long long tq = ch.folded
+                        ? (rows > 0 ? ((long long)L.batch * (rows + qspan) + ch.MT * 128 - 1) / (ch.MT * 128) * ch.nsplit : 0)
+                        : (long long)((rows + ch.MT * 128 - 1) / (ch.MT * 128)) * ch.nsplit * L.batch;
                     tiles += tq;
                     max_rows = std::max(max_rows, rows);
                     int t = L.cls[q].term_begin;
@@ -257,9 +263,9 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
                 }
                 char line[512];
                 snprintf(line, sizeof(line), "conv layer=%d pass=%d kernel=%s N=%d NPAD=%d nsplit=%d MT=%d rows_alloc=%d span=%d tmem=%d "
-                         "TB=%d nbs=%d nteams=%d fuse=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu",
-                         h->cur_layer, h->cur_pass, ch.persistent ? "persistent" : (ch.nteams == 4 ? "sparse4" : "dense2"), L.N,
-                         ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, tiles, mmas,
+                         "TB=%d nbs=%d nteams=%d fuse=%d ksplit=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu",
+                         h->cur_layer, h->cur_pass, ch.folded ? "fold" : (ch.persistent ? "persistent" : (ch.nteams == 4 ? "sparse4" : "dense2")), L.N,
+                         ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, ch.ksplit, tiles, mmas,
                          max_rows, umma_choice_smem_bytes(ch), ch.pack_bytes);
                 h->audit->push_back(line);
             }
@@ -942,6 +948,23 @@ int wun_scatter_windows(WunHandle* h, const float* outputs, const int64_t* start
     launch_scatter_windows(outputs, (const long long*)starts, (int)n_windows, h->plan.cfg.num_sources,
                            (int)h->plan.T_out, h->plan.cfg.num_channels, preds, n_frames, (cudaStream_t)stream);
     WUN_CUDA_OK(cudaGetLastError());
+    return WUN_OK;
+}
+
+int wun_feed_batch(WunHandle* h, const float* pool, int64_t total_frames, const int64_t* track_offset,
+                   const int64_t* track_length, int64_t n_tracks, int64_t batch, int augmentation, uint64_t seed,
+                   int64_t* step_state, float* mix_out, float* targets_out, int64_t* chosen, void* stream) {
+    if (!h || !pool || !track_offset || !track_length || !step_state || !mix_out || !targets_out)
+        return set_err(WUN_E_INVALID, "null argument");
+    if (n_tracks < 1 || n_tracks > (1 << 30) || batch < 1 || batch > 65535 || total_frames < h->plan.T_in)
+        return set_err(WUN_E_INVALID, "feeder: need >= 1 track, 1 <= batch <= 65535 and a pool of at least T_in frames");
+    if (h->plan.cfg.num_sources < 1 || h->plan.cfg.num_sources > 8) return set_err(WUN_E_INVALID, "feeder: 1..8 sources");
+    int rc = check_device();
+    if (rc != WUN_OK) return rc;
+    WUN_CUDA_OK(launch_feed_batch(pool, total_frames, (const long long*)track_offset, (const long long*)track_length,
+                                  (int)n_tracks, (int)batch, h->plan.cfg.num_sources, h->plan.cfg.num_channels,
+                                  (int)h->plan.T_in, (int)h->plan.T_out, augmentation, (unsigned long long)seed,
+                                  (long long*)step_state, mix_out, targets_out, (long long*)chosen, (cudaStream_t)stream));
     return WUN_OK;
 }
 

@@ -81,4 +81,10 @@ void launch_gather_windows(const float* padded, long long n_padded, const long l
 void launch_scatter_windows(const float* outs, const long long* starts, int n_windows, int n_sources, int T_out,
                             int C, float* preds, long long n_frames, cudaStream_t stream);
 
+// kernels_feed.cu: one training batch cut out of a device-resident track pool (random snippet, random_amplify, centre crop)
+cudaError_t launch_feed_batch(const float* pool, long long total_frames, const long long* track_offset,
+                              const long long* track_length, int n_tracks, int batch, int K, int C, int T_in, int T_out,
+                              int augmentation, unsigned long long seed, long long* step_state, float* mix_out,
+                              float* targets_out, long long* chosen, cudaStream_t stream);
+
 }  // namespace wun

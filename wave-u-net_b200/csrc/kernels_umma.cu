@@ -179,10 +179,13 @@ __device__ unsigned long long g_umma_timing[16];
 #define T_NOW() clock64()
 #define T_ADD(i, v) atomicAdd(&g_umma_timing[i], (unsigned long long)(v))
 #define T_WAIT(i, stmt) do { long long t__ = clock64(); stmt; T_ADD(i, clock64() - t__); } while (0)
+#define T_MARK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_fold_trace[i] = clock64(); } while (0)
+__device__ unsigned long long g_fold_trace[32];
 #else
 #define T_NOW() 0LL
 #define T_ADD(i, v) do { } while (0)
 #define T_WAIT(i, stmt) stmt
+#define T_MARK(i) do { } while (0)
 #endif
 
 constexpr int kSlabStages = 3;
@@ -756,6 +759,339 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Batch-folded cluster split-K variant for the deep layers (down7 ... up7 at training batch sizes, everything at small
+// batch): a class there has only a handful of rows per batch item (M4: 23 + 8 at down11, 5 + 4 at the bottleneck), so
+// one 128-row tile per (item, class) wastes most of the M dimension, and the few CTAs each walk the whole
+// (plane, chunk, tap) K loop and stream the whole weight set on their own (64 CTAs x 75 us at 1-3 % of the FLOPs).
+//   * FOLDING: the rows of all batch items form one virtual row sequence, item b at [b*pitch, b*pitch + rows) with
+//     pitch = rows + widest tap span.  A slab row u maps to (item u / pitch, plane row m_lo + u % pitch + dmin); output
+//     row v of item v / pitch reads slab rows v + (d - dmin) which stay inside the same item's segment, so the tap shifts
+//     of the MMAs are unchanged; accumulator rows with v % pitch >= rows are discarded.  Tiles may straddle items.
+//   * SPLIT-K OVER A CLUSTER: the L.ksplit CTAs of a cluster share one tile; CTA k takes a contiguous range of the
+//     tile's (plane, 16-channel chunk) jobs (and only streams those jobs' weights), dumps its partial accumulator to its
+//     own shared memory, and after a cluster barrier every CTA reduces + finishes (bias / LeakyReLU / slope / accumulate)
+//     a 1/ksplit share of the tile's rows, reading the partials of its peers through distributed shared memory.
+// grid = (tiles * ksplit, nsplit, classes), cluster = (ksplit, 1, 1); warps as in plane_conv_umma_kernel<4>.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+constexpr int kFoldTeams = 4, kFoldSlabStages = 6, kFoldMaxSplit = 8;
+
+__global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold(const __grid_constant__ UmmaLaunch L) {
+    constexpr int kMmaWarp = kFoldTeams * 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) T_MARK(0);
+    const int cls = blockIdx.z, split = blockIdx.y;
+    const int S = L.ksplit;
+    const int tile = blockIdx.x / S;
+    const int krank = (int)cluster_ctarank();
+    const UmmaClass& K = L.cls[cls];
+    const int pitch = L.fold_pitch[cls];
+    const int rows_q = K.out.m_hi - K.out.m_lo;
+    const int RT = L.MT * 128;
+    const int v0 = tile * RT;
+    if (rows_q <= 0 || v0 >= L.batch * pitch) return;        // the whole cluster (same tile, same class) leaves together
+
+    int J = 0;                                               // (plane, chunk) jobs of this class; this CTA takes [j0, j1)
+    for (int g = 0; g < K.ngroups; ++g) J += (L.planes[K.groups[g].plane].C + 15) >> 4;
+    const int j0 = (int)((long long)J * krank / S), j1 = (int)((long long)J * (krank + 1) / S);
+    const bool has_work = j1 > j0;
+
+    const int NPAD = L.NPAD;
+    const uint32_t slab_bytes = 64u * L.rows_alloc;
+    const uint32_t bblk_bytes = 64u * NPAD;
+    uint8_t* slab0 = smem;
+    uint8_t* bring0 = smem + kFoldSlabStages * slab_bytes;
+    const int TB = L.TB, nbs = L.nbs;
+    const uint32_t bstage_bytes = bblk_bytes * TB;
+    // the partial-accumulator tile (RT x (NPAD+4) fp32) re-uses the pipeline memory once every MMA has retired
+    const int SWF = NPAD + 4;
+    const uint32_t pipe_bytes = kFoldSlabStages * slab_bytes + nbs * bstage_bytes;
+    const uint32_t part_bytes = (uint32_t)RT * (uint32_t)SWF * 4u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((pipe_bytes > part_bytes ? pipe_bytes : part_bytes) + 127u) / 128u * 128u);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int SLAB_FULL = 0, SLAB_EMPTY = kFoldSlabStages, B_FULL = 2 * kFoldSlabStages, B_EMPTY = 2 * kFoldSlabStages + kBStagesMax,
+              ACC_FULL = 2 * kFoldSlabStages + 2 * kBStagesMax;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
+    float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);
+    for (int i = tid; i < NPAD; i += blockDim.x) {
+        const int n = split * NPAD + i;
+        bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kFoldSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
+        for (int i = 0; i < kBStagesMax; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    if (tid == 0) T_MARK(1);
+
+    if (warp < kMmaWarp) {
+        // ===================== converters: fill the slabs of this CTA's jobs =====================
+        const int team = warp >> 2, ttid = tid & 127;
+        int ji = 0;
+        for (int g = 0; g < K.ngroups; ++g) {
+            const UmmaGroup& G = K.groups[g];
+            const PlaneView& P = L.planes[G.plane];
+            const int nchunk = (P.C + 15) >> 4;
+            for (int c = 0; c < nchunk; ++c, ++ji) {
+                if (ji < j0 || ji >= j1) continue;
+                const int jl = ji - j0;
+                if ((jl % kFoldTeams) != team) continue;
+                const int st = jl % kFoldSlabStages;
+                uint8_t* Sl = slab0 + st * slab_bytes;
+                const uint32_t atom_stride = 16u * L.rows_alloc;
+                constexpr int kRB = 3;
+                bool waited = false;
+                for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
+                    float x[kRB][16];
+#pragma unroll
+                    for (int w = 0; w < kRB; ++w) {
+                        const int rr = rbase + w * kWorkerThreads + ttid;
+                        if (rr < L.rows_alloc) {
+                            const int u = v0 + rr, bb = u / pitch, off = u - bb * pitch;     // virtual row -> (item, row)
+                            load_row16(P, bb, (bb < L.batch) ? K.out.m_lo + off + G.dmin : -(1 << 30), c * 16, x[w]);
+                        }
+                    }
+                    if (!waited) { mbar_wait(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1); waited = true; }
+#pragma unroll
+                    for (int w = 0; w < kRB; ++w) {
+                        const int rr = rbase + w * kWorkerThreads + ttid;
+                        if (rr >= L.rows_alloc) continue;
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[w][2 * i]), h1 = __float2bfloat16_rn(x[w][2 * i + 1]);
+                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i] = pack_bf16x2(x[w][2 * i] - __bfloat162float(h0), x[w][2 * i + 1] - __bfloat162float(h1));
+                        }
+                        *reinterpret_cast<uint4*>(Sl + 16u * rr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(Sl + atom_stride + 16u * rr) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<uint4*>(Sl + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(Sl + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(BAR(SLAB_FULL + st));
+                if (tid == 0 && jl == 0) T_MARK(2);
+            }
+        }
+        if (tid == 0) T_MARK(3);
+        // ===================== team 0: partial accumulator -> own shared memory (TMEM lane quarter = warp id) ==========
+        if (team == 0) {
+            float* part = reinterpret_cast<float*>(smem);
+            if (has_work) { mbar_wait(BAR(ACC_FULL), 0); tc_fence_after(); }
+            if (tid == 0) T_MARK(4);
+            for (int mt = 0; mt < L.MT; ++mt)
+                for (int cb = 0; cb < NPAD; cb += 16) {
+                    __syncwarp();
+                    float v[16];
+                    if (has_work) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + cb), v);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    }
+                    float4* dst = reinterpret_cast<float4*>(part + (size_t)(mt * 128 + warp * 32 + lane) * SWF + cb);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            tc_fence_before();
+            if (tid == 0) T_MARK(5);
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        if (has_work && elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t atom_stride = 16u * L.rows_alloc;
+            const uint32_t b_lbo = 32u * NPAD;
+            int ji = 0, bi = 0;
+            uint32_t first = 0;
+            for (int g = 0; g < K.ngroups; ++g) {
+                const UmmaGroup& G = K.groups[g];
+                const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                for (int c = 0; c < nchunk; ++c, ++ji) {
+                    if (ji < j0 || ji >= j1) continue;
+                    const int jl = ji - j0;
+                    const int st = jl % kFoldSlabStages;
+                    mbar_wait(BAR(SLAB_FULL + st), (jl / kFoldSlabStages) & 1);
+                    tc_fence_after();
+                    if (jl == 0) T_MARK(8);
+                    const uint32_t sa = smem_u32(slab0 + st * slab_bytes);
+                    const uint64_t a_hi0 = umma_desc(sa, atom_stride, 128), a_lo0 = umma_desc(sa + 2 * atom_stride, atom_stride, 128);
+                    for (int t0 = G.term_begin; t0 < G.term_end; t0 += TB, ++bi) {
+                        const int bs = bi % nbs;
+                        mbar_wait(BAR(B_FULL + bs), (bi / nbs) & 1);
+                        tc_fence_after();
+                        if (bi == 0) T_MARK(9);
+                        if (bi == 1) T_MARK(10);
+                        if (bi == 4) T_MARK(11);
+                        const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
+                        const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
+                        const int nt = min(TB, G.term_end - t0);
+                        for (int tt = 0; tt < nt; ++tt) {
+                            const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
+                            const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
+                            const uint64_t aoff = (uint64_t)(uint32_t)(L.d[t0 + tt] - G.dmin);
+                            for (int mt = 0; mt < L.MT; ++mt) {
+                                const uint64_t a_hi = a_hi0 + aoff + (uint64_t)(128u * mt), a_lo = a_lo0 + aoff + (uint64_t)(128u * mt);
+                                const uint32_t td = tmem_base + (uint32_t)(mt * NPAD);
+                                umma_bf16(td, a_lo, b_hi, idesc, first);
+                                umma_bf16(td, a_hi, b_lo, idesc, 1u);
+                                umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                            }
+                            first = 1u;
+                        }
+                        umma_commit(BAR(B_EMPTY + bs));
+                    }
+                    umma_commit(BAR(SLAB_EMPTY + st));
+                }
+            }
+            umma_commit(BAR(ACC_FULL));
+            T_MARK(12);
+        }
+        __syncwarp();
+    } else {
+        // ===================== weight loader: only the blocks of this CTA's jobs =====================
+        if (has_work && elect_one()) {
+            const uint8_t* src = K.wpack[split];
+            int bi = 0, ji = 0;
+            size_t blk = 0;
+            for (int g = 0; g < K.ngroups; ++g) {
+                const UmmaGroup& G = K.groups[g];
+                const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                const int nterm = G.term_end - G.term_begin;
+                for (int c = 0; c < nchunk; ++c, ++ji) {
+                    if (ji < j0 || ji >= j1) { blk += nterm; continue; }
+                    for (int t0 = 0; t0 < nterm; t0 += TB, ++bi) {
+                        const int nt = min(TB, nterm - t0);
+                        const int bs = bi % nbs;
+                        mbar_wait(BAR(B_EMPTY + bs), ((bi / nbs) & 1) ^ 1);
+                        mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes * nt);
+                        bulk_g2s(smem_u32(bring0 + bs * bstage_bytes), src + blk * bblk_bytes, bblk_bytes * nt, BAR(B_FULL + bs));
+                        blk += nt;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L.tmem_cols);
+    }
+    if (tid == 0) T_MARK(6);
+    cluster_sync_all();                                   // every CTA of the cluster has published its partial tile
+    if (tid == 0) T_MARK(7);
+    {
+        // ===================== reduce + finish a 1/S share of the tile's rows (all threads) =====================
+        uint32_t peer[kFoldMaxSplit];
+#pragma unroll
+        for (int s = 0; s < kFoldMaxSplit; ++s) peer[s] = (s < S) ? mapa_shared(smem_u32(smem), (uint32_t)s) : 0u;
+        const int r0 = RT * krank / S, r1 = RT * (krank + 1) / S;
+        const int n0 = split * NPAD;
+        const int Q = min(NPAD, L.N - n0) >> 2;              // real output columns of this split / 4 (host: N % 4 == 0)
+        for (int it = tid; it < (r1 - r0) * Q; it += blockDim.x) {
+            const int rl = it / Q, q = it - rl * Q;
+            const int r = r0 + rl;
+            const int v = v0 + r, bb = v / pitch, off = v - bb * pitch;
+            if (bb >= L.batch || off >= rows_q) continue;     // padding rows between the items' segments
+            const int m = K.out.m_lo + off;
+            const uint32_t eoff = ((uint32_t)r * (uint32_t)SWF + 4u * (uint32_t)q) * 4u;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int s = 0; s < kFoldMaxSplit; ++s)
+                if (s < S) { const float4 p = ld_dsmem_v4(peer[s] + eoff); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            if (L.epilogue == EPI_BIAS_LRELU) {
+                o.x += bias_s[4 * q]; o.y += bias_s[4 * q + 1]; o.z += bias_s[4 * q + 2]; o.w += bias_s[4 * q + 3];
+                o.x = fmaxf(0.2f * o.x, o.x); o.y = fmaxf(0.2f * o.y, o.y); o.z = fmaxf(0.2f * o.z, o.z); o.w = fmaxf(0.2f * o.w, o.w);
+            }
+            const long long roff = (long long)bb * K.out.bstride + n0 + (long long)m * K.out.rstride;
+            if (L.epilogue == EPI_SLOPE && K.out.saved) {
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
+                o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
+                o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
+            }
+            float4* dst = reinterpret_cast<float4*>(K.out.base + roff) + q;
+            if (m >= K.out.acc_lo && m < K.out.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            *dst = o;
+        }
+    }
+    if (tid == 0) T_MARK(13);
+    cluster_sync_all();                                   // nobody leaves while a peer may still read its shared memory
+    if (tid == 0) T_MARK(14);
+}
+
+#ifdef WUN_UMMA_TIMING
+}  // namespace wun
+// timing builds only (tools/fold_trace.py): the clock64 marks CTA (0,0,0) of the last plane_conv_umma_fold launch left
+extern "C" int wun_debug_fold_trace(unsigned long long* out, int n) {
+    if (n > 32) n = 32;
+    return (int)cudaMemcpyFromSymbol(out, wun::g_fold_trace, sizeof(unsigned long long) * n);
+}
+namespace wun {
+#endif
+
+static size_t umma_fold_smem_bytes(const UmmaLaunch& L) {
+    const size_t pipe = (size_t)kFoldSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
+    const size_t part = (size_t)L.MT * 128u * ((size_t)L.NPAD + 4u) * 4u;
+    return ((pipe > part ? pipe : part) + 127) / 128 * 128 + (2 * kFoldSlabStages + 2 * kBStagesMax + 1) * 8 + 32 + 4 * (size_t)L.NPAD;
+}
+
+static cudaError_t launch_plane_conv_fold(const UmmaLaunch& L, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(plane_conv_umma_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int max_tiles = 0;
+    for (int q = 0; q < L.ncls; ++q) {
+        const int rows = L.cls[q].out.m_hi - L.cls[q].out.m_lo;
+        if (rows <= 0) continue;
+        max_tiles = max(max_tiles, (L.batch * L.fold_pitch[q] + L.MT * 128 - 1) / (L.MT * 128));
+    }
+    if (max_tiles <= 0) return cudaSuccess;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(max_tiles * L.ksplit), (unsigned)L.nsplit, (unsigned)L.ncls);
+    cfg.blockDim = dim3(kFoldTeams * 128 + 64);
+    cfg.dynamicSmemBytes = umma_fold_smem_bytes(L);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)L.ksplit; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, plane_conv_umma_fold, L);
+}
+
 static size_t umma_pers_smem_bytes(const UmmaLaunch& L) {
     const size_t CW = (L.NPAD < 128) ? L.NPAD : 128;
     const size_t kSlabStages = (L.nteams == 3) ? 4 : 3;
@@ -783,6 +1119,7 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    if (L.folded) return launch_plane_conv_fold(L, stream);
     int max_tiles = 0, total = 0;
     for (int q = 0; q < L.ncls; ++q) {
         const int rows = L.cls[q].out.m_hi - L.cls[q].out.m_lo;
@@ -1034,6 +1371,7 @@ size_t umma_choice_smem_bytes(const UmmaChoice& ch) {
     memset(&U, 0, sizeof(U));
     U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc; U.TB = ch.TB; U.nbs = ch.nbs;
     U.nteams = ch.nteams; U.persistent = ch.persistent;
+    if (ch.folded) return umma_fold_smem_bytes(U);
     return ch.persistent ? umma_pers_smem_bytes(U) : umma_smem_bytes(U);
 }
 
@@ -1457,10 +1795,15 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     }
     ch->NPAD = (ch->nsplit == 1) ? npad_total : (((L.N + ch->nsplit - 1) / ch->nsplit + 15) / 16 * 16);
     int maxspan = 0, max_rows = 0;
+    int cls_span[kMaxClasses], cls_jobs[kMaxClasses];
     size_t bytes = 0;
+    // packed-weight columns reserved per block: independent of the batch-dependent tiling below (the arena is sized by a
+    // batch-1 dry run), i.e. the widest of the 1- and 2-way output-channel splits
+    const int pack_cols = max(npad_total, 2 * (((L.N + 1) / 2 + 15) / 16 * 16));
     for (int q = 0; q < L.ncls; ++q) {
         const OutView& O = L.cls[q];
         max_rows = max(max_rows, O.m_hi - O.m_lo);
+        cls_span[q] = 0; cls_jobs[q] = 0;
         int ngroups = 0, t = O.term_begin;
         while (t < O.term_end) {
             const int p = L.terms[t].plane;
@@ -1468,12 +1811,79 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
             while (t1 < O.term_end && L.terms[t1].plane == p) { dmin = min(dmin, L.terms[t1].d); dmax = max(dmax, L.terms[t1].d); ++t1; }
             if (dmax - dmin > 24) return false;
             maxspan = max(maxspan, dmax - dmin);
-            bytes += (size_t)((L.planes[p].C + 15) / 16) * (t1 - t) * 64u * ch->NPAD * ch->nsplit;
+            cls_span[q] = max(cls_span[q], dmax - dmin);
+            cls_jobs[q] += (L.planes[p].C + 15) / 16;
+            bytes += (size_t)((L.planes[p].C + 15) / 16) * (t1 - t) * 64u * pack_cols;
             ++ngroups; t = t1;
         }
         if (ngroups > kUmmaMaxGroups) return false;
     }
     if (max_rows <= 0) return false;
+    ch->pack_bytes = (bytes + 255) / 256 * 256;
+    {   // batch-folded cluster split-K kernel (plane_conv_umma_fold): launches whose row tiles leave SMs idle.
+        // WUN_FOLD: 0 = never, 1 (default) = launches the unfolded tiling would run on <= 148 CTAs, 2 = whenever it fits.
+        const char* env = getenv("WUN_FOLD");
+        const int mode = env ? atoi(env) : 1;
+        bool ok = mode != 0 && (L.N % 4 == 0);
+        long long old_ctas = 0;
+        int jmin = 1 << 30;
+        for (int q = 0; q < L.ncls; ++q) {
+            const OutView& O = L.cls[q];
+            if (O.m_hi <= O.m_lo) continue;
+            if (O.rstride % 4 || O.bstride % 4 || (reinterpret_cast<uintptr_t>(O.base) & 15) ||
+                (O.saved && (reinterpret_cast<uintptr_t>(O.saved) & 15))) ok = false;
+            old_ctas += (long long)((O.m_hi - O.m_lo + 127) / 128) * L.batch;
+            jmin = min(jmin, cls_jobs[q]);
+        }
+        if (ok && mode == 1 && old_ctas > 148) ok = false;
+        if (ok) {
+            const int nsplit = (npad_total <= 256) ? 1 : 2;
+            const int NPAD = (nsplit == 1) ? npad_total : (((L.N + 1) / 2 + 15) / 16 * 16);
+            int best_mt = 0, best_s = 0; long long best_ctas = 0;
+            for (int MT = 2; MT >= 1; --MT) {
+                if ((size_t)MT * 128 * (NPAD + 4) * 4 > 160 * 1024 || MT * NPAD > 512) continue;
+                long long T = 0;
+                for (int q = 0; q < L.ncls; ++q) {
+                    const int rows = L.cls[q].m_hi - L.cls[q].m_lo;
+                    if (rows > 0) T += ((long long)L.batch * (rows + cls_span[q]) + MT * 128 - 1) / (MT * 128);
+                }
+                T *= nsplit;
+                for (int S = 1; S <= kFoldMaxSplit && S <= jmin; ++S) {
+                    const long long ctas = T * S;
+                    // One CTA per SM and a cluster lives inside one GPC: resident clusters of this kernel's footprint as
+                    // cudaOccupancyMaxActiveClusters reports them on B200 (tools/cluster_probe: 148 74 45 33 26 22 15 15),
+                    // one less for S >= 3 as margin for parts with other SM harvesting.  More clusters than slots = a second
+                    // wave (seen: S = 7 x 18 tiles, 50 us vs 32 us for its neighbours).
+                    static const int kClusterSlots[kFoldMaxSplit + 1] = {0, 148, 74, 44, 32, 25, 21, 14, 14};
+                    if (T > kClusterSlots[S]) continue;
+                    (void)ctas;
+                    if (ctas > best_ctas) { best_ctas = ctas; best_mt = MT; best_s = S; }   // ties: the larger MT / smaller S seen first
+                }
+            }
+            if (best_ctas > 0) {
+                const int rows_alloc = best_mt * 128 + (maxspan + 7) / 8 * 8;
+                const int blk = 64 * NPAD;
+                int TB = 36864 / blk;
+                if (TB > 4) TB = 4;
+                if (TB < 1) TB = 1;
+                int nbs = 147456 / (TB * blk);
+                if (nbs > kBStagesMax) nbs = kBStagesMax;
+                const long long left = 200 * 1024 - (long long)kFoldSlabStages * 64 * rows_alloc - 4096;
+                while (nbs > 2 && (long long)nbs * TB * blk > left) --nbs;
+                if (nbs < 2) nbs = 2;
+                if ((long long)nbs * TB * blk <= left) {        // else: fall through to the unfolded kernels
+                    ch->folded = 1; ch->ksplit = best_s; ch->nsplit = nsplit; ch->NPAD = NPAD; ch->MT = best_mt;
+                    ch->rows_alloc = rows_alloc;
+                    int tm = 32;
+                    while (tm < best_mt * NPAD) tm *= 2;
+                    ch->tmem_cols = tm;
+                    ch->nteams = 4; ch->persistent = 0; ch->fuse = 0;
+                    ch->TB = TB; ch->nbs = nbs;
+                    return true;
+                }
+            }
+        }
+    }
     // two co-resident CTAs per SM beat one big one (measured): keep TMEM <= 256 columns and smem <= ~110 KB
     int MT = 256 / ch->NPAD;
     if (MT > 2) MT = 2;
@@ -1492,7 +1902,6 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
         const int mode = env ? atoi(env) : 0;
         ch->fuse = (mode > 0 && ch->NPAD <= 64) ? mode : 0;
     }
-    ch->pack_bytes = (bytes + 255) / 256 * 256;
     // weight ring: stages of TB taps (fewer barrier round trips for the single MMA-issuing thread).  Launches that
     // fill the GPU keep it at ~48 KB so two CTAs fit per SM; launches with fewer CTAs than SMs (the deep layers) are
     // weight-stream-latency bound, so they get a deep ring instead.
@@ -1579,6 +1988,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     for (int p = 0; p < L.nplanes; ++p) U.planes[p] = L.planes[p];
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
     U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.fuse = ch.fuse; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
+    U.folded = ch.folded; U.ksplit = ch.ksplit;
     PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
     int nterm_total = 0;
     for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);
@@ -1604,6 +2014,15 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
             J0.g_nchunk[g] = (L.planes[p].C + 15) / 16; J0.g_nterm[g] = t1 - t; J0.g_term_begin[g] = t; J0.g_C[g] = L.planes[p].C;
             nblocks += J0.g_nchunk[g] * J0.g_nterm[g];
             t = t1;
+        }
+        {   // folded launches: virtual rows per batch item = the class's rows + its widest tap span
+            int span = 0;
+            for (int g = 0; g < K.ngroups; ++g) {
+                int dmax = K.groups[g].dmin;
+                for (int tt = K.groups[g].term_begin; tt < K.groups[g].term_end; ++tt) dmax = max(dmax, L.terms[tt].d);
+                span = max(span, dmax - K.groups[g].dmin);
+            }
+            U.fold_pitch[q] = max(1, K.out.m_hi - K.out.m_lo + span);
         }
         J0.ngroups = K.ngroups; J0.nblocks = nblocks;
         for (int sp = 0; sp < ch.nsplit; ++sp) {

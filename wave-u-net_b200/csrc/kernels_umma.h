@@ -38,6 +38,9 @@ struct UmmaLaunch {
     int nteams;             // converter teams of the non-persistent kernel: 2 (dense launches) or 4 (sparse)
     int persistent;         // 1: one-CTA-per-SM tile loop with double-buffered TMEM (big layers)
     int fuse;               // 1: fused-N MMAs over [B_hi | B_lo] (2 per product; accumulator tile = 2*NPAD columns)
+    int folded;             // 1: batch-folded row tiles + cluster split-K (plane_conv_umma_fold; the deep, few-row layers)
+    int ksplit;             // folded: CTAs per cluster; each takes a contiguous range of the tile's (plane, chunk) jobs
+    int fold_pitch[kMaxClasses];   // folded: virtual rows per batch item of a class = its rows + its widest tap span
     const float* bias;
     int epilogue;
     int batch;
@@ -64,6 +67,7 @@ struct UmmaPackLaunch {
 
 struct UmmaChoice {         // tiling decisions for one ConvLaunch
     int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs, persistent, nteams, fuse;
+    int folded, ksplit;     // batch-folded cluster split-K kernel (sparse launches)
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 

@@ -17,7 +17,7 @@ SYMBOLS = [
     "wun_output_frames", "wun_param_count", "wun_param_numel", "wun_param_table", "wun_workspace_bytes",
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
     "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step", "wun_adam_step_device", "wun_set_grad_buckets", "wun_stream_wait_grad_bucket",
-    "wun_gather_windows", "wun_scatter_windows", "wun_last_error", "wun_version", "wun_describe",
+    "wun_gather_windows", "wun_scatter_windows", "wun_feed_batch", "wun_last_error", "wun_version", "wun_describe",
     "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_debug_run_layer", "wun_crc32c", "wun_debug_plan",
 ]
 
@@ -70,6 +70,7 @@ def _load():
     lib.wun_stream_wait_grad_bucket.argtypes = [H, ctypes.c_int, VP]
     lib.wun_gather_windows.argtypes = [H, VP, I64, VP, I64, VP, VP]
     lib.wun_scatter_windows.argtypes = [H, VP, VP, I64, VP, I64, VP]
+    lib.wun_feed_batch.argtypes = [H, VP, I64, VP, VP, I64, I64, ctypes.c_int, ctypes.c_uint64, VP, VP, VP, VP, VP]
     lib.wun_last_error.restype = ctypes.c_char_p
     lib.wun_version.restype = ctypes.c_char_p
     lib.wun_describe.argtypes = [H, ctypes.c_char_p, I64]
@@ -325,6 +326,23 @@ class Engine(object):
     def stream_wait_grad_bucket(self, k, stream):
         """Make torch stream `stream` wait until bucket k of the last enqueued forward_backward is final."""
         check(lib.wun_stream_wait_grad_bucket(self._h, int(k), ctypes.c_void_p(stream.cuda_stream)))
+
+    def feed_batch(self, pool, track_offset, track_length, batch, augmentation, seed, step_state, mix_out, targets_out,
+                   chosen=None):
+        """One training batch cut out of the device-resident track pool (wun_feed_batch): random snippet per example,
+        random_amplify, centre crop.  All arguments are CUDA tensors owned by the caller (wun.feeder.DeviceFeeder)."""
+        import torch
+        K = targets_out.shape[0]
+        assert K == self.cfg.num_sources and pool.shape[2] == self.cfg.num_channels
+        assert pool.is_cuda and pool.dtype == torch.float32 and pool.is_contiguous() and pool.dim() == 3 and pool.shape[0] == K + 1
+        assert track_offset.dtype == torch.int64 and track_length.dtype == torch.int64 and step_state.dtype == torch.int64
+        assert tuple(mix_out.shape) == (batch, self.T_in, pool.shape[2]) and mix_out.is_contiguous()
+        assert tuple(targets_out.shape) == (K, batch, self.T_out, pool.shape[2]) and targets_out.is_contiguous()
+        with torch.cuda.device(mix_out.device):
+          check(lib.wun_feed_batch(self._h, pool.data_ptr(), pool.shape[1], track_offset.data_ptr(), track_length.data_ptr(),
+                                 track_offset.numel(), int(batch), int(bool(augmentation)), int(seed) & (2 ** 64 - 1),
+                                 step_state.data_ptr(), mix_out.data_ptr(), targets_out.data_ptr(),
+                                 chosen.data_ptr() if chosen is not None else None, self._stream(mix_out.device)))
 
     def gather_windows(self, padded, starts, mix_batch):
         check(lib.wun_gather_windows(self._h, padded.data_ptr(), padded.shape[0], starts.data_ptr(),
