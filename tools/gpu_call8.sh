@@ -1,0 +1,18 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+i=0
+for cfg in "X=0" "WUN_FOLD_COMPACT=1" "WUN_FOLD_PREFETCH=1" "WUN_SPLIT_COLSUM=0" "WUN_FOLD_COMPACT=1 WUN_FOLD_PREFETCH=1"; do
+  echo "=== bench $cfg"
+  env $cfg timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/c8_bench_$i.json 2> gpurun_out/c8_bench_$i.err
+  tail -2 gpurun_out/c8_bench_$i.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/c8_bench_$i.json").read().strip().splitlines()[-1])
+    print("ms/step %.3f  e2e %.3e  families %s" % (d["ms_per_step"], d["e2e"]["value"], {k:round(v["us"]) for k,v in d.get("families",{}).items()}))
+except Exception as e:
+    print("bench failed:", e)
+PY
+  i=$((i+1))
+done

@@ -111,6 +111,73 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// The same MMA with the two 64-bit shared-memory descriptors given as (low word, high word) pairs: along a K loop only the
+// 14-bit start-address field in the LOW word changes (tap shift, row tile, weight block), so the single issuing thread
+// advances descriptors with one 32-bit add each instead of rebuilding 64-bit values.
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_w, uint32_t a_hw, uint32_t b_w, uint32_t b_hw, uint32_t idesc,
+                                            uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_w), "r"(a_hw), "r"(b_w), "r"(b_hw), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t kDescHi128 = (128u >> 4) | (1u << 14);     // high word of a SWIZZLE_NONE descriptor with SBO = 128 B
+
+// One weight-ring stage of the conv K loop: nt <= 4 taps with CONSECUTIVE row shifts (shift0, shift0 + 1, ...) x MT row tiles
+// x the three split-precision MMAs, fully unrolled, every descriptor one word add away from the previous one.  The issue
+// loop is the critical path of every conv kernel (tools/umma_rate_bench: ~200 cycles of dependent uniform-datapath
+// arithmetic per tap in the generic loop, more than the 3 MMAs of a tap take for N <= 128), so nothing but adds and the
+// MMAs themselves remain here.  a_hi_w / a_lo_w: low words of the hi / lo sub-slab descriptors at row shift 0, tile 0;
+// b_hi_w / b_lo_w: low words of the stage's first weight block; blk16 = bytes of one tap's block / 16.
+template <int MT>
+__device__ __forceinline__ void issue_taps(uint32_t a_hi_w, uint32_t a_lo_w, uint32_t b_hi_w, uint32_t b_lo_w, uint32_t blk16, int nt,
+                                           uint32_t td, uint32_t acc_stride, uint32_t idesc, uint32_t& first) {
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+        if (tt < nt) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t ah = a_hi_w + (uint32_t)(tt + 128 * mt), al = a_lo_w + (uint32_t)(tt + 128 * mt);
+                const uint32_t bh = b_hi_w + (uint32_t)tt * blk16, bl = b_lo_w + (uint32_t)tt * blk16;
+                const uint32_t t = td + (uint32_t)mt * acc_stride;
+                umma_bf16_w(t, al, kDescHi128, bh, kDescHi128, idesc, first);
+                umma_bf16_w(t, ah, kDescHi128, bl, kDescHi128, idesc, 1u);
+                umma_bf16_w(t, ah, kDescHi128, bh, kDescHi128, idesc, 1u);
+            }
+            first = 1u;
+        }
+    }
+}
+
+// Fused-N form of the same stage: per tap and row tile  D[:, 0:2N] += A_hi x [B_hi | B_lo]  (one MMA, N = 2*NPAD, the weight
+// block keeps B_hi and B_lo adjacent per K atom) and  D[:, 0:N] += A_lo x B_hi  - 2 MMAs per product instead of 3; the epilogue
+// adds the two accumulator halves.  tools/umma_rate_bench: 114 vs 153-173 cycles per K step and row tile for N <= 64.
+template <int MT>
+__device__ __forceinline__ void issue_taps_fused(uint32_t a_hi_w, uint32_t a_lo_w, uint32_t b_hi_w, uint32_t blk16, int nt, uint32_t td,
+                                                 uint32_t acc_stride, uint32_t idesc, uint32_t idesc2, uint32_t& first) {
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+        if (tt < nt) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t ah = a_hi_w + (uint32_t)(tt + 128 * mt), al = a_lo_w + (uint32_t)(tt + 128 * mt);
+                const uint32_t bh = b_hi_w + (uint32_t)tt * blk16;
+                const uint32_t t = td + (uint32_t)mt * acc_stride;
+                umma_bf16_w(t, ah, kDescHi128, bh, kDescHi128, idesc2, first);
+                umma_bf16_w(t, al, kDescHi128, bh, kDescHi128, idesc, 1u);
+            }
+            first = 1u;
+        }
+    }
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -413,6 +480,16 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                         const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
                         const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
                         const int nt = min(TB, G.term_end - t0);
+                        if (L.consec) {
+                            const uint32_t sh = (uint32_t)(t0 - G.term_begin);
+                            const uint32_t ahw = umma_desc_lo(sa, atom_stride) + sh, alw = umma_desc_lo(sa + 2 * atom_stride, atom_stride) + sh;
+                            const uint32_t bhw = umma_desc_lo(sb, b_lbo), blw = umma_desc_lo(sb + 16u * NPAD, b_lbo);
+                            if (L.fuse) {
+                                if (L.MT == 2) issue_taps_fused<2>(ahw, alw, bhw, bblk_bytes >> 4, nt, tmem_base, 2u * NPAD, idesc, idesc2, first);
+                                else issue_taps_fused<1>(ahw, alw, bhw, bblk_bytes >> 4, nt, tmem_base, 2u * NPAD, idesc, idesc2, first);
+                            } else if (L.MT == 2) issue_taps<2>(ahw, alw, bhw, blw, bblk_bytes >> 4, nt, tmem_base, (uint32_t)NPAD, idesc, first);
+                            else issue_taps<1>(ahw, alw, bhw, blw, bblk_bytes >> 4, nt, tmem_base, (uint32_t)NPAD, idesc, first);
+                        } else
                         for (int tt = 0; tt < nt; ++tt) {
                             const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
                             const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
@@ -541,7 +618,8 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t acc_cols = (uint32_t)(L.MT * NPAD);               // columns of one accumulator buffer
+    const uint32_t acc_w = (uint32_t)(L.fuse ? 2 * NPAD : NPAD);      // accumulator columns of one row tile (fused-N: two halves)
+    const uint32_t acc_cols = (uint32_t)L.MT * acc_w;                 // columns of one accumulator buffer
 
     if (warp < kMmaWarp) {
         // ===================== converters =====================
@@ -621,6 +699,18 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                             const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
                             const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
                             const int nt = min(TB, G.term_end - t0);
+                            if (L.consec) {
+                                const uint32_t sh = (uint32_t)(t0 - G.term_begin);
+                                const uint32_t ahw = umma_desc_lo(sa, atom_stride) + sh, alw = umma_desc_lo(sa + 2 * atom_stride, atom_stride) + sh;
+                                const uint32_t bhw = umma_desc_lo(sb, b_lbo), blw = umma_desc_lo(sb + 16u * NPAD, b_lbo);
+                                const uint32_t td0 = tmem_base + buf * acc_cols;
+                                if (L.fuse) {
+                                    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 2) << 17) | ((128u >> 4) << 24);
+                                    if (L.MT == 2) issue_taps_fused<2>(ahw, alw, bhw, bblk_bytes >> 4, nt, td0, acc_w, idesc, idesc2, first);
+                                    else issue_taps_fused<1>(ahw, alw, bhw, bblk_bytes >> 4, nt, td0, acc_w, idesc, idesc2, first);
+                                } else if (L.MT == 2) issue_taps<2>(ahw, alw, bhw, blw, bblk_bytes >> 4, nt, td0, (uint32_t)NPAD, idesc, first);
+                                else issue_taps<1>(ahw, alw, bhw, blw, bblk_bytes >> 4, nt, td0, (uint32_t)NPAD, idesc, first);
+                            } else
                             for (int tt = 0; tt < nt; ++tt) {
                                 const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
                                 const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
@@ -689,7 +779,13 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                         for (int cb = 0; cb < cw; cb += 16) {
                             __syncwarp();
                             float v[16];
-                            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)(mt * NPAD + c0 + cb), v);
+                            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)mt * acc_w + (uint32_t)(c0 + cb), v);
+                            if (L.fuse) {                     // second accumulator half: A_hi x B_lo
+                                float v2[16];
+                                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)mt * acc_w + (uint32_t)(NPAD + c0 + cb), v2);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                            }
                             if (L.epilogue == EPI_BIAS_LRELU) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
@@ -790,7 +886,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
     float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 
@@ -867,6 +963,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                 const int st = jl % kFoldSlabStages;
                 uint8_t* Sl = slab0 + st * slab_bytes;
                 const uint32_t atom_stride = 16u * L.rows_alloc;
+                if (!(L.fold_flags & 1)) {
                 constexpr int kRB = 3;
                 bool waited = false;
                 for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
@@ -896,6 +993,31 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                         *reinterpret_cast<uint4*>(Sl + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         *reinterpret_cast<uint4*>(Sl + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
+                }
+                } else {
+                // One row per thread and pass, NOT the 3-row unrolled batches of the long-running kernels: these launches live
+                // ~20 us, and the cold instruction fetch of a 250-instruction straight-line body cost more than the load
+                // latency it hid (fold trace: first slab ready 7-14 k cycles after kernel start).
+                bool waited = false;
+#pragma unroll 1
+                for (int rr = ttid; rr < L.rows_alloc; rr += kWorkerThreads) {
+                    float x[16];
+                    const int u = v0 + rr, bb = u / pitch, off = u - bb * pitch;             // virtual row -> (item, row)
+                    load_row16(P, bb, (bb < L.batch) ? K.out.m_lo + off + G.dmin : -(1 << 30), c * 16, x);
+                    if (!waited) { mbar_wait(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1); waited = true; }
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+                        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[i] = pack_bf16x2(x[2 * i] - __bfloat162float(h0), x[2 * i + 1] - __bfloat162float(h1));
+                    }
+                    *reinterpret_cast<uint4*>(Sl + 16u * rr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(Sl + atom_stride + 16u * rr) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(Sl + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(Sl + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+                if (!waited) mbar_wait(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1);
                 }
                 fence_proxy_async();
                 mbar_arrive(BAR(SLAB_FULL + st));
@@ -954,6 +1076,13 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                         const uint32_t sb = smem_u32(bring0 + bs * bstage_bytes);
                         const uint64_t b_hi0 = umma_desc(sb, b_lbo, 128), b_lo0 = umma_desc(sb + 16u * NPAD, b_lbo, 128);
                         const int nt = min(TB, G.term_end - t0);
+                        if (L.consec) {
+                            const uint32_t sh = (uint32_t)(t0 - G.term_begin);
+                            const uint32_t ahw = umma_desc_lo(sa, atom_stride) + sh, alw = umma_desc_lo(sa + 2 * atom_stride, atom_stride) + sh;
+                            const uint32_t bhw = umma_desc_lo(sb, b_lbo), blw = umma_desc_lo(sb + 16u * NPAD, b_lbo);
+                            if (L.MT == 2) issue_taps<2>(ahw, alw, bhw, blw, bblk_bytes >> 4, nt, tmem_base, (uint32_t)NPAD, idesc, first);
+                            else issue_taps<1>(ahw, alw, bhw, blw, bblk_bytes >> 4, nt, tmem_base, (uint32_t)NPAD, idesc, first);
+                        } else
                         for (int tt = 0; tt < nt; ++tt) {
                             const uint64_t boff = (uint64_t)((bblk_bytes >> 4) * tt);
                             const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
@@ -980,6 +1109,23 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
         // ===================== weight loader: only the blocks of this CTA's jobs =====================
         if (has_work && elect_one()) {
             const uint8_t* src = K.wpack[split];
+            if (L.fold_flags & 2) {   // ask L2 for this CTA's whole weight range up front: the packs were written at the start of the step and have
+                // usually been evicted since; the ring below then streams L2 hits instead of waiting for HBM stage by stage
+                size_t b0 = 0, b1 = 0;
+                int jj = 0;
+                for (int g = 0; g < K.ngroups; ++g) {
+                    const int nchunk = (L.planes[K.groups[g].plane].C + 15) >> 4;
+                    const int nterm = K.groups[g].term_end - K.groups[g].term_begin;
+                    for (int c = 0; c < nchunk; ++c, ++jj) {
+                        if (jj < j0) b0 += nterm;
+                        if (jj < j1) b1 += nterm;
+                    }
+                }
+                for (size_t b = b0; b < b1; b += 4) {
+                    const uint32_t bytes = (uint32_t)((b1 - b < 4 ? b1 - b : 4) * bblk_bytes);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + b * bblk_bytes), "r"(bytes) : "memory");
+                }
+            }
             int bi = 0, ji = 0;
             size_t blk = 0;
             for (int g = 0; g < K.ngroups; ++g) {
@@ -1024,10 +1170,13 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
             if (bb >= L.batch || off >= rows_q) continue;     // padding rows between the items' segments
             const int m = K.out.m_lo + off;
             const uint32_t eoff = ((uint32_t)r * (uint32_t)SWF + 4u * (uint32_t)q) * 4u;
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 part[kFoldMaxSplit];                          // all peer loads in flight together, then the sum
 #pragma unroll
             for (int s = 0; s < kFoldMaxSplit; ++s)
-                if (s < S) { const float4 p = ld_dsmem_v4(peer[s] + eoff); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                part[s] = (s < S) ? ld_dsmem_v4(peer[s] + eoff) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o = part[0];
+#pragma unroll
+            for (int s = 1; s < kFoldMaxSplit; ++s) { o.x += part[s].x; o.y += part[s].y; o.z += part[s].z; o.w += part[s].w; }
             if (L.epilogue == EPI_BIAS_LRELU) {
                 o.x += bias_s[4 * q]; o.y += bias_s[4 * q + 1]; o.z += bias_s[4 * q + 2]; o.w += bias_s[4 * q + 3];
                 o.x = fmaxf(0.2f * o.x, o.x); o.y = fmaxf(0.2f * o.y, o.y); o.z = fmaxf(0.2f * o.z, o.z); o.w = fmaxf(0.2f * o.w, o.w);
@@ -1468,13 +1617,24 @@ cudaError_t launch_wgrad_umma(const UmmaWgradLaunch& L, cudaStream_t stream) {
 // with zero rows around the valid range; the wgrad kernel then fills its stages with cp.async.bulk issued by ONE thread
 // instead of 12 converter warps re-converting the same rows in every (class, plane, tap-set) CTA.
 // ------------------------------------------------------------------------------------------------
+constexpr int kSplitRB = 2048;     // rows of one (item, 16-channel chunk) a CTA of the split pass covers (8 per thread)
+
+// blockIdx.y = job, blockIdx.x = (item, chunk, row block).  Thread t converts rows rb + t, rb + t + 256, ...; for a class-gradient
+// view (job.colsum != null) it also keeps the 16 column sums of its rows, the CTA reduces them (shuffles + shared memory)
+// and adds scale * sum to the bias gradient - the layer's bias gradient costs no launch and no extra pass over dPre.
 __global__ void __launch_bounds__(256) split_views_kernel(const __grid_constant__ SplitJobs J) {
     const SplitJob& job = J.job[blockIdx.y];
-    const long long total = (long long)J.batch * job.nchunk * job.rows;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i % job.rows);
-        const int c = (int)((i / job.rows) % job.nchunk);
-        const int b = (int)(i / ((long long)job.rows * job.nchunk));
+    const int nrb = (job.rows + kSplitRB - 1) / kSplitRB;
+    const int total = J.batch * job.nchunk * nrb;
+    if ((int)blockIdx.x >= total) return;
+    const int rbi = blockIdx.x % nrb, c = (blockIdx.x / nrb) % job.nchunk, b = blockIdx.x / (nrb * job.nchunk);
+    const int r_end = min(job.rows, (rbi + 1) * kSplitRB);
+    const long long ps = (long long)job.rows * 16;
+    uint8_t* obase = job.out + (((long long)b * job.nchunk + c) * 4) * ps;
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    for (int r = rbi * kSplitRB + threadIdx.x; r < r_end; r += 256) {
         float x[16];
         load_row16(job.V, b, job.row0 + r, c * 16, x);      // zero outside the valid rows / channels; MID planes blended here
         uint32_t hi[8], lo[8];
@@ -1484,23 +1644,44 @@ __global__ void __launch_bounds__(256) split_views_kernel(const __grid_constant_
             hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
             lo[k] = pack_bf16x2(x[2 * k] - __bfloat162float(h0), x[2 * k + 1] - __bfloat162float(h1));
         }
-        const long long ps = (long long)job.rows * 16;
-        uint8_t* o = job.out + (((long long)b * job.nchunk + c) * 4) * ps + (long long)r * 16;
+        uint8_t* o = obase + (long long)r * 16;
         *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(o + ps) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
         *reinterpret_cast<uint4*>(o + 2 * ps) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         *reinterpret_cast<uint4*>(o + 3 * ps) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        if (job.colsum) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] += x[k];
+        }
+    }
+    if (job.colsum) {                                        // uniform per CTA
+        __shared__ float red[8][16];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp][k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16 && c * 16 + (int)threadIdx.x < job.V.C) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+            atomicAdd(job.colsum + c * 16 + threadIdx.x, t * J.colsum_scale);
+        }
     }
 }
 
 cudaError_t launch_split_views(const SplitJobs& J, cudaStream_t stream) {
     if (J.njobs <= 0) return cudaSuccess;
     long long most = 0;
-    for (int j = 0; j < J.njobs; ++j) most = max(most, (long long)J.batch * J.job[j].nchunk * J.job[j].rows);
-    long long blocks = (most + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    if (blocks < 1) blocks = 1;
-    split_views_kernel<<<dim3((unsigned)blocks, J.njobs), 256, 0, stream>>>(J);
+    for (int j = 0; j < J.njobs; ++j)
+        most = max(most, (long long)J.batch * J.job[j].nchunk * ((J.job[j].rows + kSplitRB - 1) / kSplitRB));
+    if (most < 1) return cudaSuccess;
+    if (most > 0x7fffffffLL) return cudaErrorInvalidValue;
+    split_views_kernel<<<dim3((unsigned)most, J.njobs), 256, 0, stream>>>(J);
     return cudaGetLastError();
 }
 
@@ -1732,36 +1913,50 @@ cudaError_t launch_wgrad_umma_bulk(const UmmaWgradLaunch& L, const WgSplit& S, c
 // per K atom the block is a K-major [hi rows 0..NPAD) | lo rows NPAD..2*NPAD) matrix, so ONE descriptor with
 // N = 2*NPAD covers [B_hi | B_lo] (fused-N mode) and N = NPAD covers B_hi alone.
 // ------------------------------------------------------------------------------------------------
+// One thread per (block, K atom, n): 8 k-values -> one 16-byte hi store and one 16-byte lo store (consecutive n = consecutive
+// 16 B: coalesced); the fp32 reads are coalesced along n (forward: w_sn = 1) or 32 B contiguous per thread (dgrad: w_sk = 1).
+// (Round 1 used one thread per bf16 element with 2-byte stores: 448 us per step for the 60 packs; this form moves the same
+// bytes with 1/16 of the threads.)
 __global__ void __launch_bounds__(256) umma_pack_kernel(const __grid_constant__ UmmaPackLaunch PL) {
     const UmmaPackJob& J = PL.jobs[blockIdx.y];
-    const long long total = (long long)J.nblocks * PL.NPAD * 16;
+    const long long total = (long long)J.nblocks * PL.NPAD * 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int kk16 = (int)(i % 16);
-        const int n = (int)((i / 16) % PL.NPAD);
-        const int bi = (int)(i / (16LL * PL.NPAD));
+        const int n = (int)(i % PL.NPAD);
+        const int a = (int)((i / PL.NPAD) & 1);
+        const int bi = (int)(i / (2LL * PL.NPAD));
         int g = 0, base = 0;
         while (g < J.ngroups - 1 && bi >= base + J.g_nchunk[g] * J.g_nterm[g]) { base += J.g_nchunk[g] * J.g_nterm[g]; ++g; }
         const int rel = bi - base;
         const int chunk = rel / J.g_nterm[g], term = J.g_term_begin[g] + rel % J.g_nterm[g];
-        const int k = chunk * 16 + kk16;              // channel within the plane
+        const int k0 = chunk * 16 + a * 8;            // first of this thread's 8 channels within the plane
         const int nn = J.n0 + n;
-        float w = 0.f;
-        if (k < J.g_C[g] && nn < PL.N)
-            w = __ldg(PL.W + (long long)PL.woff[term] + (long long)k * PL.w_sk + (long long)nn * PL.w_sn);
-        const __nv_bfloat16 h = __float2bfloat16_rn(w);
-        const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
-        const int a = kk16 >> 3, kk = kk16 & 7;
+        float w[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) w[kk] = 0.f;
+        if (nn < PL.N) {
+            const float* src = PL.W + (long long)PL.woff[term] + (long long)k0 * PL.w_sk + (long long)nn * PL.w_sn;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                if (k0 + kk < J.g_C[g]) w[kk] = __ldg(src + (long long)kk * PL.w_sk);
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(w[2 * q]), h1 = __float2bfloat16_rn(w[2 * q + 1]);
+            hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[q] = pack_bf16x2(w[2 * q] - __bfloat162float(h0), w[2 * q + 1] - __bfloat162float(h1));
+        }
         uint8_t* blk = J.out + (size_t)bi * 64u * PL.NPAD;
-        const size_t off = (size_t)a * 32u * PL.NPAD + (size_t)(n >> 3) * 128u + (size_t)(n & 7) * 16u + (size_t)kk * 2u;
-        *reinterpret_cast<__nv_bfloat16*>(blk + off) = h;
-        *reinterpret_cast<__nv_bfloat16*>(blk + 16u * PL.NPAD + off) = l;
+        const size_t off = (size_t)a * 32u * PL.NPAD + (size_t)(n >> 3) * 128u + (size_t)(n & 7) * 16u;
+        *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(blk + 16u * PL.NPAD + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
 cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream) {
     int maxblk = 0;
     for (int j = 0; j < PL.njobs; ++j) maxblk = max(maxblk, PL.jobs[j].nblocks);
-    const long long total = (long long)maxblk * PL.NPAD * 16;
+    const long long total = (long long)maxblk * PL.NPAD * 2;
     if (total <= 0 || PL.njobs <= 0) return cudaSuccess;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
@@ -1899,8 +2094,8 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
         // Measured: no step-time gain (8.583 vs 8.584 ms) - those launches are not MMA-bound - but the separate hi*lo
         // accumulator halves the worst-case rounding error, so the mode stays available.
         const char* env = getenv("WUN_FUSE_N");
-        const int mode = env ? atoi(env) : 0;
-        ch->fuse = (mode > 0 && ch->NPAD <= 64) ? mode : 0;
+        const int mode = env ? atoi(env) : 1;       // round 2: default on (lean issue loop made the small-N launches MMA-bound)
+        ch->fuse = (mode > 0 && ch->NPAD <= 64) ? 1 : 0;
     }
     // weight ring: stages of TB taps (fewer barrier round trips for the single MMA-issuing thread).  Launches that
     // fill the GPU keep it at ~48 KB so two CTAs fit per SM; launches with fewer CTAs than SMs (the deep layers) are
@@ -1940,8 +2135,7 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
                            (mode == 6 && (L.epilogue == EPI_BIAS_LRELU || ch->NPAD > 80));
         const char* envm = getenv("WUN_PERS_MIN");
         const int min_per_sm = envm ? atoi(envm) : 3;
-        if (allow && ch->fuse != 2 && n_ctas >= (long long)min_per_sm * 148 && 2 * MT * ch->NPAD <= 512) {
-            ch->fuse = 0;
+        if (allow && n_ctas >= (long long)min_per_sm * 148 && 2 * MT * ch->NPAD * (ch->fuse ? 2 : 1) <= 512) {
             ch->persistent = 1;
             // (128-row tiles for better last-round balance were tried - rounds x height cost model - and lost badly:
             //  9.04 vs 8.51 ms/step; the 256-row tile amortises the slab halo and the per-tile pipeline ramp.)
@@ -1957,15 +2151,15 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
             if (ch->nbs > kBStagesMax) ch->nbs = kBStagesMax;
             if (ch->nbs < 2) { ch->nbs = 2; ch->nteams = 2; }
             int tm2 = 32;
-            while (tm2 < 2 * MT * ch->NPAD) tm2 *= 2;
+            while (tm2 < 2 * MT * ch->NPAD * (ch->fuse ? 2 : 1)) tm2 *= 2;
             ch->tmem_cols = tm2;
         }
     }
-    if (ch->fuse) {
-        ch->fuse = 1;
+    if (ch->fuse && !ch->persistent) {
         int tmf = 32;
         while (tmf < 2 * MT * ch->NPAD) tmf *= 2;
-        ch->tmem_cols = tmf;
+        if (ch->nteams == 2 && tmf > 256) ch->fuse = 0;      // two CTAs per SM share the 512 TMEM columns
+        else ch->tmem_cols = tmf;
     }
     return true;
 }
@@ -1989,6 +2183,17 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
     U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.fuse = ch.fuse; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
     U.folded = ch.folded; U.ksplit = ch.ksplit;
+    {   // A/B switches of the folded kernel: WUN_FOLD_COMPACT (bit 0: one-row converter passes), WUN_FOLD_PREFETCH (bit 1: L2 prefetch)
+        static const int flags = [] {
+            const char* a = getenv("WUN_FOLD_COMPACT"); const char* b = getenv("WUN_FOLD_PREFETCH");
+            return ((a && a[0] == '1') ? 1 : 0) | ((b && b[0] == '1') ? 2 : 0);
+        }();
+        U.fold_flags = flags;
+    }
+    {   // every group's taps sorted with consecutive row shifts (checked below): lean issue loop; WUN_LEAN=0 = generic loop (A/B)
+        static const int lean = [] { const char* e = getenv("WUN_LEAN"); return (e && e[0] == '0') ? 0 : 1; }();
+        U.consec = lean;
+    }
     PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
     int nterm_total = 0;
     for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);
@@ -2009,6 +2214,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
             int t1 = t;
             while (t1 < K.out.term_end && L.terms[t1].plane == p) { G.dmin = min(G.dmin, L.terms[t1].d); ++t1; }
             G.term_end = t1;
+            for (int tt = t; tt < t1; ++tt) if (L.terms[tt].d != L.terms[t].d + (tt - t)) U.consec = 0;
             const int g = K.ngroups++;
             K.groups[g] = G;
             J0.g_nchunk[g] = (L.planes[p].C + 15) / 16; J0.g_nterm[g] = t1 - t; J0.g_term_begin[g] = t; J0.g_C[g] = L.planes[p].C;

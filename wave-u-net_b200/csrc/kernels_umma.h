@@ -38,7 +38,9 @@ struct UmmaLaunch {
     int nteams;             // converter teams of the non-persistent kernel: 2 (dense launches) or 4 (sparse)
     int persistent;         // 1: one-CTA-per-SM tile loop with double-buffered TMEM (big layers)
     int fuse;               // 1: fused-N MMAs over [B_hi | B_lo] (2 per product; accumulator tile = 2*NPAD columns)
+    int consec;             // 1: within every group the terms are sorted by row shift, d = dmin, dmin+1, ... (issue_taps path)
     int folded;             // 1: batch-folded row tiles + cluster split-K (plane_conv_umma_fold; the deep, few-row layers)
+    int fold_flags;         // folded: bit 0 = one-row converter passes (compact code), bit 1 = L2 prefetch of the CTA's weights
     int ksplit;             // folded: CTAs per cluster; each takes a contiguous range of the tile's (plane, chunk) jobs
     int fold_pitch[kMaxClasses];   // folded: virtual rows per batch item of a class = its rows + its widest tap span
     const float* bias;
@@ -115,11 +117,13 @@ struct SplitJob {           // materialise plane rows [row0, row0 + rows) of V a
     PlaneView V;
     uint8_t* out;           // [batch][nchunk][4][rows][16 B]
     int nchunk, rows, row0;
+    float* colsum;          // class-gradient views: bias gradient [V.C] that receives colsum_scale * column sums (else null)
 };
 
 struct SplitJobs {
     SplitJob job[kSplitMaxJobs];
     int njobs, batch;
+    float colsum_scale;
 };
 
 struct WgSplit {            // where the wgrad groups find their operands (filled next to the SplitJobs)
