@@ -65,6 +65,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
     }
 }
+// The same for the warps that are NOT the MMA issuer (converters waiting for a free slab, epilogue warps waiting for an
+// accumulator, the weight loader waiting for a free ring stage): back off with nanosleep between polls, so that their
+// polling does not take issue slots and shared-memory cycles from the single thread that feeds the tensor pipe.
+__device__ __forceinline__ void mbar_wait_bg(uint32_t bar, uint32_t parity) {
+#ifdef WUN_NO_BACKOFF
+    mbar_wait(bar, parity);
+#else
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned ns = 20;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (ns < 160) ns *= 2;
+        if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+    }
+#endif
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // One lane of a CONVERGED warp, chosen by the hardware.  Unlike `lane == 0` this tells the compiler that exactly one
 // thread runs the region, so every tcgen05.mma / commit / bulk copy inside is a plain instruction instead of an
@@ -255,13 +272,88 @@ __device__ unsigned long long g_fold_trace[32];
 #define T_MARK(i) do { } while (0)
 #endif
 
+// A (plane, tile) pair whose slab would hold nothing but zero rows - the tile's rows plus the group's tap span lie
+// entirely outside the plane's valid rows - contributes nothing: converters, MMA issuer and weight loader all skip the
+// group (same test, same order, so their job / ring counters stay in step).  This is what the dgrad of a down block
+// looks like outside the skip window: the gradient of the odd rows (g_odd) is zero there, i.e. for ~89 % of the tiles
+// 7-8 of the 15 taps have an all-zero operand.
+__device__ __forceinline__ bool group_is_empty(const UmmaLaunch& L, const UmmaGroup& G, int m_base) {
+    const PlaneView& P = L.planes[G.plane];
+    const int lo = m_base + G.dmin;
+    return lo + L.rows_alloc <= P.r_lo || lo >= P.r_hi;
+}
+
+
+// Phase 2 of the conv epilogue for one warp: write out the 32 accumulator rows it staged (row r0 + 0..31 of the tile), lanes
+// running over (row, 4-column quad) pairs.  The LeakyReLU-slope read of the saved activation and the accumulate read of the
+// destination (dgrad) are issued for kEpiBatch items BEFORE any of them is used: the dgrad epilogue is a chain of dependent
+// global loads (measured: down1 dgrad 410 us with one load in flight per lane vs 175 us for the forward of the same layer,
+// whose epilogue only stores), so memory-level parallelism is what it needs.
+constexpr int kEpiBatch = 4;
+// forward launches (nothing to read back) keep the straight loop; the two forms live in separate kernel instantiations
+// (template parameter DG) because the batched form's registers slowed the forward kernels down when both shared one body
+// (down1 forward 149 -> 195 us).
+__device__ __forceinline__ void epi_write_rows_simple(const float* __restrict__ stage, int SW, int r0, int lane, int Q, int m0,
+                                                      const OutView& O, long long tile_off, bool slope) {
+    for (int it = lane; it < 32 * Q; it += 32) {
+        const int rl = it / Q, q = it - rl * Q;
+        const int m = m0 + rl;
+        if (m >= O.m_hi) continue;
+        const long long roff = tile_off + (long long)m * O.rstride;
+        float4 o = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
+        if (slope) {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(O.saved + roff) + q);
+            o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
+            o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
+        }
+        float4* dst = reinterpret_cast<float4*>(O.base + roff) + q;
+        if (m >= O.acc_lo && m < O.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        *dst = o;
+    }
+}
+__device__ __forceinline__ void epi_write_rows_vec(const float* __restrict__ stage, int SW, int r0, int lane, int Q, int m0,
+                                                   const OutView& O, long long tile_off, bool slope) {
+    const int nit = 32 * Q;
+    for (int it0 = lane; it0 < nit; it0 += 32 * kEpiBatch) {
+        float4 o[kEpiBatch], sv[kEpiBatch], old[kEpiBatch];
+        float4* dst[kEpiBatch];
+        bool ok[kEpiBatch], acc[kEpiBatch];
+#pragma unroll
+        for (int u = 0; u < kEpiBatch; ++u) {
+            const int it = it0 + 32 * u;
+            const int rl = it / Q, q = it - rl * Q;
+            const int m = m0 + rl;
+            ok[u] = it < nit && m < O.m_hi;
+            acc[u] = ok[u] && m >= O.acc_lo && m < O.acc_hi;
+            const long long roff = tile_off + (long long)m * O.rstride;
+            dst[u] = reinterpret_cast<float4*>(O.base + roff) + q;
+            if (ok[u]) {
+                o[u] = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
+                if (slope) sv[u] = __ldg(reinterpret_cast<const float4*>(O.saved + roff) + q);
+                if (acc[u]) old[u] = *dst[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEpiBatch; ++u) {
+            if (!ok[u]) continue;
+            float4 v = o[u];
+            if (slope) {
+                v.x *= (sv[u].x > 0.f) ? 1.f : 0.2f; v.y *= (sv[u].y > 0.f) ? 1.f : 0.2f;
+                v.z *= (sv[u].z > 0.f) ? 1.f : 0.2f; v.w *= (sv[u].w > 0.f) ? 1.f : 0.2f;
+            }
+            if (acc[u]) { v.x += old[u].x; v.y += old[u].y; v.z += old[u].z; v.w += old[u].w; }
+            *dst[u] = v;
+        }
+    }
+}
+
 constexpr int kSlabStages = 3;
 constexpr int kBStagesMax = 6;   // weight ring: L.nbs stages of L.TB taps each
 constexpr int kWorkerThreads = 128;
 
 // NTEAMS converter teams (4 warps each) take jobs round-robin: 2 teams / 3 slab stages when two CTAs share an SM (dense
 // launches), 4 teams / 6 stages for the sparse deep-layer launches whose K loop is converter-latency bound.
-template <int NTEAMS>
+template <int NTEAMS, bool DG>
 __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plane_conv_umma_kernel(const __grid_constant__ UmmaLaunch L) {
     constexpr int kSlabStages = (NTEAMS == 2) ? 3 : 6;
     constexpr int kMmaWarp = NTEAMS * 4, kSlabMax = 6;
@@ -322,6 +414,7 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
             const UmmaGroup& G = K.groups[g];
             const PlaneView& P = L.planes[G.plane];
             const int nchunk = (P.C + 15) >> 4;
+            if (group_is_empty(L, G, m_base)) continue;
             for (int c = 0; c < nchunk; ++c, ++ji) {
                 if ((ji % NTEAMS) != team) continue;
                 const int st = ji % kSlabStages;
@@ -340,8 +433,8 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                         if (rr < L.rows_alloc) load_row16(P, b, m_base + G.dmin + rr, c * 16, x[u]);
                     }
                     if (!waited) {
-                        if (tid == 0) { T_WAIT(6, mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1)); }
-                        else mbar_wait(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
+                        if (tid == 0) { T_WAIT(6, mbar_wait_bg(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1)); }
+                        else mbar_wait_bg(BAR(SLAB_EMPTY + st), ((ji / kSlabStages) & 1) ^ 1);
                         waited = true;
                     }
 #pragma unroll
@@ -368,11 +461,13 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
         }
         // ===================== epilogue (team 0: TMEM lane quarter = warp id) =====================
         if (team == 0) {
-        if (tid == 0) { T_WAIT(8, mbar_wait(BAR(ACC_FULL), 0)); }
-        else mbar_wait(BAR(ACC_FULL), 0);
+        if (tid == 0) { T_WAIT(8, mbar_wait_bg(BAR(ACC_FULL), 0)); }
+        else mbar_wait_bg(BAR(ACC_FULL), 0);
         tc_fence_after();
         const long long t_epi = T_NOW();
         const int n0 = split * NPAD;
+        bool any_group = false;                          // all groups skipped as empty: the accumulator was never written = zeros
+        for (int g = 0; g < K.ngroups; ++g) any_group = any_group || !group_is_empty(L, K.groups[g], m_base);
         // Stage each 128 x CW accumulator block in shared memory (the slab / weight ring is idle now: every MMA
         // has retired), then write it out with one warp per output row: fully coalesced stores, and the
         // LeakyReLU-slope / accumulate reads of the dgrad epilogue are coalesced too.
@@ -396,6 +491,10 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                     } else {
                         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + c0 + cb), v);
                     }
+                    if (!any_group) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    }
                     if (L.epilogue == EPI_BIAS_LRELU) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -416,23 +515,10 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
                 if (vec) {
-                    const int Q = ncols >> 2;
-                    for (int it = lane; it < 32 * Q; it += 32) {
-                        const int rl = it / Q, q = it - rl * Q;
-                        const int r = warp * 32 + rl;
-                        const int m = m_base + mt * 128 + r;
-                        if (m >= K.out.m_hi) continue;
-                        const long long roff = tile_off + (long long)m * K.out.rstride;
-                        float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
-                        if (L.epilogue == EPI_SLOPE && K.out.saved) {
-                            const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
-                            o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
-                            o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
-                        }
-                        float4* dst = reinterpret_cast<float4*>(K.out.base + roff) + q;
-                        if (m >= K.out.acc_lo && m < K.out.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                        *dst = o;
-                    }
+                    if (DG) epi_write_rows_vec(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, tile_off,
+                                               L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
+                    else epi_write_rows_simple(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, tile_off,
+                                               L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
                 } else {
                     for (int it = lane; it < 32 * ncols; it += 32) {
                         const int rl = it / ncols, j = it - rl * ncols;
@@ -466,6 +552,7 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
             for (int g = 0; g < K.ngroups; ++g) {
                 const UmmaGroup& G = K.groups[g];
                 const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                if (group_is_empty(L, G, m_base)) continue;
                 for (int c = 0; c < nchunk; ++c, ++ji) {
                     const int st = ji % kSlabStages;
                     T_WAIT(4, mbar_wait(BAR(SLAB_FULL + st), (ji / kSlabStages) & 1));
@@ -530,11 +617,12 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 const UmmaGroup& G = K.groups[g];
                 const int nchunk = (L.planes[G.plane].C + 15) >> 4;
                 const int nterm = G.term_end - G.term_begin;
+                if (group_is_empty(L, G, m_base)) { blk += (size_t)nchunk * nterm; continue; }
                 for (int c = 0; c < nchunk; ++c) {
                     for (int t0 = 0; t0 < nterm; t0 += TB, ++bi) {
                         const int nt = min(TB, nterm - t0);
                         const int bs = bi % nbs;
-                        T_WAIT(10, mbar_wait(BAR(B_EMPTY + bs), ((bi / nbs) & 1) ^ 1));
+                        T_WAIT(10, mbar_wait_bg(BAR(B_EMPTY + bs), ((bi / nbs) & 1) ^ 1));
                         mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes * nt);
                         bulk_g2s(smem_u32(bring0 + bs * bstage_bytes), src + blk * bblk_bytes, bblk_bytes * nt, BAR(B_FULL + bs));
                         blk += nt;
@@ -583,7 +671,7 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaLaunch& L, int t) {
 
 // PT converter teams (4 warps each): warps [0, 4PT) convert, warp 4PT issues MMAs, 4PT+1 streams weights, 4PT+2..4PT+5
 // run the epilogue (4PT+2 = 2 mod 4, so `warp & 3` covers the four TMEM lane quarters).  PT+1 slab stages.
-template <int PT>
+template <int PT, bool DG>
 __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
     constexpr int kSlabStages = PT + 1;
     constexpr int kMmaWarp = 4 * PT, kLoadWarp = 4 * PT + 1, kEpiWarp0 = 4 * PT + 2;
@@ -632,6 +720,7 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                 const UmmaGroup& G = K.groups[g];
                 const PlaneView& P = L.planes[G.plane];
                 const int nchunk = (P.C + 15) >> 4;
+                if (group_is_empty(L, G, tc.m_base)) continue;
                 for (int c = 0; c < nchunk; ++c, ++jg) {
                     if ((jg % PT) != team) continue;
                     const int st = jg % kSlabStages;
@@ -646,7 +735,7 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                             const int rr = rbase + u * kWorkerThreads + ttid;
                             if (rr < L.rows_alloc) load_row16(P, tc.b, tc.m_base + G.dmin + rr, c * 16, x[u]);
                         }
-                        if (!waited) { mbar_wait(BAR(SLAB_EMPTY + st), ((jg / kSlabStages) & 1) ^ 1); waited = true; }
+                        if (!waited) { mbar_wait_bg(BAR(SLAB_EMPTY + st), ((jg / kSlabStages) & 1) ^ 1); waited = true; }
 #pragma unroll
                         for (int u = 0; u < kRB; ++u) {
                             const int rr = rbase + u * kWorkerThreads + ttid;
@@ -686,6 +775,7 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                 for (int g = 0; g < K.ngroups; ++g) {
                     const UmmaGroup& G = K.groups[g];
                     const int nchunk = (L.planes[G.plane].C + 15) >> 4;
+                    if (group_is_empty(L, G, tc.m_base)) continue;
                     for (int c = 0; c < nchunk; ++c, ++jg) {
                         const int st = jg % kSlabStages;
                         mbar_wait(BAR(SLAB_FULL + st), (jg / kSlabStages) & 1);
@@ -746,11 +836,12 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                     const UmmaGroup& G = K.groups[g];
                     const int nchunk = (L.planes[G.plane].C + 15) >> 4;
                     const int nterm = G.term_end - G.term_begin;
+                    if (group_is_empty(L, G, tc.m_base)) { blk += (size_t)nchunk * nterm; continue; }
                     for (int c = 0; c < nchunk; ++c)
                         for (int t0 = 0; t0 < nterm; t0 += TB, ++bg) {
                             const int nt = min(TB, nterm - t0);
                             const int bs = bg % nbs;
-                            mbar_wait(BAR(B_EMPTY + bs), ((bg / nbs) & 1) ^ 1);
+                            mbar_wait_bg(BAR(B_EMPTY + bs), ((bg / nbs) & 1) ^ 1);
                             mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes * nt);
                             bulk_g2s(smem_u32(bring0 + bs * bstage_bytes), src + blk * bblk_bytes, bblk_bytes * nt, BAR(B_FULL + bs));
                             blk += nt;
@@ -768,8 +859,10 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
             const UmmaClass& K = L.cls[tc.cls];
             const int buf = k & 1;
             const int n0 = tc.split * NPAD;
-            mbar_wait(BAR(ACC_FULL + buf), (k >> 1) & 1);
+            mbar_wait_bg(BAR(ACC_FULL + buf), (k >> 1) & 1);
             tc_fence_after();
+            bool any_group = false;                      // all groups skipped as empty: the accumulator was never written = zeros
+            for (int g = 0; g < K.ngroups; ++g) any_group = any_group || !group_is_empty(L, K.groups[g], tc.m_base);
             const int c0_last = min((NPAD - 1) / CW, (L.N - n0 - 1) / CW) * CW;      // last column block that holds real channels
             for (int mt = 0; mt < L.MT; ++mt) {
                 for (int c0 = 0; c0 < NPAD; c0 += CW) {
@@ -785,6 +878,10 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                                 tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)mt * acc_w + (uint32_t)(NPAD + c0 + cb), v2);
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                            }
+                            if (!any_group) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = 0.f;
                             }
                             if (L.epilogue == EPI_BIAS_LRELU) {
 #pragma unroll
@@ -810,23 +907,10 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                         const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                          ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
                         if (vec) {
-                            const int Q = ncols >> 2;
-                            for (int it = lane; it < 32 * Q; it += 32) {
-                                const int rl = it / Q, q = it - rl * Q;
-                                const int r = q4 * 32 + rl;
-                                const int m = tc.m_base + mt * 128 + r;
-                                if (m >= K.out.m_hi) continue;
-                                const long long roff = tile_off + (long long)m * K.out.rstride;
-                                float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * SW + 4 * q);
-                                if (L.epilogue == EPI_SLOPE && K.out.saved) {
-                                    const float4 sv = __ldg(reinterpret_cast<const float4*>(K.out.saved + roff) + q);
-                                    o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
-                                    o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
-                                }
-                                float4* dst = reinterpret_cast<float4*>(K.out.base + roff) + q;
-                                if (m >= K.out.acc_lo && m < K.out.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                                *dst = o;
-                            }
+                            if (DG) epi_write_rows_vec(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tile_off,
+                                                       L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
+                            else epi_write_rows_simple(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tile_off,
+                                                       L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
                         } else {
                             for (int it = lane; it < 32 * ncols; it += 32) {
                                 const int rl = it / ncols, j = it - rl * ncols;
@@ -976,7 +1060,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                             load_row16(P, bb, (bb < L.batch) ? K.out.m_lo + off + G.dmin : -(1 << 30), c * 16, x[w]);
                         }
                     }
-                    if (!waited) { mbar_wait(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1); waited = true; }
+                    if (!waited) { mbar_wait_bg(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1); waited = true; }
 #pragma unroll
                     for (int w = 0; w < kRB; ++w) {
                         const int rr = rbase + w * kWorkerThreads + ttid;
@@ -1004,7 +1088,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                     float x[16];
                     const int u = v0 + rr, bb = u / pitch, off = u - bb * pitch;             // virtual row -> (item, row)
                     load_row16(P, bb, (bb < L.batch) ? K.out.m_lo + off + G.dmin : -(1 << 30), c * 16, x);
-                    if (!waited) { mbar_wait(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1); waited = true; }
+                    if (!waited) { mbar_wait_bg(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1); waited = true; }
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -1017,7 +1101,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                     *reinterpret_cast<uint4*>(Sl + 2 * atom_stride + 16u * rr) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(Sl + 3 * atom_stride + 16u * rr) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
-                if (!waited) mbar_wait(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1);
+                if (!waited) mbar_wait_bg(BAR(SLAB_EMPTY + st), ((jl / kFoldSlabStages) & 1) ^ 1);
                 }
                 fence_proxy_async();
                 mbar_arrive(BAR(SLAB_FULL + st));
@@ -1028,7 +1112,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
         // ===================== team 0: partial accumulator -> own shared memory (TMEM lane quarter = warp id) ==========
         if (team == 0) {
             float* part = reinterpret_cast<float*>(smem);
-            if (has_work) { mbar_wait(BAR(ACC_FULL), 0); tc_fence_after(); }
+            if (has_work) { mbar_wait_bg(BAR(ACC_FULL), 0); tc_fence_after(); }
             if (tid == 0) T_MARK(4);
             for (int mt = 0; mt < L.MT; ++mt)
                 for (int cb = 0; cb < NPAD; cb += 16) {
@@ -1137,7 +1221,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                     for (int t0 = 0; t0 < nterm; t0 += TB, ++bi) {
                         const int nt = min(TB, nterm - t0);
                         const int bs = bi % nbs;
-                        mbar_wait(BAR(B_EMPTY + bs), ((bi / nbs) & 1) ^ 1);
+                        mbar_wait_bg(BAR(B_EMPTY + bs), ((bi / nbs) & 1) ^ 1);
                         mbar_arrive_expect_tx(BAR(B_FULL + bs), bblk_bytes * nt);
                         bulk_g2s(smem_u32(bring0 + bs * bstage_bytes), src + blk * bblk_bytes, bblk_bytes * nt, BAR(B_FULL + bs));
                         blk += nt;
@@ -1255,16 +1339,22 @@ size_t umma_smem_bytes(const UmmaLaunch& L) {
     return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * 6 + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD;
 }
 
+template <typename KernelT>
+static cudaError_t set_smem_limit(KernelT kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(plane_conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(plane_conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(plane_conv_umma_persistent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(plane_conv_umma_persistent<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = set_smem_limit(plane_conv_umma_kernel<2, false>, 200 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<2, true>, 200 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<4, false>, 220 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<4, true>, 220 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_persistent<2, false>, 220 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_persistent<2, true>, 220 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_persistent<3, false>, 220 * 1024);
+        if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_persistent<3, true>, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1278,16 +1368,28 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     }
     total *= L.nsplit;
     if (max_tiles <= 0) return cudaSuccess;
+    const bool dg = L.epilogue == EPI_SLOPE;      // dgrad: batched read-back epilogue (separate instantiation)
     if (L.persistent) {
         const int grid = total < 148 ? total : 148;
-        if (L.nteams == 3) plane_conv_umma_persistent<3><<<grid, 3 * 128 + 192, umma_pers_smem_bytes(L), stream>>>(L, total);
-        else plane_conv_umma_persistent<2><<<grid, 2 * 128 + 192, umma_pers_smem_bytes(L), stream>>>(L, total);
+        const size_t smem = umma_pers_smem_bytes(L);
+        if (L.nteams == 3) {
+            if (dg) plane_conv_umma_persistent<3, true><<<grid, 3 * 128 + 192, smem, stream>>>(L, total);
+            else plane_conv_umma_persistent<3, false><<<grid, 3 * 128 + 192, smem, stream>>>(L, total);
+        } else {
+            if (dg) plane_conv_umma_persistent<2, true><<<grid, 2 * 128 + 192, smem, stream>>>(L, total);
+            else plane_conv_umma_persistent<2, false><<<grid, 2 * 128 + 192, smem, stream>>>(L, total);
+        }
         return cudaGetLastError();
     }
     const size_t smem = umma_smem_bytes(L);
     dim3 grid(max_tiles, L.nsplit, L.batch * L.ncls);
-    if (L.nteams == 4) plane_conv_umma_kernel<4><<<grid, 4 * 128 + 64, smem, stream>>>(L);
-    else plane_conv_umma_kernel<2><<<grid, 2 * 128 + 64, smem, stream>>>(L);
+    if (L.nteams == 4) {
+        if (dg) plane_conv_umma_kernel<4, true><<<grid, 4 * 128 + 64, smem, stream>>>(L);
+        else plane_conv_umma_kernel<4, false><<<grid, 4 * 128 + 64, smem, stream>>>(L);
+    } else {
+        if (dg) plane_conv_umma_kernel<2, true><<<grid, 2 * 128 + 64, smem, stream>>>(L);
+        else plane_conv_umma_kernel<2, false><<<grid, 2 * 128 + 64, smem, stream>>>(L);
+    }
     return cudaGetLastError();
 }
 
@@ -1393,8 +1495,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) wgrad_umma_kernel(const __gri
                     }
                 }
                 if (!waited) {
-                    if (tid == 0) { T_WAIT(6, mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1)); }
-                    else mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
+                    if (tid == 0) { T_WAIT(6, mbar_wait_bg(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1)); }
+                    else mbar_wait_bg(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
                     waited = true;
                 }
 #pragma unroll
@@ -1428,8 +1530,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) wgrad_umma_kernel(const __gri
         }
         // ===================== epilogue: accumulators -> reductions into dW =====================
         // TMEM lane quarter = warp % 4; the CW/4 warps of a quarter split the taps.
-        if (tid == 0) { T_WAIT(8, mbar_wait(BAR(ACC), 0)); }
-        else mbar_wait(BAR(ACC), 0);
+        if (tid == 0) { T_WAIT(8, mbar_wait_bg(BAR(ACC), 0)); }
+        else mbar_wait_bg(BAR(ACC), 0);
         tc_fence_after();
         const long long t_epi = T_NOW();
         const int q4 = warp & 3;
@@ -1755,7 +1857,7 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
                 const int b = gch / Gp.chunks_per_batch;
                 const int rc = Gp.m_lo + (gch % Gp.chunks_per_batch) * kWgRK;      // first G row of the chunk
                 const int rowA = (swap ? rc : rc + dmin) - a_row0, rowB = (swap ? rc + dmin : rc) - b_row0;   // array indices
-                mbar_wait(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
+                mbar_wait_bg(BAR(EMPTY + st), ((ci / nst) & 1) ^ 1);
                 mbar_arrive_expect_tx(BAR(FULL + st), tx);
                 const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
                 for (int g = 0; g < chunksA; ++g) {
@@ -1807,7 +1909,7 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
         }
         __syncwarp();
     } else if (warp >= 4) {
-        mbar_wait(BAR(ACC), 0);
+        mbar_wait_bg(BAR(ACC), 0);
         tc_fence_after();
         const int q4 = warp & 3;
         const int m = ca0 + q4 * 32 + lane;
