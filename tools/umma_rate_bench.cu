@@ -35,12 +35,14 @@ __device__ __forceinline__ void commit(uint32_t bar) { asm volatile("tcgen05.com
 // mode 0: same operands every MMA; 1: rotating operands (3 MMAs per product); 2: rotating, fused-N (2 MMAs per product);
 // 3: rotating, hi*hi only (1 MMA per K step: what a single-pass bf16 kernel would issue)
 template <int STYLE>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int N, int MT, int iters, long long* out, const int* __restrict__ taps) {
+__global__ void __launch_bounds__(384, 1) rate_kernel(int mode, int N, int MT, int iters, long long* out, const int* __restrict__ taps, int bg, volatile int* stop_flag) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_holder;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    __shared__ volatile int done;
+    if (threadIdx.x == 0) done = 0;
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_holder)) : "memory");
@@ -51,6 +53,22 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int N, int MT, i
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = tmem_holder;
+    if (warp >= 4) {
+        // background shared-memory traffic (what converter / epilogue warps generate next to the MMA issuer):
+        // bg 1: 16-byte stores, bg 2: 16-byte loads, bg 3: both; into the last 8 KB of the buffer (not an MMA operand)
+        uint4* scratch = reinterpret_cast<uint4*>(smem + 192 * 1024) + (threadIdx.x - 128);
+        uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+        if (bg) {
+            while (!done) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if (bg & 1) scratch[(r & 1) * 256] = v;
+                    if (bg & 2) { uint4 t = scratch[(r & 1) * 256]; v.x ^= t.y; }
+                }
+            }
+        }
+        if (v.x == 0xdeadbeef) out[1] = v.x;
+    }
     if (STYLE == 0) {
     if (warp == 0 && elect_one()) {        // elect.sync, not lane == 0: otherwise every MMA is wrapped in an ELECT retry loop
         // slab stage: [hi a0 | hi a1 | lo a0 | lo a1][rows_alloc][16 B]; 3 stages; weight ring behind them: blocks of 64*N bytes
@@ -81,6 +99,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int N, int MT, i
         mbar_wait(smem_u32(&bar), 0);
         long long t1 = clock64();
         if (blockIdx.x == 0) out[0] = t1 - t0;
+        done = 1;
     }
     } else if (warp == 0) {
         // STYLE 1: every lane of the issuing warp runs the loop (warp-uniform values -> uniform datapath), only the MMAs of
@@ -123,6 +142,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int N, int MT, i
         mbar_wait(smem_u32(&bar), 0);
         long long t1 = clock64();
         if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[0] = t1 - t0;
+        done = 1;
     }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -138,22 +158,21 @@ int main() {
     int* dtaps; CK(cudaMalloc(&dtaps, sizeof(htaps))); CK(cudaMemcpy(dtaps, htaps, sizeof(htaps), cudaMemcpyHostToDevice));
     const char* names[4] = {"same operands, 3 MMA", "rotating operands, 3 MMA", "rotating, fused-N 2 MMA", "rotating, 1 MMA (hi*hi)"};
     printf("cycles per PRODUCT K step (M=128 rows x N x K=16; math floor at 4096 MAC/clk: 3 MMAs = 1.5*N, fused = 1.5*N)\n");
-    for (int N : {32, 48, 96, 144, 192, 256})
+    for (int N : {32, 48, 96, 144})
         for (int MT : {1, 2}) {
-            if (MT * N * 2 > 512) continue;
-            for (int mode = 0; mode < 4; ++mode) {
+            for (int mode : {1, 2}) {
                 if (mode == 2 && 2 * N > 256) continue;
                 const int iters = 60;
-                double r[2];
-                for (int style = 0; style < 2; ++style) {
-                    if (style == 0) rate_kernel<0><<<148, 128, 200 * 1024>>>(mode, N, MT, iters, dout, dtaps);
-                    else rate_kernel<1><<<148, 128, 200 * 1024>>>(mode, N, MT, iters, dout, dtaps);
+                double r[4];
+                for (int bg = 0; bg < 4; ++bg) {
+                    rate_kernel<0><<<148, 384, 200 * 1024>>>(mode, N, MT, iters, dout, dtaps, bg, nullptr);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("ERROR %s\n", cudaGetErrorString(e)); return 1; }
                     long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
-                    r[style] = (double)cyc / (iters * 8 * MT);
+                    r[bg] = (double)cyc / (iters * 8 * MT);
                 }
-                printf("N=%3d MT=%d %-26s : one elected region %7.1f | warp-uniform loop %7.1f  cycles / K step / row tile (math %d)\n", N, MT, names[mode], r[0], r[1], (mode == 3 ? N / 2 : 3 * N / 2));
+                printf("N=%3d MT=%d %-26s : alone %6.1f | +8 warps storing %6.1f | loading %6.1f | both %6.1f   cycles / K step / row tile\n",
+                       N, MT, names[mode], r[0], r[1], r[2], r[3]);
             }
         }
     return 0;

@@ -1653,8 +1653,12 @@ bool umma_plan_wgrad(UmmaWgradLaunch* L) {
         G.n_tapsets = (G.ntaps + tpc - 1) / tpc;
         tpc = (G.ntaps + G.n_tapsets - 1) / G.n_tapsets;   // balance
         G.taps_per_cta = tpc;
+        {   // fused-N (bulk-fed kernel): only where it costs no extra tap set, i.e. the doubled accumulators still fit TMEM
+            static const int fuse_on = [] { const char* e = getenv("WUN_WG_FUSE"); return (e && e[0] == '0') ? 0 : 1; }();
+            G.fuse = (fuse_on && 2 * NT <= 256 && tpc * 2 * NT <= 512) ? 1 : 0;
+        }
         int tm = 32;
-        while (tm < tpc * NT) tm *= 2;
+        while (tm < tpc * NT * (G.fuse ? 2 : 1)) tm *= 2;
         G.tmem_cols = tm;
         G.chunks_per_batch = (rows + kWgRK - 1) / kWgRK;
         work += (long long)L->batch * G.chunks_per_batch * G.n_tapsets * G.n_mtiles * G.n_ntiles;
@@ -1880,6 +1884,8 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*NT
+            const uint32_t accw = (uint32_t)(Gp.fuse ? 2 * NT : NT);
             uint32_t accum = 0;
             for (int ci = 0; ci < nchunks; ++ci) {
                 const int st = ci % nst;
@@ -1891,7 +1897,19 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
                 for (int t = 0; t < ntap; ++t) {
                     const uint64_t shift = (uint64_t)(uint32_t)(Gp.d[tap0 + t] - dmin);
                     const uint64_t sha = swap ? 0ull : shift, shb = swap ? shift : 0ull;
-                    const uint32_t td = tmem_base + (uint32_t)(t * NT);
+                    const uint32_t td = tmem_base + (uint32_t)t * accw;
+                    if (Gp.fuse) {
+                        // fused-N: the B stage keeps the lo atom planes right behind the hi atom planes at the same stride, so one
+                        // descriptor with N = 2*NT covers [B_hi | B_lo]: 2 MMAs per product, halves summed in the epilogue
+#pragma unroll
+                        for (int ks = 0; ks < kWgRK / 16; ++ks) {
+                            const uint64_t koff = (uint64_t)(16 * ks);
+                            const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
+                            const uint64_t b_hi = b_hi0 + shb + koff;
+                            umma_bf16(td, a_hi, b_hi, idesc2, (ks == 0) ? accum : 1u);
+                            umma_bf16(td, a_lo, b_hi, idesc, 1u);
+                        }
+                    } else {
 #pragma unroll
                     for (int ks = 0; ks < kWgRK / 16; ++ks) {
                         const uint64_t koff = (uint64_t)(16 * ks);
@@ -1900,6 +1918,7 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
                         umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
                         umma_bf16(td, a_hi, b_lo, idesc, 1u);
                         umma_bf16(td, a_hi, b_hi, idesc, 1u);
+                    }
                     }
                 }
                 accum = 1u;
@@ -1921,7 +1940,13 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
                 if (cb0 + cb >= SB.C) break;
                 __syncwarp();
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * NT + cb), v);
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * (Gp.fuse ? 2 * NT : NT) + cb), v);
+                if (Gp.fuse) {
+                    float v2[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * 2 * NT + NT + cb), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
                 if (!m_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] *= L.scale;

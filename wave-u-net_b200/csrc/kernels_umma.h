@@ -95,6 +95,7 @@ struct WgGroup {
     int chunks_per_cta;     // consecutive (batch-folded) chunks one CTA reduces
     int n_ctas_x;           // ceil(batch*chunks_per_batch / chunks_per_cta)
     int tmem_cols;
+    int fuse;               // bulk-fed kernel: fused-N MMAs (A_hi x [B_hi|B_lo], A_lo x B_hi); accumulator stride 2*NT per tap
     int z0;                 // first blockIdx.z of this group (one z per tap set)
 };
 
