@@ -69,12 +69,33 @@ struct WunHandle {
     bool use_side = true;                // WUN_SIDE_STREAM=0 disables
     bool first_fast = true;              // dedicated first-layer kernels (kernels_first.cu); WUN_FIRST_LAYER=0 = generic path
     bool bulk_wgrad = true;              // split pass + bulk-copy-fed tcgen05 wgrad; WUN_BULK_WGRAD=0 = converter-fed kernel
+    // output layer in the last up block's conv epilogue (kernels_umma.h OutputFuse).  WUN_OUT_FUSE: 0 = separate kernels, 1 (default) =
+    // estimates + loss + dL/dpre + the gradient w.r.t. the features fused, the output convs' weight gradient as its own launch on
+    // the wgrad stream (off the critical path), 2 = the weight gradient in the epilogue too (measured slower: it serialises
+    // ~650 shuffle-reduction instructions per row tile on the four epilogue warps)
+    int out_fuse_mode = 1;
+    const OutputFuse* fuse_out = nullptr;   // set by run_forward around the last up block's forward conv
+    bool out_fused = false;              // that conv carried the output layer: no output_fwd / output_dgrad / output_wgrad launches
+    float* bw_grads = nullptr;           // wun_forward_backward: gradient buffer / scale, known to the forward pass for the fused epilogue
+    float bw_scale = 1.f;
+    int pair_min_ctas = 120;             // WUN_PAIR_MIN_CTAS
+    // LeakyReLU sign masks (plan.h Plan::mask_twin): which tensors' masks the last forward pass really wrote (the first-layer
+    // kernel and the non-folded tcgen05 kernels do), in which workspace; the dgrad epilogues then read bits instead of floats
+    bool sign_masks = true;              // WUN_SIGN_MASK=0 disables
+    std::vector<char> mask_live;
+    const float* mask_ws = nullptr; int mask_batch = 0;
+    std::vector<int> cur_mask_tensors;   // conv_forward -> launch_conv: tensors whose masks this launch would write
+    bool pair_fwd = true;                // the same for the forward classes of the up blocks; WUN_PAIR_FWD=0 disables
+    int pair_dgrad = 4;                  // pair-merged dgrad classes (launch.h OutView::pairC); WUN_PAIR_DGRAD=0 off, 1 all, 2 down blocks only,
+                                         // 3 up blocks only, 4 (default) down blocks whose merged width still takes the fused-N MMAs (2C <= 64)
     size_t split_item_bytes = 0;         // per batch item: largest split arena any layer's wgrad needs (dry run)
     cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
     // weight packs are hoisted off the critical path: phase 1 enqueues every pack kernel of the step on the side stream
     // (they only depend on the parameters), phase 2 enqueues everything else; phase 0 = inline (inference, debug hook)
     int phase = 0;
     size_t arena_cur = 0;                // bump pointer into the pack arena (same sequence in phase 1 and 2)
+    size_t pack_floor = 0;               // launch_conv reserves at least this much: the pair-merge decision depends on the batch
+                                         // (folded or not) but the arena is sized by a batch-1 dry run, so both forms' bytes count
     size_t arena_sum = 0;                // total pack bytes of one forward+backward (dry run)
     cudaEvent_t packs_event = nullptr;
     bool packs_pending = false;          // main stream has not yet waited for the hoisted packs
@@ -188,6 +209,14 @@ static const float* tensor_ptr(const WunHandle* h, int tensor) {
     return h->ws + h->lay.off[tensor];
 }
 
+// sign mask of `tensor` as seen through a view with this row offset (launch.h OutView::mask), or null
+static uint8_t* mask_ptr(const WunHandle* h, int tensor, int row_offset, int C) {
+    if (!h->sign_masks || tensor < 0 || tensor >= (int)h->plan.mask_twin.size()) return nullptr;
+    const int mt = h->plan.mask_twin[tensor];
+    if (mt < 0 || h->lay.off[mt] < 0) return nullptr;
+    return reinterpret_cast<uint8_t*>(h->ws + h->lay.off[mt]) + ((long long)row_offset * C) / 8;
+}
+
 static void tensor_geom(const WunHandle* h, int tensor, int64_t* rows, int* C, bool* per_batch) {
     if (tensor == TENSOR_MIX) { *rows = h->plan.T_in; *C = h->plan.cfg.num_channels; *per_batch = true; return; }
     const TensorSpec& t = h->plan.tensors[tensor];
@@ -232,10 +261,13 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
     const bool use_umma = h->umma_enabled && h->umma_pass[h->cur_pass] && umma_plan_from_conv(L, &ch);
     const size_t slot = (size_t)h->cur_layer * 3 + h->cur_pass;
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
+    if (use_umma && !ch.folded && h->phase != 1)
+        for (int t : h->cur_mask_tensors) h->mask_live[t] = 1;      // the persistent / dense epilogues store the sign bits
     if (use_umma) {
+        if (h->fuse_out && h->debug_iters == 0 && umma_output_fusable(L, ch, h->fuse_out->O)) h->out_fused = true;
         if (h->phase != 1) h->launches += 2;    // weight pack + conv (counted once)
         if (h->dry) {
-            h->arena_bytes = std::max(h->arena_bytes, ch.pack_bytes); h->arena_sum += ch.pack_bytes;
+            h->arena_bytes = std::max(h->arena_bytes, std::max(ch.pack_bytes, h->pack_floor)); h->arena_sum += std::max(ch.pack_bytes, h->pack_floor);
             if (h->audit) {
                 long long tiles = 0, mmas = 0; int max_rows = 0, span = 0;
                 for (int q = 0; q < L.ncls; ++q) {
@@ -263,16 +295,17 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
                 }
                 char line[512];
                 snprintf(line, sizeof(line), "conv layer=%d pass=%d kernel=%s N=%d NPAD=%d nsplit=%d MT=%d rows_alloc=%d span=%d tmem=%d "
-                         "TB=%d nbs=%d nteams=%d fuse=%d ksplit=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu",
+                         "TB=%d nbs=%d nteams=%d fuse=%d ksplit=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu pair=%d outfuse=%d",
                          h->cur_layer, h->cur_pass, ch.folded ? "fold" : (ch.persistent ? "persistent" : (ch.nteams == 4 ? "sparse4" : "dense2")), L.N,
                          ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, ch.ksplit, tiles, mmas,
-                         max_rows, umma_choice_smem_bytes(ch), ch.pack_bytes);
+                         max_rows, umma_choice_smem_bytes(ch), ch.pack_bytes, L.pairC,
+                         (h->fuse_out && umma_output_fusable(L, ch, h->fuse_out->O)) ? 1 : 0);
                 h->audit->push_back(line);
             }
             return WUN_OK;
         }
         uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total) + h->arena_cur;
-        h->arena_cur += ch.pack_bytes;
+        h->arena_cur += std::max(ch.pack_bytes, h->pack_floor);
         UmmaLaunch U; UmmaPackLaunch PL;
         cudaError_t e = umma_build(L, ch, arena, &U, &PL);
         if (e == cudaSuccess && h->phase != 2) e = launch_umma_pack(PL, (h->phase == 1) ? h->side : h->stream);
@@ -293,7 +326,9 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
                 h->packs_pending = false;
             }
             const int iters = (h->debug_iters > 0) ? h->debug_iters : 1;
-            for (int i = 0; i < iters && e == cudaSuccess; ++i) e = launch_plane_conv_umma(U, h->stream);
+            const OutputFuse* fuse = (h->fuse_out && h->debug_iters == 0 && umma_output_fusable(L, ch, h->fuse_out->O)) ? h->fuse_out : nullptr;
+            if (fuse) h->out_fused = true;
+            for (int i = 0; i < iters && e == cudaSuccess; ++i) e = launch_plane_conv_umma(U, h->stream, fuse);
         }
         if (e != cudaSuccess) return set_err(WUN_E_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(e));
         return WUN_OK;
@@ -333,7 +368,61 @@ static bool first_layer_desc(const WunHandle* h, const ConvOp& op, FirstLayer* F
     F->W = h->params + h->plan.params[op.w_param].offset;
     F->bias = h->params + h->plan.params[op.b_param].offset;
     F->batch = h->batch;
+    F->dec_mask = mask_ptr(h, c0.out.tensor, 0, op.cout);
+    F->odd_mask = mask_ptr(h, c1.out.tensor, 0, op.cout);
     return true;
+}
+
+// Two classes of equal width -> one pair-merged class (launch.h OutView::pairC), or false if the pair does not qualify.
+static bool merge_pair(const ConvLaunch& S, ConvLaunch* out) {
+    if (S.ncls != 2 || S.N % 4 != 0 || 2 * S.N > 256) return false;
+    const OutView& A = S.cls[0];
+    const OutView& B = S.cls[1];
+    if (A.m_hi <= A.m_lo || B.m_hi <= B.m_lo) return false;
+    // worthwhile only when most rows exist in both classes (the union is what gets computed)
+    const int lo = std::min(A.m_lo, B.m_lo), hi = std::max(A.m_hi, B.m_hi);
+    if ((long long)(hi - lo) * 4 > 3LL * ((A.m_hi - A.m_lo) + (B.m_hi - B.m_lo))) return false;
+    ConvLaunch M = S;
+    M.ncls = 1; M.N = 2 * S.N; M.pairC = S.N; M.max_rows = hi - lo;
+    OutView& O = M.cls[0];
+    O = A;
+    O.m_lo = lo; O.m_hi = hi;
+    O.pairC = S.N;
+    O.base2 = B.base; O.bstride2 = B.bstride; O.rstride2 = B.rstride; O.saved2 = B.saved;
+    O.acc_lo2 = B.acc_lo; O.acc_hi2 = B.acc_hi;
+    O.mask2 = B.mask; O.smask2 = B.smask;
+    O.lo_h[0] = A.m_lo; O.hi_h[0] = A.m_hi; O.lo_h[1] = B.m_lo; O.hi_h[1] = B.m_hi;
+    // union of the two classes' (plane, shift) terms
+    int nt = 0;
+    Term merged[kMaxTerms];
+    for (int t = A.term_begin; t < A.term_end; ++t) { merged[nt] = S.terms[t]; merged[nt].woff2 = -1; ++nt; }
+    for (int t = B.term_begin; t < B.term_end; ++t) {
+        int f = -1;
+        for (int u = 0; u < nt; ++u) if (merged[u].plane == S.terms[t].plane && merged[u].d == S.terms[t].d) f = u;
+        if (f < 0) {
+            if (nt >= kMaxTerms) return false;
+            merged[nt] = S.terms[t]; merged[nt].woff = -1; merged[nt].woff2 = S.terms[t].woff; ++nt;
+        } else {
+            merged[f].woff2 = S.terms[t].woff;
+        }
+    }
+    std::stable_sort(merged, merged + nt, [](const Term& a, const Term& b) {
+        if (a.plane != b.plane) return a.plane < b.plane;
+        return a.d < b.d;
+    });
+    for (int t = 0; t < nt; ++t) M.terms[t] = merged[t];
+    O.term_begin = 0; O.term_end = nt;
+    *out = M;
+    return true;
+}
+
+// Measured (M4 batch 16, same box A/B): merged launches that fill the GPU win (up8..up11 forward 78/66/95/115 -> 56/58/67/83 us),
+// a merged launch with far fewer CTAs than SMs loses to the two-class form (up7 forward 64 -> 72 us at 80 CTAs).
+static bool pair_worthwhile(const WunHandle* h, const ConvLaunch& M, const UmmaChoice& ch) {
+    long long ctas = 0;
+    for (int q = 0; q < M.ncls; ++q)
+        ctas += (long long)((M.cls[q].m_hi - M.cls[q].m_lo + ch.MT * 128 - 1) / (ch.MT * 128)) * ch.nsplit * M.batch;
+    return ctas >= h->pair_min_ctas;
 }
 
 static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
@@ -343,12 +432,15 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
         if (first_layer_desc(h, op, &F)) {
             if (h->phase == 1) return WUN_OK;
             ++h->launches;
+            if (F.dec_mask) h->mask_live[op.classes[0].out.tensor] = 1;
+            if (F.odd_mask) h->mask_live[op.classes[1].out.tensor] = 1;
             if (!h->dry) launch_first_fwd(F, h->plan.cfg.num_channels, op.cout, h->stream);
             return WUN_OK;
         }
     }
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
+    h->cur_mask_tensors.clear();
     L.nplanes = (int)op.planes.size();
     for (int p = 0; p < L.nplanes; ++p) L.planes[p] = make_plane(h, op.planes[p]);
     L.ncls = (int)op.classes.size();
@@ -359,6 +451,8 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
         PlaneView ov = make_plane(h, c.out);
         o.base = const_cast<float*>(ov.base); o.bstride = ov.bstride; o.rstride = ov.rstride;
         o.m_lo = c.m_lo; o.m_hi = c.m_hi; o.saved = nullptr; o.acc_lo = o.acc_hi = 0;
+        o.mask = (c.out.kind == PLANE_DIRECT && c.out.C % 8 == 0) ? mask_ptr(h, c.out.tensor, c.out.row_offset, c.out.C) : nullptr;
+        if (o.mask) h->cur_mask_tensors.push_back(c.out.tensor);
         o.term_begin = nt;
         for (const auto& t : c.terms) {
             if (nt >= kMaxTerms) return set_err(WUN_E_INVALID, "too many conv terms");
@@ -371,7 +465,22 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
     L.W = h->params + h->plan.params[op.w_param].offset;
     L.bias = h->params + h->plan.params[op.b_param].offset;
     L.epilogue = EPI_BIAS_LRELU; L.batch = h->batch; L.max_rows = max_rows;
-    return launch_conv(h, L);
+    // the even / odd output rows of an up block (and of the bottleneck) read the same planes at the same shifts: one
+    // pair-merged class of 2*cout columns (out tensor viewed as [B, rows/2, 2*cout]) - 6+6 taps instead of 2 x (5+5)
+    ConvLaunch M;
+    h->pack_floor = 0;
+    if (h->pair_fwd && L.ncls == 2 && h->umma_enabled && h->umma_pass[0] && merge_pair(L, &M)) {
+        UmmaChoice ch0, ch;
+        const bool ok0 = umma_plan_from_conv(L, &ch0), ok1 = umma_plan_from_conv(M, &ch);
+        if (ok0 && ok1) {
+            h->pack_floor = std::max(ch0.pack_bytes, ch.pack_bytes);
+            if (!ch0.folded && pair_worthwhile(h, M, ch)) L = M;
+        }
+    }
+    const int rc = launch_conv(h, L);
+    h->pack_floor = 0;
+    h->cur_mask_tensors.clear();
+    return rc;
 }
 
 // dgrad: one class per forward input plane that needs a gradient; the forward classes' gradient
@@ -400,6 +509,9 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
         o.base = const_cast<float*>(ov.base); o.bstride = ov.bstride; o.rstride = ov.rstride;
         o.m_lo = dc.r_lo; o.m_hi = dc.r_hi;
         o.saved = op.plane_slope[dc.plane] ? make_plane(h, v).base : nullptr;
+        if (o.saved && v.kind == PLANE_DIRECT && v.tensor >= 0 && v.tensor < (int)h->mask_live.size() && h->mask_live[v.tensor] &&
+            h->mask_ws == h->ws && h->mask_batch == h->batch)
+            o.smask = mask_ptr(h, v.tensor, v.row_offset, v.C);
         o.acc_lo = dc.acc_lo; o.acc_hi = dc.acc_hi;
         o.term_begin = nt;
         for (int q = 0; q < (int)op.classes.size(); ++q)
@@ -436,10 +548,29 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
         // slope is per class (saved != null); classes without saved use EPI_PLAIN semantics via null check
         S.epilogue = EPI_SLOPE;
         S.batch = h->batch;
-        if (S.max_rows > 0) {
-            int rc = launch_conv(h, S);
-            if (rc != WUN_OK) return rc;
+        if (S.max_rows <= 0) continue;
+        // Pair merge: two classes of the same width (the even / odd input rows of a down block; the skip-even / skip-odd or
+        // the copied / interpolated inputs of an up block) read the same gradient planes with the same row shifts.  As ONE
+        // class of N = 2C columns every slab is staged once instead of twice and a tap costs one MMA instead of two (for
+        // N <= 64 an MMA costs the same ~46 cycles whatever N is) - launch.h OutView::pairC.
+        ConvLaunch M;
+        // Measured (M4 batch 16, same-box A/B): down1 (2C = 48, fused-N MMAs) 368 -> 332 us; wider pairs lose the fused-N form and
+        // got slower (down2 276 -> 317, down3 216 -> 250, down4 156 -> 183, up11 194 -> 215 us): their dgrad is bound by the
+        // epilogue's slope / accumulate read-backs, not by slab fills or MMAs.
+        const bool pair_on = h->pair_dgrad == 1 || (h->pair_dgrad == 2 && op.planes.size() == 2) || (h->pair_dgrad == 3 && op.planes.size() == 4) ||
+                             (h->pair_dgrad == 4 && op.planes.size() == 2 && 2 * S.N <= 64);
+        h->pack_floor = 0;
+        if (h->pair_dgrad != 0 && S.ncls == 2 && h->umma_enabled && h->umma_pass[1] && merge_pair(S, &M)) {
+            UmmaChoice ch0, ch;       // the deep, few-row layers keep the batch-folded kernel (it has no pair-merged epilogue)
+            const bool ok0 = umma_plan_from_conv(S, &ch0), ok1 = umma_plan_from_conv(M, &ch);
+            if (ok0 && ok1) {
+                h->pack_floor = std::max(ch0.pack_bytes, ch.pack_bytes);
+                if (pair_on && !ch0.folded && pair_worthwhile(h, M, ch)) S = M;
+            }
         }
+        int rc = launch_conv(h, S);
+        h->pack_floor = 0;
+        if (rc != WUN_OK) return rc;
     }
     return WUN_OK;
 }
@@ -533,7 +664,11 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
         // WUN_SPLIT_COLSUM=1: bias column sums inside the split pass instead of their own launches.  Isolated, the wgrad family
         // is 10 % faster that way (2.38 vs 2.66 ms at M4 B=16), but the whole step was 0.05 ms slower in the same-box A/B (the
         // small colsum launches fill SMs the big-shared-memory kernels leave thread slots on), so it stays optional.
-        static const bool fused_colsum = [] { const char* e = getenv("WUN_SPLIT_COLSUM"); return e && e[0] == '1'; }();
+        // WUN_SPLIT_COLSUM=2: fused only for the layers with few rows (their colsum launches are pure launch latency on the wgrad stream)
+        static const int colsum_mode = [] { const char* e = getenv("WUN_SPLIT_COLSUM"); return e ? atoi(e) : 0; }();
+        int max_rows_g = 0;
+        for (const auto& dp : class_dpre) max_rows_g = std::max(max_rows_g, dp.r_hi - dp.r_lo);
+        const bool fused_colsum = colsum_mode == 1 || (colsum_mode == 2 && max_rows_g <= 4096);
         if (bulk) { ++h->launches; if (h->dry) h->split_item_bytes = std::max(h->split_item_bytes, split_need); }
         if (!bulk || !fused_colsum) colsum_launches();
         if (!h->dry) {
@@ -635,6 +770,7 @@ static void fill_output_launch(const WunHandle* h, OutputLaunch* O, const float*
 static int run_forward(WunHandle* h, const float* targets, float* outputs, float* loss, int training) {
     const Plan& P = h->plan;
     const int L = P.cfg.num_layers;
+    if (h->phase != 1) { h->mask_live.assign(P.tensors.size(), 0); h->mask_ws = h->ws; h->mask_batch = h->batch; }
     for (int i = 0; i < L; ++i) {
         const UpsampleSpec& us = P.ups[i];
         if (us.interp_param >= 0) {
@@ -648,10 +784,36 @@ static int run_forward(WunHandle* h, const float* targets, float* outputs, float
     for (int i = 0; i < L; ++i)
         if ((rc = conv_forward(h, P.down[i], i)) != WUN_OK) return rc;
     if ((rc = conv_forward(h, P.bottleneck, L)) != WUN_OK) return rc;
-    for (int i = 0; i < L; ++i)
-        if ((rc = conv_forward(h, P.up[i], L + 1 + i)) != WUN_OK) return rc;
     OutputLaunch O;
     fill_output_launch(h, &O, targets, outputs, loss, training);
+    OutputFuse OF;
+    memset(&OF, 0, sizeof(OF));
+    h->out_fused = false;
+    for (int i = 0; i < L; ++i) {
+        if (i == L - 1 && h->out_fuse_mode != 0 && P.cfg.output_filter_size == 1) {
+            // the output layer rides in this conv's epilogue when the planner picks the persistent kernel for it
+            OF.O = O;
+            const bool bw = targets != nullptr && h->bw_grads != nullptr;
+            OF.gfeat = bw ? const_cast<float*>(tensor_ptr(h, P.grad_twin[P.t_feat])) : nullptr;
+            OF.grads = (bw && h->out_fuse_mode == 2) ? h->bw_grads : nullptr;
+            OF.grad_scale = h->bw_scale;
+            const ConvOp& op = P.up[i];
+            bool geom = op.classes.size() >= 1 && op.classes.size() <= (size_t)kMaxClasses;
+            OF.t_step = geom ? op.classes[0].out.row_step : 0;
+            for (size_t q = 0; geom && q < op.classes.size(); ++q) {
+                const ViewSpec& v = op.classes[q].out;
+                if (v.tensor != P.t_feat || v.row_step != OF.t_step || v.kind != PLANE_DIRECT) geom = false;
+                OF.t0[q] = v.row_offset;
+            }
+            // a pair-merged launch has ONE class whose second half is the next frame: classes (even, odd rows) = offsets (0, 1)
+            if (geom && op.classes.size() == 2 && !(OF.t0[0] == 0 && OF.t0[1] == 1 && OF.t_step == 2)) geom = false;
+            if (geom && (targets == nullptr || bw)) h->fuse_out = &OF;       // (loss without gradients: the separate kernel)
+        }
+        rc = conv_forward(h, P.up[i], L + 1 + i);
+        h->fuse_out = nullptr;
+        if (rc != WUN_OK) return rc;
+    }
+    if (h->out_fused) return WUN_OK;
     if (h->phase != 1) ++h->launches;
     if (!h->dry && h->phase != 1) launch_output_fwd(O, h->stream);
     return WUN_OK;
@@ -670,8 +832,12 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     }
     OutputLaunch O;
     fill_output_launch(h, &O, targets, nullptr, nullptr, 1);
-    if (h->phase != 1) h->launches += 2;
-    if (!h->dry && h->phase != 1) {
+    // fused forward (run_forward): dL/dpre and the feature gradient already exist; only the output convs' weight gradient is left
+    // (mode 1), and it goes to the wgrad stream right after the first fork below
+    const bool out_wgrad_late = h->out_fused && h->out_fuse_mode != 2;
+    if (h->phase != 1 && !h->out_fused) h->launches += 2;
+    if (h->phase != 1 && out_wgrad_late) h->launches += 1;
+    if (!h->dry && h->phase != 1 && !h->out_fused) {
         launch_output_wgrad(O, grads, scale, h->stream);
         launch_output_dgrad(O, const_cast<float*>(tensor_ptr(h, P.grad_twin[P.t_feat])), h->stream);
     }
@@ -681,6 +847,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     for (int i = L - 1; i >= 0; --i) {
         const ConvOp& op = P.up[i];
         if ((rc = fork_side(h)) != WUN_OK) return rc;
+        if (i == L - 1 && out_wgrad_late && !h->dry && h->phase != 1) launch_output_wgrad(O, grads, scale, h->wstream);
         if ((rc = mark_grads_ready(h, ready_from, h->wstream)) != WUN_OK) return rc;
         ready_from = std::min(ready_from, op_first_offset(P, op, &P.ups[i]));
         if ((rc = conv_wgrad(h, op, grads, scale, L + 1 + i)) != WUN_OK) return rc;
@@ -741,6 +908,7 @@ static int begin_call(WunHandle* h, const float* params, const float* mix, int64
     h->dry = dry;
     h->launches = 0;
     h->batch = (int)batch;
+    h->bw_grads = nullptr; h->bw_scale = 1.f; h->fuse_out = nullptr; h->out_fused = false;
     if (dry) return WUN_OK;
     { int rc0 = check_device(); if (rc0 != WUN_OK) return rc0; }
     if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
@@ -784,6 +952,11 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* v = getenv("WUN_FIRST_LAYER"); h->first_fast = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_PACK_EVENTS"); h->pack_events_on = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = !(v && v[0] == '0'); }
+    { const char* v = getenv("WUN_PAIR_DGRAD"); h->pair_dgrad = v ? atoi(v) : 4; }
+    { const char* v = getenv("WUN_PAIR_MIN_CTAS"); h->pair_min_ctas = v ? atoi(v) : 120; }
+    { const char* v = getenv("WUN_SIGN_MASK"); h->sign_masks = !(v && v[0] == '0'); }
+    { const char* v = getenv("WUN_OUT_FUSE"); h->out_fuse_mode = v ? atoi(v) : 1; }
+    { const char* v = getenv("WUN_PAIR_FWD"); h->pair_fwd = !(v && v[0] == '0'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");
     // dry run: which kernel each layer uses and how much pack scratch the tcgen05 launches need
     wun_launches_forward_backward(h);
@@ -875,6 +1048,7 @@ int wun_forward_backward(WunHandle* h, const float* params, const float* mix, co
     if (!targets || !loss || !grads) return set_err(WUN_E_INVALID, "targets/loss/grads must not be null");
     WUN_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), h->stream));
     WUN_CUDA_OK(cudaMemsetAsync(grads, 0, sizeof(float) * h->plan.param_numel, h->stream));
+    h->bw_grads = grads; h->bw_scale = grad_scale;
     if (h->use_side && h->umma_enabled) {
         // phase 1: every weight pack of the step on the side stream, behind the work already enqueued on `stream`
         rc = ensure_side(h);

@@ -289,61 +289,137 @@ __device__ __forceinline__ bool group_is_empty(const UmmaLaunch& L, const UmmaGr
 // destination (dgrad) are issued for kEpiBatch items BEFORE any of them is used: the dgrad epilogue is a chain of dependent
 // global loads (measured: down1 dgrad 410 us with one load in flight per lane vs 175 us for the forward of the same layer,
 // whose epilogue only stores), so memory-level parallelism is what it needs.
-constexpr int kEpiBatch = 4;
+#ifndef WUN_EPI_BATCH
+#define WUN_EPI_BATCH 4
+#endif
+constexpr int kEpiBatch = WUN_EPI_BATCH;
 // forward launches (nothing to read back) keep the straight loop; the two forms live in separate kernel instantiations
 // (template parameter DG) because the batched form's registers slowed the forward kernels down when both shared one body
 // (down1 forward 149 -> 195 us).
+// Pair-merged classes (OutView::pairC > 0): the quad's column decides which of the two views a value belongs to (col0 = first
+// launch column of the staged block, a multiple of 4 like pairC, so a quad never straddles the halves).
+// PAIR = false (forward instantiations, which never see a pair-merged class) compiles the second view away.
+struct EpiDst { float* dst; const float* saved; bool use_mask, ok, acc; };
+template <bool PAIR>
+__device__ __forceinline__ EpiDst epi_dst(const OutView& O, int b, int m, int col, bool slope) {
+    EpiDst d;
+    if (PAIR && O.pairC > 0) {
+        const int h = (col >= O.pairC) ? 1 : 0;
+        d.ok = m >= O.lo_h[h] && m < O.hi_h[h];
+        const long long off = h ? ((long long)b * O.bstride2 + (long long)m * O.rstride2 + (col - O.pairC))
+                                : ((long long)b * O.bstride + (long long)m * O.rstride + col);
+        d.dst = (h ? O.base2 : O.base) + off;
+        const float* sv = h ? O.saved2 : O.saved;
+        d.use_mask = slope && (h ? O.smask2 : O.smask) != nullptr;     // sign bits (staged by phase 1) instead of the saved activation
+        d.saved = (slope && sv && !d.use_mask) ? sv + off : nullptr;
+        d.acc = d.ok && (h ? (m >= O.acc_lo2 && m < O.acc_hi2) : (m >= O.acc_lo && m < O.acc_hi));
+    } else {
+        d.ok = m < O.m_hi;
+        const long long off = (long long)b * O.bstride + (long long)m * O.rstride + col;
+        d.dst = O.base + off;
+        d.use_mask = slope && O.smask != nullptr;
+        d.saved = (slope && O.saved && !d.use_mask) ? O.saved + off : nullptr;
+        d.acc = d.ok && m >= O.acc_lo && m < O.acc_hi;
+    }
+#ifdef WUN_EXP_NOSLOPE          // timing experiment only (wrong gradients): what the slope read-back of the dgrad epilogue costs
+    d.saved = nullptr; d.use_mask = false;
+#endif
+    return d;
+}
 __device__ __forceinline__ void epi_write_rows_simple(const float* __restrict__ stage, int SW, int r0, int lane, int Q, int m0,
-                                                      const OutView& O, long long tile_off, bool slope) {
+                                                      const OutView& O, int b, int col0, bool slope) {
     for (int it = lane; it < 32 * Q; it += 32) {
         const int rl = it / Q, q = it - rl * Q;
-        const int m = m0 + rl;
-        if (m >= O.m_hi) continue;
-        const long long roff = tile_off + (long long)m * O.rstride;
+        const EpiDst d = epi_dst<true>(O, b, m0 + rl, col0 + 4 * q, slope);
+        if (!d.ok) continue;
         float4 o = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
-        if (slope) {
-            const float4 sv = __ldg(reinterpret_cast<const float4*>(O.saved + roff) + q);
+        if (d.saved) {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(d.saved));
             o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
             o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
         }
-        float4* dst = reinterpret_cast<float4*>(O.base + roff) + q;
-        if (m >= O.acc_lo && m < O.acc_hi) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        float4* dst = reinterpret_cast<float4*>(d.dst);
+        if (d.acc) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
         *dst = o;
     }
 }
+// mstage: the sign-mask bytes phase 1 fetched for the staged block, 16 per row (one per 8 columns) - the slope of a quad is 4 bits
+// of shared memory instead of a dependent 16-byte global read-back (launch.h OutView::smask).
 __device__ __forceinline__ void epi_write_rows_vec(const float* __restrict__ stage, int SW, int r0, int lane, int Q, int m0,
-                                                   const OutView& O, long long tile_off, bool slope) {
+                                                   const OutView& O, int b, int col0, bool slope, const uint8_t* __restrict__ mstage) {
     const int nit = 32 * Q;
     for (int it0 = lane; it0 < nit; it0 += 32 * kEpiBatch) {
         float4 o[kEpiBatch], sv[kEpiBatch], old[kEpiBatch];
-        float4* dst[kEpiBatch];
-        bool ok[kEpiBatch], acc[kEpiBatch];
+        EpiDst d[kEpiBatch];
 #pragma unroll
         for (int u = 0; u < kEpiBatch; ++u) {
             const int it = it0 + 32 * u;
             const int rl = it / Q, q = it - rl * Q;
-            const int m = m0 + rl;
-            ok[u] = it < nit && m < O.m_hi;
-            acc[u] = ok[u] && m >= O.acc_lo && m < O.acc_hi;
-            const long long roff = tile_off + (long long)m * O.rstride;
-            dst[u] = reinterpret_cast<float4*>(O.base + roff) + q;
-            if (ok[u]) {
+            d[u] = epi_dst<true>(O, b, m0 + rl, col0 + 4 * q, slope);
+            d[u].ok = d[u].ok && it < nit;
+            if (d[u].ok) {
                 o[u] = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
-                if (slope) sv[u] = __ldg(reinterpret_cast<const float4*>(O.saved + roff) + q);
-                if (acc[u]) old[u] = *dst[u];
+                if (d[u].saved) sv[u] = __ldg(reinterpret_cast<const float4*>(d[u].saved));
+                if (d[u].acc) old[u] = *reinterpret_cast<const float4*>(d[u].dst);
             }
         }
 #pragma unroll
         for (int u = 0; u < kEpiBatch; ++u) {
-            if (!ok[u]) continue;
+            if (!d[u].ok) continue;
             float4 v = o[u];
-            if (slope) {
+            if (d[u].use_mask) {
+                const int it = it0 + 32 * u;
+                const int rl = it / Q, q = it - rl * Q;
+                const unsigned bits = (unsigned)mstage[(r0 + rl) * 16 + (q >> 1)] >> ((q & 1) * 4);
+                v.x *= (bits & 1u) ? 1.f : 0.2f; v.y *= (bits & 2u) ? 1.f : 0.2f;
+                v.z *= (bits & 4u) ? 1.f : 0.2f; v.w *= (bits & 8u) ? 1.f : 0.2f;
+            } else if (d[u].saved) {
                 v.x *= (sv[u].x > 0.f) ? 1.f : 0.2f; v.y *= (sv[u].y > 0.f) ? 1.f : 0.2f;
                 v.z *= (sv[u].z > 0.f) ? 1.f : 0.2f; v.w *= (sv[u].w > 0.f) ? 1.f : 0.2f;
             }
-            if (acc[u]) { v.x += old[u].x; v.y += old[u].y; v.z += old[u].z; v.w += old[u].w; }
-            *dst[u] = v;
+            if (d[u].acc) { v.x += old[u].x; v.y += old[u].y; v.z += old[u].z; v.w += old[u].w; }
+            *reinterpret_cast<float4*>(d[u].dst) = v;
         }
+    }
+}
+
+// Forward epilogue, thread = accumulator row: sign bits of the 16 activations v[] it is about to stage (launch columns
+// [col0, col0 + 16) of row m), one byte per 8 channels, into the tensor's sign mask (launch.h OutView::mask).
+__device__ __forceinline__ void epi_store_sign_bits(const OutView& O, int pairC, int N, int b, int m, int col0, const float* v) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int col = col0 + 8 * g;
+        if (col >= N) continue;
+        unsigned bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bits |= (v[8 * g + j] > 0.f) ? (1u << j) : 0u;
+        const int h = (pairC > 0 && col >= pairC) ? 1 : 0;
+        uint8_t* mk = h ? O.mask2 : O.mask;
+        const bool ok = (pairC > 0) ? (m >= O.lo_h[h] && m < O.hi_h[h]) : (m < O.m_hi);
+        if (!ok || !mk) continue;
+        const long long off = h ? ((long long)b * O.bstride2 + (long long)m * O.rstride2 + (col - pairC))
+                                : ((long long)b * O.bstride + (long long)m * O.rstride + col);
+        mk[off >> 3] = (uint8_t)bits;
+    }
+}
+
+// dgrad epilogue, thread = accumulator row: request the sign-mask bytes of its row for the launch columns [col0, col0 + cw)
+// (cw <= 128: up to 16 independent byte loads in flight per thread, consumed after the accumulator read-out); rows / halves
+// without a mask give 0.
+__device__ __forceinline__ void epi_fetch_sign_bytes(const OutView& O, int pairC, int N, int b, int m, int col0, int cw, uint32_t* mw) {
+    mw[0] = mw[1] = mw[2] = mw[3] = 0u;
+    if (!O.smask && !(pairC > 0 && O.smask2)) return;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        const int col = col0 + 8 * g;
+        if (8 * g >= cw || col >= N) continue;
+        const int h = (pairC > 0 && col >= pairC) ? 1 : 0;
+        const uint8_t* sm = h ? O.smask2 : O.smask;
+        const bool ok = (pairC > 0) ? (m >= O.lo_h[h] && m < O.hi_h[h]) : (m < O.m_hi);
+        if (!ok || !sm) continue;
+        const long long off = h ? ((long long)b * O.bstride2 + (long long)m * O.rstride2 + (col - pairC))
+                                : ((long long)b * O.bstride + (long long)m * O.rstride + col);
+        mw[g >> 2] |= (uint32_t)__ldg(sm + (off >> 3)) << (8 * (g & 3));
     }
 }
 
@@ -386,9 +462,10 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
               ACC_FULL = 2 * kSlabMax + 2 * kBStagesMax;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
     float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // NPAD floats: this split's bias
+    uint8_t* mstage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + NPAD) + 15) & ~(uintptr_t)15);   // 128 rows x 16 sign-mask bytes (dgrad epilogue)
     for (int i = tid; i < NPAD; i += blockDim.x) {
         const int n = split * NPAD + i;
-        bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f;
+        bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + ((L.pairC > 0 && n >= L.pairC) ? n - L.pairC : n)) : 0.f;
     }
 
     if (tid == 0) {
@@ -478,6 +555,8 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
             for (int c0 = 0; c0 < NPAD; c0 += CW) {
                 if (n0 + c0 >= L.N) break;
                 const int cw = min(CW, NPAD - c0);
+                uint32_t mw[4];
+                if (DG && L.epilogue == EPI_SLOPE) epi_fetch_sign_bytes(K.out, L.pairC, L.N, b, m_base + mt * 128 + warp * 32 + lane, n0 + c0, cw, mw);
                 // phase 1: thread = accumulator row (TMEM lane)
                 for (int cb = 0; cb < cw; cb += 16) {
                     __syncwarp();
@@ -501,11 +580,13 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                             const float y = v[j] + bias_s[c0 + cb + j];
                             v[j] = fmaxf(0.2f * y, y);
                         }
+                        if (!DG && K.out.mask) epi_store_sign_bits(K.out, L.pairC, L.N, b, m_base + mt * 128 + warp * 32 + lane, n0 + c0 + cb, v);
                     }
                     float4* dst = reinterpret_cast<float4*>(stage + (size_t)(warp * 32 + lane) * SW + cb);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
+                if (DG && L.epilogue == EPI_SLOPE) *reinterpret_cast<uint4*>(mstage + (warp * 32 + lane) * 16) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                 __syncwarp();
                 // phase 2: each warp writes out the 32 rows it staged itself (no block barrier needed); lanes run over
                 // (row, 4-column quad) pairs so that narrow layers (N = 24..48) still use every lane and a whole warp
@@ -514,11 +595,11 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 const long long tile_off = (long long)b * K.out.bstride + n0 + c0;
                 const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
-                if (vec) {
-                    if (DG) epi_write_rows_vec(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, tile_off,
-                                               L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
-                    else epi_write_rows_simple(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, tile_off,
-                                               L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
+                if (vec) {      // (pair-merged classes always take this path: the planner checks both views)
+                    if (DG) epi_write_rows_vec(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, b, n0 + c0,
+                                               L.epilogue == EPI_SLOPE, mstage);
+                    else epi_write_rows_simple(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, b, n0 + c0,
+                                               L.epilogue == EPI_SLOPE);
                 } else {
                     for (int it = lane; it < 32 * ncols; it += 32) {
                         const int rl = it / ncols, j = it - rl * ncols;
@@ -671,8 +752,13 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaLaunch& L, int t) {
 
 // PT converter teams (4 warps each): warps [0, 4PT) convert, warp 4PT issues MMAs, 4PT+1 streams weights, 4PT+2..4PT+5
 // run the epilogue (4PT+2 = 2 mod 4, so `warp & 3` covers the four TMEM lane quarters).  PT+1 slab stages.
-template <int PT, bool DG>
-__global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+// NCOL = number of output-conv columns (nconv * C) of the fused output layer, 0 = plain conv.  The fused epilogue is compiled per
+// width: generic code predicated up to 8 columns was 6000 instructions (95 KB) that the four epilogue warps streamed through the
+// instruction cache once per row tile - 70k cycles per 128 rows, measured.
+template <int PT, bool DG, int NCOL>
+__device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_tiles, const OutputFuse* FP) {
+    constexpr bool OUTL = NCOL > 0;
+    constexpr int NC = OUTL ? NCOL : 1;          // array extent of the per-column registers
     constexpr int kSlabStages = PT + 1;
     constexpr int kMmaWarp = 4 * PT, kLoadWarp = 4 * PT + 1, kEpiWarp0 = 4 * PT + 2;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -694,7 +780,26 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
               ACC_FULL = 2 * kSlabStages + 2 * kBStagesMax, ACC_EMPTY = ACC_FULL + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_EMPTY + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // nsplit * NPAD floats
-    for (int i = tid; i < NPAD * L.nsplit; i += blockDim.x) bias_s[i] = (L.bias && i < L.N) ? __ldg(L.bias + i) : 0.f;
+    uint8_t* mstage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + NPAD * L.nsplit) + 15) & ~(uintptr_t)15);   // 128 rows x 16 sign-mask bytes (dgrad epilogue)
+    for (int i = tid; i < NPAD * L.nsplit; i += blockDim.x)
+        bias_s[i] = (L.bias && i < L.N) ? __ldg(L.bias + ((L.pairC > 0 && i >= L.pairC) ? i - L.pairC : i)) : 0.f;
+    // fused output layer (OUTL): [wout (C+F) x ncol | bout ncol | dpre 128 rows x 2 halves x ncol | wacc 4 warps x (C+F+1) x ncol]
+    float *wout_s = nullptr, *bout_s = nullptr, *dpre_s = nullptr, *wacc_s = nullptr;
+    int o_ncol = 0, o_cin = 0, o_nw = 0;
+    if (OUTL) {
+        const OutputLaunch& O = FP->O;
+        o_ncol = O.nconv * O.C; o_cin = O.C + O.F; o_nw = (o_cin + 1) * o_ncol;
+        wout_s = reinterpret_cast<float*>(mstage + 2048);         // (behind the 2 KB sign-mask stage)
+        bout_s = wout_s + o_cin * o_ncol;
+        dpre_s = bout_s + ((o_ncol + 3) & ~3);
+        wacc_s = dpre_s + 128 * 2 * o_ncol;
+        for (int i = tid; i < o_cin * o_ncol; i += blockDim.x) {       // kernel [ofs = 1][C+F][C] per output conv (OutputLayer.py:8)
+            const int cin = i / o_ncol, q = i - cin * o_ncol, conv = q / O.C, oc = q - conv * O.C;
+            wout_s[i] = __ldg(O.params + O.w_off[conv] + (long long)cin * O.C + oc);
+        }
+        for (int i = tid; i < o_ncol; i += blockDim.x) bout_s[i] = __ldg(O.params + O.b_off[i / O.C] + (i % O.C));
+        for (int i = tid; i < 4 * o_nw; i += blockDim.x) wacc_s[i] = 0.f;
+    }
     if (tid == 0) {
         for (int i = 0; i < kSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
         for (int i = 0; i < kBStagesMax; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
@@ -854,6 +959,7 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
         // ===================== epilogue warps: TMEM lane quarter = warp & 3 =====================
         const int q4 = warp & 3;
         int k = 0;
+        float o_lsum = 0.f;                                    // OUTL: this thread's share of the squared error
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
             const TileCoord tc = decode_tile(L, t);
             const UmmaClass& K = L.cls[tc.cls];
@@ -865,10 +971,52 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
             for (int g = 0; g < K.ngroups; ++g) any_group = any_group || !group_is_empty(L, K.groups[g], tc.m_base);
             const int c0_last = min((NPAD - 1) / CW, (L.N - n0 - 1) / CW) * CW;      // last column block that holds real channels
             for (int mt = 0; mt < L.MT; ++mt) {
+                float o_pre0[NC], o_pre1[NC];     // OUTL: output-conv pre-activations of this thread's row (two frames when pair-merged)
+#pragma unroll
+                for (int q = 0; q < NC; ++q) { o_pre0[q] = 0.f; o_pre1[q] = 0.f; }
+                // OUTL: everything the row's frames need from global memory (mix at the feature / output crop, targets incl. the
+                // difference source's) is requested HERE, so that the latency hides under the accumulator read-out below
+                float o_x0[2] = {0.f, 0.f}, o_x1[2] = {0.f, 0.f}, o_mo0[2] = {0.f, 0.f}, o_mo1[2] = {0.f, 0.f};
+                float o_tg0[NC + 2], o_tg1[NC + 2];
+                bool o_ok0 = false, o_ok1 = false;
+                if (OUTL) {
+                    const OutputLaunch& O = FP->O;
+                    const bool o_two = O.C == 2;                  // (C is 1 or 2: no runtime divisions in the unrolled code)
+                    const int m = tc.m_base + mt * 128 + q4 * 32 + lane;
+                    const long long src_stride = (long long)O.batch * O.T_out * O.C;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int tt = FP->t0[tc.cls] + FP->t_step * m + hh;
+                        bool ok = (L.pairC > 0) ? (m >= K.out.lo_h[hh] && m < K.out.hi_h[hh]) : (hh == 0 && m < K.out.m_hi);
+                        ok = ok && tt < O.T_out;
+                        float* xm = hh ? o_x1 : o_x0;
+                        float* mo = hh ? o_mo1 : o_mo0;
+                        float* tg = hh ? o_tg1 : o_tg0;
+                        if (hh) o_ok1 = ok; else o_ok0 = ok;
+                        if (ok) {
+                            const float* mixrow = O.mix + ((long long)tc.b * O.T_in + O.crop_feat + tt) * O.C;
+                            const float* mixout = O.mix + ((long long)tc.b * O.T_in + O.crop_out + tt) * O.C;
+                            xm[0] = __ldg(mixrow); if (O.C > 1) xm[1] = __ldg(mixrow + 1);
+                            if (O.output_type == 1) { mo[0] = __ldg(mixout); if (O.C > 1) mo[1] = __ldg(mixout + 1); }
+                            if (O.targets) {
+                                const long long frame = ((long long)tc.b * O.T_out + tt) * O.C;
+#pragma unroll
+                                for (int q = 0; q < NC; ++q)
+                                    tg[q] = __ldg(O.targets + (long long)(o_two ? (q >> 1) : q) * src_stride + frame + (o_two ? (q & 1) : 0));
+                                if (O.output_type == 1) {
+                                    tg[NC] = __ldg(O.targets + (long long)O.nconv * src_stride + frame);
+                                    if (O.C > 1) tg[NC + 1] = __ldg(O.targets + (long long)O.nconv * src_stride + frame + 1);
+                                }
+                            }
+                        }
+                    }
+                }
                 for (int c0 = 0; c0 < NPAD; c0 += CW) {
                     const bool last_block = (mt == L.MT - 1) && (c0 == c0_last);
                     if (n0 + c0 < L.N) {
                         const int cw = min(CW, NPAD - c0);
+                        uint32_t mw[4];
+                        if (DG && L.epilogue == EPI_SLOPE) epi_fetch_sign_bytes(K.out, L.pairC, L.N, tc.b, tc.m_base + mt * 128 + q4 * 32 + lane, n0 + c0, cw, mw);
                         for (int cb = 0; cb < cw; cb += 16) {
                             __syncwarp();
                             float v[16];
@@ -889,15 +1037,106 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                                     const float y = v[j] + bias_s[n0 + c0 + cb + j];
                                     v[j] = fmaxf(0.2f * y, y);
                                 }
+                                if (!DG && K.out.mask) epi_store_sign_bits(K.out, L.pairC, L.N, tc.b, tc.m_base + mt * 128 + q4 * 32 + lane, n0 + c0 + cb, v);
                             }
                             float4* dst = reinterpret_cast<float4*>(stage + (size_t)(q4 * 32 + lane) * SW + cb);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            if (OUTL) {                      // 1x1 output convs: feature part of [crop(mix) || features] . W
+                                const int o_C = FP->O.C;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int col = c0 + cb + j;              // (nsplit == 1: n0 == 0)
+                                    if (col < L.N) {
+                                        const bool h1 = L.pairC > 0 && col >= L.pairC;       // uniform over the warp
+                                        const float* w = wout_s + (o_C + (h1 ? col - L.pairC : col)) * o_ncol;
+                                        if (h1) {
+#pragma unroll
+                                            for (int q = 0; q < NC; ++q) o_pre1[q] = fmaf(v[j], w[q], o_pre1[q]);
+                                        } else {
+#pragma unroll
+                                            for (int q = 0; q < NC; ++q) o_pre0[q] = fmaf(v[j], w[q], o_pre0[q]);
+                                        }
+                                    }
+                                }
+                            }
                         }
+                        if (DG && L.epilogue == EPI_SLOPE) *reinterpret_cast<uint4*>(mstage + (q4 * 32 + lane) * 16) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                     }
                     if (last_block) {                       // every tcgen05.ld of this buffer has completed: hand it back
                         tc_fence_before();
                         mbar_arrive(BAR(ACC_EMPTY + buf));
+                    }
+                    float o_g0[NC], o_g1[NC];     // OUTL: dL/dpre of the row's frames
+                    if (OUTL) {
+                        const OutputLaunch& O = FP->O;
+                        const bool o_two = O.C == 2;
+                        const int r = q4 * 32 + lane, m = tc.m_base + mt * 128 + r;
+                        const long long src_stride = (long long)O.batch * O.T_out * O.C;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float* pre = hh ? o_pre1 : o_pre0;
+                            float* g = hh ? o_g1 : o_g0;
+                            const float* xm = hh ? o_x1 : o_x0;
+                            const float* mo = hh ? o_mo1 : o_mo0;
+                            const float* tg = hh ? o_tg1 : o_tg0;
+#pragma unroll
+                            for (int q = 0; q < NC; ++q) g[q] = 0.f;
+                            const int tt = FP->t0[tc.cls] + FP->t_step * m + hh;
+                            if (hh ? o_ok1 : o_ok0) {
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    if (c < O.C) {
+#pragma unroll
+                                        for (int q = 0; q < NC; ++q) pre[q] = fmaf(xm[c], wout_s[c * o_ncol + q], pre[q]);
+                                    }
+                                }
+                                float est[NC];
+#pragma unroll
+                                for (int q = 0; q < NC; ++q) {
+                                    float e = pre[q] + bout_s[q];
+                                    if (O.activation == 0) e = tanhf(e);                              // UnetAudioSeparator.py:131-136
+                                    else if (!O.training) e = fminf(fmaxf(e, -1.f), 1.f);             // AudioClip, Utils.py:89-92
+                                    est[q] = e;
+                                }
+                                const long long frame = ((long long)tc.b * O.T_out + tt) * O.C;
+                                float g_last[2] = {0.f, 0.f};
+                                if (O.output_type == 1) {                                             // OutputLayer.py:17-22
+#pragma unroll
+                                    for (int oc = 0; oc < 2; ++oc) {
+                                        if (oc >= O.C) continue;
+                                        float sacc = 0.f;
+#pragma unroll
+                                        for (int q = 0; q < NC; ++q) if ((o_two ? (q & 1) : 0) == oc) sacc += est[q];
+                                        float last = mo[oc] - sacc;
+                                        if (!O.training) last = fminf(fmaxf(last, -1.f), 1.f);
+                                        if (O.outputs) O.outputs[(long long)O.nconv * src_stride + frame + oc] = last;
+                                        if (O.targets) {
+                                            const float e = last - tg[NC + oc];
+                                            o_lsum = fmaf(e, e, o_lsum);
+                                            g_last[oc] = 2.f * e * O.inv_count;
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int q = 0; q < NC; ++q) {
+                                    const int conv = o_two ? (q >> 1) : q, oc = o_two ? (q & 1) : 0;
+                                    if (O.outputs) O.outputs[(long long)conv * src_stride + frame + oc] = est[q];
+                                    if (O.targets) {
+                                        const float e = est[q] - tg[q];
+                                        o_lsum = fmaf(e, e, o_lsum);
+                                        float gg = 2.f * e * O.inv_count - ((oc == 0) ? g_last[0] : g_last[1]);   // Training.py:62-63 / OutputLayer.py:20
+                                        if (O.activation == 0) gg *= (1.f - est[q] * est[q]);         // tanh'
+                                        if (O.dpre) O.dpre[((long long)tc.b * O.T_out + tt) * o_ncol + q] = gg;
+                                        g[q] = gg;
+                                    }
+                                }
+                            }
+                            if (FP->gfeat) {
+#pragma unroll
+                                for (int q = 0; q < NC; ++q) dpre_s[(r * 2 + hh) * o_ncol + q] = g[q];
+                            }
+                        }
                     }
                     if (n0 + c0 < L.N) {
                         const int cw = min(CW, NPAD - c0);
@@ -907,10 +1146,10 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                         const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                          ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
                         if (vec) {
-                            if (DG) epi_write_rows_vec(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tile_off,
-                                                       L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
-                            else epi_write_rows_simple(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tile_off,
-                                                       L.epilogue == EPI_SLOPE && K.out.saved != nullptr);
+                            if (DG) epi_write_rows_vec(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tc.b, n0 + c0,
+                                                       L.epilogue == EPI_SLOPE, mstage);
+                            else epi_write_rows_simple(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tc.b, n0 + c0,
+                                                       L.epilogue == EPI_SLOPE);
                         } else {
                             for (int it = lane; it < 32 * ncols; it += 32) {
                                 const int rl = it / ncols, j = it - rl * ncols;
@@ -926,7 +1165,68 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
                             }
                         }
                         __syncwarp();
+                        if (OUTL && FP->gfeat) {
+                            const OutputLaunch& O = FP->O;
+                            // (a) gradient w.r.t. the features' pre-activation: slope(feature) * dpre . W^T, written with the feature
+                            //     tensor's geometry into its gradient twin (lanes over (row, quad) like the feature store above)
+                            const int Q = ncols >> 2;
+                            for (int it = lane; it < 32 * Q; it += 32) {
+                                const int rl = it / Q, qd = it - rl * Q, col = 4 * qd;
+                                const EpiDst d = epi_dst<true>(K.out, tc.b, tc.m_base + mt * 128 + q4 * 32 + rl, col, false);
+                                if (!d.ok) continue;
+                                const bool h1 = L.pairC > 0 && col >= L.pairC;
+                                const float4 f = *reinterpret_cast<const float4*>(stage + (size_t)(q4 * 32 + rl) * SW + col);
+                                const float* dp = dpre_s + ((q4 * 32 + rl) * 2 + (h1 ? 1 : 0)) * o_ncol;
+                                const float* w = wout_s + (O.C + (h1 ? col - L.pairC : col)) * o_ncol;
+                                float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+                                #pragma unroll
+                                for (int q = 0; q < NC; ++q) {
+                                    const float dq = dp[q];
+                                    sx = fmaf(dq, w[q], sx); sy = fmaf(dq, w[o_ncol + q], sy);
+                                    sz = fmaf(dq, w[2 * o_ncol + q], sz); sw = fmaf(dq, w[3 * o_ncol + q], sw);
+                                }
+                                float4 go;
+                                go.x = sx * ((f.x > 0.f) ? 1.f : 0.2f); go.y = sy * ((f.y > 0.f) ? 1.f : 0.2f);
+                                go.z = sz * ((f.z > 0.f) ? 1.f : 0.2f); go.w = sw * ((f.w > 0.f) ? 1.f : 0.2f);
+                                *reinterpret_cast<float4*>(FP->gfeat + (d.dst - O.feat)) = go;
+                            }
+                            // (b) output-conv weight / bias gradients: thread = its own row again, warp-reduced, summed per warp in shared memory
+                            const int r = q4 * 32 + lane;
+                            if (FP->grads)
+                            for (int cin = 0; cin <= o_cin; ++cin) {
+                                float x0, x1;
+                                if (cin < O.C) { x0 = (cin == 0) ? o_x0[0] : o_x0[1]; x1 = (cin == 0) ? o_x1[0] : o_x1[1]; }
+                                else if (cin < o_cin) {
+                                    x0 = stage[(size_t)r * SW + (cin - O.C)];
+                                    x1 = (L.pairC > 0) ? stage[(size_t)r * SW + L.pairC + (cin - O.C)] : 0.f;
+                                } else { x0 = 1.f; x1 = 1.f; }
+#pragma unroll
+                                for (int q = 0; q < NC; ++q) {
+                                    float val = fmaf(x0, o_g0[q], x1 * o_g1[q]);
+#pragma unroll
+                                    for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+                                    if (lane == 0) wacc_s[q4 * o_nw + cin * o_ncol + q] += val;
+                                }
+                            }
+                            __syncwarp();
+                        }
                     }
+                }
+            }
+        }
+        if (OUTL) {
+            const OutputLaunch& O = FP->O;
+            if (O.targets && O.loss) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) o_lsum += __shfl_xor_sync(0xffffffffu, o_lsum, off);
+                if (lane == 0) atomicAdd(O.loss, o_lsum * O.inv_count);
+            }
+            if (FP->grads) {
+                __syncwarp();
+                for (int i = lane; i < o_nw; i += 32) {
+                    const int cin = i / o_ncol, q = i - cin * o_ncol, conv = q / O.C, oc = q - conv * O.C;
+                    const long long off = (cin < o_cin) ? O.w_off[conv] + (long long)cin * O.C + oc : O.b_off[conv] + oc;
+                    atomicAdd(FP->grads + off, wacc_s[q4 * o_nw + i] * FP->grad_scale);
                 }
             }
         }
@@ -939,6 +1239,17 @@ __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(
     }
 }
 
+template <int PT, bool DG>
+__global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+    persistent_body<PT, DG, 0>(L, total_tiles, nullptr);
+}
+// the last up block's forward conv with the output layer, the loss and the output layer's backward in its epilogue (OutputFuse);
+// NCOL = nconv * C of the output convs
+template <int NCOL>
+__global__ void __launch_bounds__(3 * 128 + 192, 1) plane_conv_umma_persistent_out(const __grid_constant__ UmmaLaunch L, int total_tiles,
+                                                                                 const __grid_constant__ OutputFuse F) {
+    persistent_body<3, false, NCOL>(L, total_tiles, &F);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Batch-folded cluster split-K variant for the deep layers (down7 ... up7 at training batch sizes, everything at small
@@ -1017,7 +1328,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
     float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);
     for (int i = tid; i < NPAD; i += blockDim.x) {
         const int n = split * NPAD + i;
-        bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f;
+        bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + ((L.pairC > 0 && n >= L.pairC) ? n - L.pairC : n)) : 0.f;
     }
     if (tid == 0) {
         for (int i = 0; i < kFoldSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
@@ -1329,14 +1640,14 @@ static size_t umma_pers_smem_bytes(const UmmaLaunch& L) {
     const size_t CW = (L.NPAD < 128) ? L.NPAD : 128;
     const size_t kSlabStages = (L.nteams == 3) ? 4 : 3;
     return (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD + 128u * (CW + 4) * 4 +
-           (2 * kSlabStages + 2 * kBStagesMax + 4) * 8 + 32 + 4 * (size_t)L.NPAD * L.nsplit;
+           (2 * kSlabStages + 2 * kBStagesMax + 4) * 8 + 32 + 4 * (size_t)L.NPAD * L.nsplit + 16 + 2048 + 16;
 }
 
 size_t umma_smem_bytes(const UmmaLaunch& L) {
     const size_t nslab = (L.nteams == 4) ? 6 : 3;
     const size_t pipe = nslab * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
     const size_t epi = 128u * ((size_t)(L.NPAD < 128 ? L.NPAD : 128) + 4u) * 4u;
-    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * 6 + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD;
+    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * 6 + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD + 2048 + 16;
 }
 
 template <typename KernelT>
@@ -1344,9 +1655,34 @@ static cudaError_t set_smem_limit(KernelT kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
+static size_t umma_outfuse_smem_bytes(const OutputLaunch& O) {
+    const size_t ncol = (size_t)O.nconv * O.C, cin = (size_t)O.C + O.F;
+    return 4 * (cin * ncol + ncol + 8 + 128 * 2 * ncol + 4 * (cin + 1) * ncol) + 64;
+}
+
+bool umma_output_fusable(const ConvLaunch& L, const UmmaChoice& ch, const OutputLaunch& O) {
+    if (!ch.persistent || ch.folded || ch.nsplit != 1 || ch.NPAD > 128 || ch.nteams != 3) return false;
+    { const int ncol = O.nconv * O.C; if (ncol != 1 && ncol != 2 && ncol != 4 && ncol != 6) return false; }     // instantiated widths
+    if (O.ofs != 1 || O.pad_left != 0 || O.Tf != O.T_out || O.C < 1 || O.C > 2 || O.nconv < 1 || O.nconv * O.C > kOutFuseMaxCols) return false;
+    if (L.N != (L.pairC > 0 ? 2 : 1) * O.F || L.N % 4 != 0 || L.epilogue != EPI_BIAS_LRELU) return false;
+    for (int q = 0; q < L.ncls; ++q) {
+        const OutView& V = L.cls[q];
+        if (V.rstride % 4 || V.bstride % 4 || (reinterpret_cast<uintptr_t>(V.base) & 15)) return false;
+    }
+    UmmaLaunch U;
+    memset(&U, 0, sizeof(U));
+    U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.rows_alloc = ch.rows_alloc; U.TB = ch.TB; U.nbs = ch.nbs; U.nteams = ch.nteams;
+    return umma_pers_smem_bytes(U) + umma_outfuse_smem_bytes(O) <= 220 * 1024;
+}
+
+cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream, const OutputFuse* fuse) {
     static bool attr_set = false;
     if (!attr_set) {
+        cudaError_t e0 = set_smem_limit(plane_conv_umma_persistent_out<1>, 220 * 1024);
+        if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<2>, 220 * 1024);
+        if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<4>, 220 * 1024);
+        if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<6>, 220 * 1024);
+        if (e0 != cudaSuccess) return e0;
         cudaError_t e = set_smem_limit(plane_conv_umma_kernel<2, false>, 200 * 1024);
         if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<2, true>, 200 * 1024);
         if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<4, false>, 220 * 1024);
@@ -1369,9 +1705,22 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream) {
     total *= L.nsplit;
     if (max_tiles <= 0) return cudaSuccess;
     const bool dg = L.epilogue == EPI_SLOPE;      // dgrad: batched read-back epilogue (separate instantiation)
+    if (fuse && !(L.persistent && !dg)) return cudaErrorInvalidValue;
     if (L.persistent) {
         const int grid = total < 148 ? total : 148;
         const size_t smem = umma_pers_smem_bytes(L);
+        if (fuse) {
+            const size_t smem_o = smem + umma_outfuse_smem_bytes(fuse->O);
+            if (L.nteams != 3) return cudaErrorInvalidValue;
+            switch (fuse->O.nconv * fuse->O.C) {
+                case 1: plane_conv_umma_persistent_out<1><<<grid, 3 * 128 + 192, smem_o, stream>>>(L, total, *fuse); break;
+                case 2: plane_conv_umma_persistent_out<2><<<grid, 3 * 128 + 192, smem_o, stream>>>(L, total, *fuse); break;
+                case 4: plane_conv_umma_persistent_out<4><<<grid, 3 * 128 + 192, smem_o, stream>>>(L, total, *fuse); break;
+                case 6: plane_conv_umma_persistent_out<6><<<grid, 3 * 128 + 192, smem_o, stream>>>(L, total, *fuse); break;
+                default: return cudaErrorInvalidValue;
+            }
+            return cudaGetLastError();
+        }
         if (L.nteams == 3) {
             if (dg) plane_conv_umma_persistent<3, true><<<grid, 3 * 128 + 192, smem, stream>>>(L, total);
             else plane_conv_umma_persistent<3, false><<<grid, 3 * 128 + 192, smem, stream>>>(L, total);
@@ -2061,10 +2410,15 @@ __global__ void __launch_bounds__(256) umma_pack_kernel(const __grid_constant__ 
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) w[kk] = 0.f;
         if (nn < PL.N) {
-            const float* src = PL.W + (long long)PL.woff[term] + (long long)k0 * PL.w_sk + (long long)nn * PL.w_sn;
+            // pair-merged launch: columns [pairC, 2*pairC) are the second class's weights (its own tap of the same row shift)
+            const bool h2 = PL.pairC > 0 && nn >= PL.pairC;
+            const int wo = h2 ? PL.woff2[term] : PL.woff[term];
+            if (wo >= 0 || PL.pairC == 0) {
+                const float* src = PL.W + (long long)wo + (long long)k0 * PL.w_sk + (long long)(h2 ? nn - PL.pairC : nn) * PL.w_sn;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-                if (k0 + kk < J.g_C[g]) w[kk] = __ldg(src + (long long)kk * PL.w_sk);
+                for (int kk = 0; kk < 8; ++kk)
+                    if (k0 + kk < J.g_C[g]) w[kk] = __ldg(src + (long long)kk * PL.w_sk);
+            }
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -2098,6 +2452,16 @@ cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream) {
 bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
     memset(ch, 0, sizeof(*ch));
     if (L.N < 16 || L.ncls < 1 || L.ncls > kMaxClasses) return false;
+    if (L.pairC > 0) {       // pair-merged classes: both views must satisfy what the vectorised epilogue assumes
+        if (L.pairC % 4 != 0 || L.N != 2 * L.pairC) return false;
+        for (int q = 0; q < L.ncls; ++q) {
+            const OutView& O = L.cls[q];
+            if (O.pairC != L.pairC) return false;
+            if (O.rstride % 4 || O.bstride % 4 || O.rstride2 % 4 || O.bstride2 % 4) return false;
+            if ((reinterpret_cast<uintptr_t>(O.base) & 15) || (reinterpret_cast<uintptr_t>(O.base2) & 15) ||
+                (reinterpret_cast<uintptr_t>(O.saved) & 15) || (reinterpret_cast<uintptr_t>(O.saved2) & 15)) return false;
+        }
+    }
     for (int p = 0; p < L.nplanes; ++p) {
         const PlaneView& P = L.planes[p];
         if (P.C % 8 != 0 || P.C < 8) return false;
@@ -2146,7 +2510,7 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
         // WUN_FOLD: 0 = never, 1 (default) = launches the unfolded tiling would run on <= 148 CTAs, 2 = whenever it fits.
         const char* env = getenv("WUN_FOLD");
         const int mode = env ? atoi(env) : 1;
-        bool ok = mode != 0 && (L.N % 4 == 0);
+        bool ok = mode != 0 && (L.N % 4 == 0) && L.pairC == 0;     // (the folded kernel's epilogue has no pair-merged form)
         long long old_ctas = 0;
         int jmin = 1 << 30;
         for (int q = 0; q < L.ncls; ++q) {
@@ -2272,7 +2636,7 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
             }
             // one CTA per SM: a deeper weight ring fits next to the slab stages and the epilogue staging tile
             const long long cw = (ch->NPAD < 128) ? ch->NPAD : 128;
-            long long left = 218 * 1024 - (long long)(ch->nteams + 1) * 64 * ch->rows_alloc - 128 * (cw + 4) * 4 - 1024 - 4LL * ch->NPAD * ch->nsplit;
+            long long left = 218 * 1024 - (long long)(ch->nteams + 1) * 64 * ch->rows_alloc - 128 * (cw + 4) * 4 - 1024 - 2080 - 4LL * ch->NPAD * ch->nsplit;
             if (left > 98304) left = 98304;
             ch->nbs = (int)(left / (TB * blk));
             if (ch->nbs > kBStagesMax) ch->nbs = kBStagesMax;
@@ -2324,7 +2688,8 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     PL.W = L.W; PL.w_sk = L.w_sk; PL.w_sn = L.w_sn; PL.N = L.N; PL.NPAD = ch.NPAD;
     int nterm_total = 0;
     for (int q = 0; q < L.ncls; ++q) nterm_total = max(nterm_total, L.cls[q].term_end);
-    for (int t = 0; t < nterm_total; ++t) { U.d[t] = L.terms[t].d; PL.woff[t] = L.terms[t].woff; }
+    for (int t = 0; t < nterm_total; ++t) { U.d[t] = L.terms[t].d; PL.woff[t] = L.terms[t].woff; PL.woff2[t] = L.terms[t].woff2; }
+    PL.pairC = L.pairC; U.pairC = L.pairC;
     uint8_t* cur = arena;
     for (int q = 0; q < L.ncls; ++q) {
         UmmaClass& K = U.cls[q];

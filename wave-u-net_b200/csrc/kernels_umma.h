@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernels.h"
 #include "launch.h"
 
 namespace wun {
@@ -46,6 +47,7 @@ struct UmmaLaunch {
     const float* bias;
     int epilogue;
     int batch;
+    int pairC;              // > 0: pair-merged classes (launch.h OutView::pairC); the bias repeats with this period
 };
 
 constexpr int kUmmaMaxPackJobs = kMaxClasses * kUmmaMaxSplit;
@@ -61,6 +63,8 @@ struct UmmaPackJob {        // one (class, split) weight pack
 struct UmmaPackLaunch {
     const float* W;
     int woff[kMaxTerms];
+    int woff2[kMaxTerms];   // pair-merged launches (pairC > 0): weight offset of columns [pairC, 2*pairC); -1 = zeros
+    int pairC;
     int w_sk, w_sn;
     int N, NPAD;
     int njobs;
@@ -146,11 +150,29 @@ constexpr int kWgOverreachG = 64, kWgOverreachP = 64 + 16;
 // fills the tiling fields (groups' P, G, taps and the common fields already set); false = not eligible
 bool umma_plan_wgrad(UmmaWgradLaunch* L);
 
+// Output layer fused into the epilogue of the last up block's forward conv (persistent kernel only; north_star "the per-source
+// tanh / difference OutputLayer is fused into the final conv").  The conv epilogue holds one feature row per thread: it applies the
+// 1x1 output convs over [crop(mix) || features] (OutputLayer.py:8,15), the activation, the difference source (:17-22) and the test-time
+// clip, writes the source estimates, and - when targets are given - the MSE loss (Training.py:50-63), dL/dpre of the output
+// convs, their weight / bias gradients and the gradient w.r.t. the features' pre-activation, so that output_fwd / output_dgrad /
+// output_wgrad launch nothing.
+constexpr int kOutFuseMaxCols = 8;    // nconv * C the fused epilogue supports (registers); wider heads use the separate kernels
+struct OutputFuse {
+    OutputLaunch O;
+    float* gfeat;           // training: dPre of the last up block (gradient twin of O.feat, same geometry) or null
+    float* grads;           // training: flat gradient buffer (O.w_off / O.b_off index it) or null
+    float grad_scale;
+    int t_step;             // output frame of (class q, row m, half h) = t0[q] + t_step * m + h
+    int t0[kMaxClasses];
+};
+// whether the conv launch `ch` plans for L can carry the output layer described by O
+bool umma_output_fusable(const ConvLaunch& L, const UmmaChoice& ch, const OutputLaunch& O);
+
 size_t umma_smem_bytes(const UmmaLaunch& L);
 // dynamic shared memory the kernel variant chosen in `ch` is launched with / of a planned wgrad launch (plan audit)
 size_t umma_choice_smem_bytes(const UmmaChoice& ch);
 size_t umma_wgrad_smem_bytes(const UmmaWgradLaunch& L);
-cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream);
+cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream, const OutputFuse* fuse = nullptr);
 cudaError_t launch_umma_pack(const UmmaPackLaunch& PL, cudaStream_t stream);
 // Decide whether / how a generic plane-convolution launch runs on tcgen05; false = not eligible (SIMT).
 bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* choice);

@@ -47,12 +47,31 @@ struct OutView {
     const float* saved;    // dgrad: forward activation with the same geometry (LeakyReLU slope) or null
     int acc_lo, acc_hi;    // rows in [acc_lo, acc_hi) accumulate into the destination (+=)
     int term_begin, term_end;
+    // Pair-merged class (pairC > 0; dgrad only): the launch computes N = 2*pairC columns per row m.  Columns [0, pairC) are
+    // the class above restricted to rows [lo_h[0], hi_h[0]); columns [pairC, 2*pairC) are a SECOND class with its own view,
+    // rows [lo_h[1], hi_h[1]) - e.g. the gradients of the even and the odd input rows of a down block (one tensor viewed as
+    // [B, rows/2, 2C]: base2 = base + C, same strides), or of the skip-even / skip-odd and copied / interpolated inputs of an
+    // up block.  Both classes read the same planes with the same row shifts, so every slab is staged (and every tap issued)
+    // once for both; m_lo / m_hi are the union of the two row ranges.
+    int pairC;
+    float* base2;
+    long long bstride2;
+    int rstride2;
+    const float* saved2;
+    int acc_lo2, acc_hi2;
+    int lo_h[2], hi_h[2];
+    // LeakyReLU sign masks (1 bit per element, bit (e & 7) of byte (e >> 3), e = element offset from `base` / `base2`):
+    //   mask / mask2   forward launches: the epilogue also stores the sign bits of what it writes (null = do not);
+    //   smask / smask2 dgrad launches: when non-null the slope is read from these bits instead of from `saved` / `saved2`.
+    uint8_t *mask, *mask2;
+    const uint8_t *smask, *smask2;
 };
 
 struct Term {
     int plane;             // index into planes[]
     int d;                 // row shift: reads plane row m + d
-    int woff;              // element offset of W[tap][coff][0]
+    int woff;              // element offset of W[tap][coff][0]; pair-merged classes: -1 = this half has no such tap (zeros)
+    int woff2;             // pair-merged classes: the same for columns [pairC, 2*pairC)
 };
 
 enum Epilogue : int { EPI_BIAS_LRELU = 0,   // y = leaky_relu(acc + bias)          (forward)
@@ -71,6 +90,7 @@ struct ConvLaunch {
     int epilogue;
     int batch;
     int max_rows;          // max over classes of (m_hi - m_lo)
+    int pairC;             // > 0: every class of this launch is pair-merged with this half width (N = 2*pairC)
 };
 
 // wgrad: dW[woff + c*w_sk + n*w_sn] += sum_{b, m in [m_lo,m_hi)} plane[b, m+d, c] * dpre[b, m, n]
