@@ -6,6 +6,8 @@ mkdir -p gpurun_out
 TAG=$1; shift
 echo "=== parity tests"
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+echo "=== warm-up bench (discarded: the first run on a fresh box is slower)"
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > /dev/null 2>&1
 i=0
 for cfg in "$@"; do
   echo "=== bench $cfg"

@@ -79,12 +79,6 @@ struct WunHandle {
     float* bw_grads = nullptr;           // wun_forward_backward: gradient buffer / scale, known to the forward pass for the fused epilogue
     float bw_scale = 1.f;
     int pair_min_ctas = 120;             // WUN_PAIR_MIN_CTAS
-    // LeakyReLU sign masks (plan.h Plan::mask_twin): which tensors' masks the last forward pass really wrote (the first-layer
-    // kernel and the non-folded tcgen05 kernels do), in which workspace; the dgrad epilogues then read bits instead of floats
-    bool sign_masks = true;              // WUN_SIGN_MASK=0 disables
-    std::vector<char> mask_live;
-    const float* mask_ws = nullptr; int mask_batch = 0;
-    std::vector<int> cur_mask_tensors;   // conv_forward -> launch_conv: tensors whose masks this launch would write
     bool pair_fwd = true;                // the same for the forward classes of the up blocks; WUN_PAIR_FWD=0 disables
     int pair_dgrad = 4;                  // pair-merged dgrad classes (launch.h OutView::pairC); WUN_PAIR_DGRAD=0 off, 1 all, 2 down blocks only,
                                          // 3 up blocks only, 4 (default) down blocks whose merged width still takes the fused-N MMAs (2C <= 64)
@@ -209,14 +203,6 @@ static const float* tensor_ptr(const WunHandle* h, int tensor) {
     return h->ws + h->lay.off[tensor];
 }
 
-// sign mask of `tensor` as seen through a view with this row offset (launch.h OutView::mask), or null
-static uint8_t* mask_ptr(const WunHandle* h, int tensor, int row_offset, int C) {
-    if (!h->sign_masks || tensor < 0 || tensor >= (int)h->plan.mask_twin.size()) return nullptr;
-    const int mt = h->plan.mask_twin[tensor];
-    if (mt < 0 || h->lay.off[mt] < 0) return nullptr;
-    return reinterpret_cast<uint8_t*>(h->ws + h->lay.off[mt]) + ((long long)row_offset * C) / 8;
-}
-
 static void tensor_geom(const WunHandle* h, int tensor, int64_t* rows, int* C, bool* per_batch) {
     if (tensor == TENSOR_MIX) { *rows = h->plan.T_in; *C = h->plan.cfg.num_channels; *per_batch = true; return; }
     const TensorSpec& t = h->plan.tensors[tensor];
@@ -261,8 +247,6 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
     const bool use_umma = h->umma_enabled && h->umma_pass[h->cur_pass] && umma_plan_from_conv(L, &ch);
     const size_t slot = (size_t)h->cur_layer * 3 + h->cur_pass;
     if (h->dry && slot < h->kernel_used.size()) h->kernel_used[slot] = use_umma ? "umma" : "simt";
-    if (use_umma && !ch.folded && h->phase != 1)
-        for (int t : h->cur_mask_tensors) h->mask_live[t] = 1;      // the persistent / dense epilogues store the sign bits
     if (use_umma) {
         if (h->fuse_out && h->debug_iters == 0 && umma_output_fusable(L, ch, h->fuse_out->O)) h->out_fused = true;
         if (h->phase != 1) h->launches += 2;    // weight pack + conv (counted once)
@@ -368,8 +352,6 @@ static bool first_layer_desc(const WunHandle* h, const ConvOp& op, FirstLayer* F
     F->W = h->params + h->plan.params[op.w_param].offset;
     F->bias = h->params + h->plan.params[op.b_param].offset;
     F->batch = h->batch;
-    F->dec_mask = mask_ptr(h, c0.out.tensor, 0, op.cout);
-    F->odd_mask = mask_ptr(h, c1.out.tensor, 0, op.cout);
     return true;
 }
 
@@ -390,7 +372,6 @@ static bool merge_pair(const ConvLaunch& S, ConvLaunch* out) {
     O.pairC = S.N;
     O.base2 = B.base; O.bstride2 = B.bstride; O.rstride2 = B.rstride; O.saved2 = B.saved;
     O.acc_lo2 = B.acc_lo; O.acc_hi2 = B.acc_hi;
-    O.mask2 = B.mask; O.smask2 = B.smask;
     O.lo_h[0] = A.m_lo; O.hi_h[0] = A.m_hi; O.lo_h[1] = B.m_lo; O.hi_h[1] = B.m_hi;
     // union of the two classes' (plane, shift) terms
     int nt = 0;
@@ -432,15 +413,12 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
         if (first_layer_desc(h, op, &F)) {
             if (h->phase == 1) return WUN_OK;
             ++h->launches;
-            if (F.dec_mask) h->mask_live[op.classes[0].out.tensor] = 1;
-            if (F.odd_mask) h->mask_live[op.classes[1].out.tensor] = 1;
             if (!h->dry) launch_first_fwd(F, h->plan.cfg.num_channels, op.cout, h->stream);
             return WUN_OK;
         }
     }
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
-    h->cur_mask_tensors.clear();
     L.nplanes = (int)op.planes.size();
     for (int p = 0; p < L.nplanes; ++p) L.planes[p] = make_plane(h, op.planes[p]);
     L.ncls = (int)op.classes.size();
@@ -451,8 +429,6 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
         PlaneView ov = make_plane(h, c.out);
         o.base = const_cast<float*>(ov.base); o.bstride = ov.bstride; o.rstride = ov.rstride;
         o.m_lo = c.m_lo; o.m_hi = c.m_hi; o.saved = nullptr; o.acc_lo = o.acc_hi = 0;
-        o.mask = (c.out.kind == PLANE_DIRECT && c.out.C % 8 == 0) ? mask_ptr(h, c.out.tensor, c.out.row_offset, c.out.C) : nullptr;
-        if (o.mask) h->cur_mask_tensors.push_back(c.out.tensor);
         o.term_begin = nt;
         for (const auto& t : c.terms) {
             if (nt >= kMaxTerms) return set_err(WUN_E_INVALID, "too many conv terms");
@@ -479,7 +455,6 @@ static int conv_forward(WunHandle* h, const ConvOp& op, int layer_index) {
     }
     const int rc = launch_conv(h, L);
     h->pack_floor = 0;
-    h->cur_mask_tensors.clear();
     return rc;
 }
 
@@ -509,9 +484,6 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
         o.base = const_cast<float*>(ov.base); o.bstride = ov.bstride; o.rstride = ov.rstride;
         o.m_lo = dc.r_lo; o.m_hi = dc.r_hi;
         o.saved = op.plane_slope[dc.plane] ? make_plane(h, v).base : nullptr;
-        if (o.saved && v.kind == PLANE_DIRECT && v.tensor >= 0 && v.tensor < (int)h->mask_live.size() && h->mask_live[v.tensor] &&
-            h->mask_ws == h->ws && h->mask_batch == h->batch)
-            o.smask = mask_ptr(h, v.tensor, v.row_offset, v.C);
         o.acc_lo = dc.acc_lo; o.acc_hi = dc.acc_hi;
         o.term_begin = nt;
         for (int q = 0; q < (int)op.classes.size(); ++q)
@@ -770,7 +742,6 @@ static void fill_output_launch(const WunHandle* h, OutputLaunch* O, const float*
 static int run_forward(WunHandle* h, const float* targets, float* outputs, float* loss, int training) {
     const Plan& P = h->plan;
     const int L = P.cfg.num_layers;
-    if (h->phase != 1) { h->mask_live.assign(P.tensors.size(), 0); h->mask_ws = h->ws; h->mask_batch = h->batch; }
     for (int i = 0; i < L; ++i) {
         const UpsampleSpec& us = P.ups[i];
         if (us.interp_param >= 0) {
@@ -954,7 +925,6 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_PAIR_DGRAD"); h->pair_dgrad = v ? atoi(v) : 4; }
     { const char* v = getenv("WUN_PAIR_MIN_CTAS"); h->pair_min_ctas = v ? atoi(v) : 120; }
-    { const char* v = getenv("WUN_SIGN_MASK"); h->sign_masks = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_OUT_FUSE"); h->out_fuse_mode = v ? atoi(v) : 1; }
     { const char* v = getenv("WUN_PAIR_FWD"); h->pair_fwd = !(v && v[0] == '0'); }
     h->kernel_used.assign((size_t)(2 * h->plan.cfg.num_layers + 1) * 3, "simt");

@@ -53,7 +53,6 @@ struct FirstLayer {
     const float* W;                                 // [k][C][N]
     const float* bias;                              // [N]
     int batch;
-    uint8_t *dec_mask, *odd_mask;                   // LeakyReLU sign masks of dec / odd (launch.h OutView::mask) or null
 };
 
 struct FirstWgrad {

@@ -83,18 +83,6 @@ __global__ void __launch_bounds__(128) first_fwd_kernel(const __grid_constant__ 
             y = acc[r][4 * n4 + 3] + bs[4 * n4 + 3]; v.w = fmaxf(0.2f * y, y);
             reinterpret_cast<float4*>(o)[n4] = v;
         }
-        uint8_t* mk = (q == 0) ? L.dec_mask : L.odd_mask;          // sign bits of the row (N / 8 bytes), for the dgrad of the next block
-        if (mk) {
-            const long long e = (q == 0) ? (long long)b * L.dec_bstride + (long long)m * N
-                                         : (long long)b * L.odd_bstride + (long long)(m - L.mo_lo) * N;
-#pragma unroll
-            for (int n8 = 0; n8 < N / 8; ++n8) {
-                unsigned bits = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bits |= ((acc[r][8 * n8 + j] + bs[8 * n8 + j]) > 0.f) ? (1u << j) : 0u;
-                mk[(e >> 3) + n8] = (uint8_t)bits;
-            }
-        }
     }
 }
 

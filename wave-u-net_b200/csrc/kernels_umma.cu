@@ -296,130 +296,103 @@ constexpr int kEpiBatch = WUN_EPI_BATCH;
 // forward launches (nothing to read back) keep the straight loop; the two forms live in separate kernel instantiations
 // (template parameter DG) because the batched form's registers slowed the forward kernels down when both shared one body
 // (down1 forward 149 -> 195 us).
-// Pair-merged classes (OutView::pairC > 0): the quad's column decides which of the two views a value belongs to (col0 = first
-// launch column of the staged block, a multiple of 4 like pairC, so a quad never straddles the halves).
-// PAIR = false (forward instantiations, which never see a pair-merged class) compiles the second view away.
-struct EpiDst { float* dst; const float* saved; bool use_mask, ok, acc; };
+// Phase 2 addressing.  The four epilogue warps are instruction-issue bound in the dgrad launches (measured: deleting the slope
+// read-back saved 0.4 ms of the step although its bytes are a third of the launch's traffic, while variants that ADDED
+// instructions to hide its latency - sign-bit masks, cp.async prefetch of the saved rows - were slower), so everything that
+// does not depend on the item is hoisted: per half (pair-merged classes have two, launch.h OutView::pairC) one base pointer that
+// already contains the batch item and the block's first column, then an item costs one 32-bit multiply-add.
+struct EpiHalf {
+    float* dst;            // + m * rstride + 4 * (quad within the half)
+    const float* saved;    // same geometry (null: no slope)
+    int rstride, lo, hi, acc_lo, acc_hi;
+};
+struct EpiBlock {
+    EpiHalf h[2];
+    int qsplit;            // quads [0, qsplit) of the staged block belong to half 0, the rest to half 1
+};
 template <bool PAIR>
-__device__ __forceinline__ EpiDst epi_dst(const OutView& O, int b, int m, int col, bool slope) {
-    EpiDst d;
-    if (PAIR && O.pairC > 0) {
-        const int h = (col >= O.pairC) ? 1 : 0;
-        d.ok = m >= O.lo_h[h] && m < O.hi_h[h];
-        const long long off = h ? ((long long)b * O.bstride2 + (long long)m * O.rstride2 + (col - O.pairC))
-                                : ((long long)b * O.bstride + (long long)m * O.rstride + col);
-        d.dst = (h ? O.base2 : O.base) + off;
-        const float* sv = h ? O.saved2 : O.saved;
-        d.use_mask = slope && (h ? O.smask2 : O.smask) != nullptr;     // sign bits (staged by phase 1) instead of the saved activation
-        d.saved = (slope && sv && !d.use_mask) ? sv + off : nullptr;
-        d.acc = d.ok && (h ? (m >= O.acc_lo2 && m < O.acc_hi2) : (m >= O.acc_lo && m < O.acc_hi));
+__device__ __forceinline__ EpiBlock epi_block(const OutView& O, int b, int col0, int Q, bool slope) {
+    EpiBlock B;
+    const bool pair = PAIR && O.pairC > 0;
+    const int c1 = pair ? max(col0, O.pairC) : 0;           // first launch column of half 1 inside / after this block
+    B.qsplit = pair ? min(Q, max(0, (O.pairC - col0) >> 2)) : Q;
+    B.h[0].dst = O.base + (long long)b * O.bstride + col0;
+    B.h[0].saved = (slope && O.saved) ? O.saved + (long long)b * O.bstride + col0 : nullptr;
+    B.h[0].rstride = O.rstride;
+    B.h[0].lo = pair ? O.lo_h[0] : O.m_lo; B.h[0].hi = pair ? O.hi_h[0] : O.m_hi;
+    B.h[0].acc_lo = O.acc_lo; B.h[0].acc_hi = O.acc_hi;
+    if (pair) {
+        // quad q >= qsplit sits at launch column col0 + 4q = half-1 column (col0 + 4q - pairC): fold (c1 - pairC) - 4 * qsplit into the base
+        const long long adj = (long long)b * O.bstride2 + (c1 - O.pairC) - 4 * B.qsplit;
+        B.h[1].dst = O.base2 + adj;
+        B.h[1].saved = (slope && O.saved2) ? O.saved2 + adj : nullptr;
+        B.h[1].rstride = O.rstride2;
+        B.h[1].lo = O.lo_h[1]; B.h[1].hi = O.hi_h[1];
+        B.h[1].acc_lo = O.acc_lo2; B.h[1].acc_hi = O.acc_hi2;
     } else {
-        d.ok = m < O.m_hi;
-        const long long off = (long long)b * O.bstride + (long long)m * O.rstride + col;
-        d.dst = O.base + off;
-        d.use_mask = slope && O.smask != nullptr;
-        d.saved = (slope && O.saved && !d.use_mask) ? O.saved + off : nullptr;
-        d.acc = d.ok && m >= O.acc_lo && m < O.acc_hi;
+        B.h[1] = B.h[0];
     }
 #ifdef WUN_EXP_NOSLOPE          // timing experiment only (wrong gradients): what the slope read-back of the dgrad epilogue costs
-    d.saved = nullptr; d.use_mask = false;
+    B.h[0].saved = nullptr; B.h[1].saved = nullptr;
 #endif
-    return d;
+    return B;
 }
+
+// Phase 2 of the conv epilogue for one warp: write out the 32 accumulator rows it staged (row r0 + 0..31 of the tile), lanes running
+// over (row, 4-column quad) pairs; (rl, q) advance incrementally (no division per item).  Forward form: nothing to read back.
+// (A separate one-view instantiation next to the pair-aware one was tried: the copies pushed the block descriptor into local
+//  memory - 352-byte stack frames - and the dgrad family from 2.2 to 3.5 ms.)
 __device__ __forceinline__ void epi_write_rows_simple(const float* __restrict__ stage, int SW, int r0, int lane, int Q, int m0,
-                                                      const OutView& O, int b, int col0, bool slope) {
-    for (int it = lane; it < 32 * Q; it += 32) {
-        const int rl = it / Q, q = it - rl * Q;
-        const EpiDst d = epi_dst<true>(O, b, m0 + rl, col0 + 4 * q, slope);
-        if (!d.ok) continue;
-        float4 o = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
-        if (d.saved) {
-            const float4 sv = __ldg(reinterpret_cast<const float4*>(d.saved));
-            o.x *= (sv.x > 0.f) ? 1.f : 0.2f; o.y *= (sv.y > 0.f) ? 1.f : 0.2f;
-            o.z *= (sv.z > 0.f) ? 1.f : 0.2f; o.w *= (sv.w > 0.f) ? 1.f : 0.2f;
-        }
-        float4* dst = reinterpret_cast<float4*>(d.dst);
-        if (d.acc) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-        *dst = o;
+                                                      const EpiBlock& B) {
+    const int dr = 32 / Q, dq = 32 - dr * Q;
+    int rl = lane / Q, q = lane - rl * Q;
+    for (; rl < 32; rl += dr, q += dq) {
+        if (q >= Q) { q -= Q; ++rl; if (rl >= 32) break; }
+        const EpiHalf& H = (q < B.qsplit) ? B.h[0] : B.h[1];
+        const int m = m0 + rl;
+        if (m < H.lo || m >= H.hi) continue;
+        const float4 o = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
+        *reinterpret_cast<float4*>(H.dst + m * H.rstride + 4 * q) = o;
     }
 }
-// mstage: the sign-mask bytes phase 1 fetched for the staged block, 16 per row (one per 8 columns) - the slope of a quad is 4 bits
-// of shared memory instead of a dependent 16-byte global read-back (launch.h OutView::smask).
+// dgrad form: the LeakyReLU-slope read of the saved activation and the accumulate read of the destination are issued for
+// kEpiBatch items BEFORE any of them is used (memory-level parallelism: the store loop is a chain of dependent global loads).
 __device__ __forceinline__ void epi_write_rows_vec(const float* __restrict__ stage, int SW, int r0, int lane, int Q, int m0,
-                                                   const OutView& O, int b, int col0, bool slope, const uint8_t* __restrict__ mstage) {
-    const int nit = 32 * Q;
-    for (int it0 = lane; it0 < nit; it0 += 32 * kEpiBatch) {
+                                                   const EpiBlock& B) {
+    const int dr = 32 / Q, dq = 32 - dr * Q;
+    int rl = lane / Q, q = lane - rl * Q;
+    while (rl < 32) {
         float4 o[kEpiBatch], sv[kEpiBatch], old[kEpiBatch];
-        EpiDst d[kEpiBatch];
+        float* dst[kEpiBatch];
+        unsigned flags = 0;           // per item: bit u = valid, bit 8+u = slope, bit 16+u = accumulate
 #pragma unroll
         for (int u = 0; u < kEpiBatch; ++u) {
-            const int it = it0 + 32 * u;
-            const int rl = it / Q, q = it - rl * Q;
-            d[u] = epi_dst<true>(O, b, m0 + rl, col0 + 4 * q, slope);
-            d[u].ok = d[u].ok && it < nit;
-            if (d[u].ok) {
-                o[u] = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
-                if (d[u].saved) sv[u] = __ldg(reinterpret_cast<const float4*>(d[u].saved));
-                if (d[u].acc) old[u] = *reinterpret_cast<const float4*>(d[u].dst);
+            if (q >= Q) { q -= Q; ++rl; }
+            if (rl < 32) {
+                const EpiHalf& H = (q < B.qsplit) ? B.h[0] : B.h[1];
+                const int m = m0 + rl;
+                if (m >= H.lo && m < H.hi) {
+                    const int off = m * H.rstride + 4 * q;
+                    dst[u] = H.dst + off;
+                    o[u] = *reinterpret_cast<const float4*>(stage + (size_t)(r0 + rl) * SW + 4 * q);
+                    flags |= 1u << u;
+                    if (H.saved) { sv[u] = __ldg(reinterpret_cast<const float4*>(H.saved + off)); flags |= 0x100u << u; }
+                    if (m >= H.acc_lo && m < H.acc_hi) { old[u] = *reinterpret_cast<const float4*>(dst[u]); flags |= 0x10000u << u; }
+                }
             }
+            rl += dr; q += dq;
         }
 #pragma unroll
         for (int u = 0; u < kEpiBatch; ++u) {
-            if (!d[u].ok) continue;
+            if (!(flags & (1u << u))) continue;
             float4 v = o[u];
-            if (d[u].use_mask) {
-                const int it = it0 + 32 * u;
-                const int rl = it / Q, q = it - rl * Q;
-                const unsigned bits = (unsigned)mstage[(r0 + rl) * 16 + (q >> 1)] >> ((q & 1) * 4);
-                v.x *= (bits & 1u) ? 1.f : 0.2f; v.y *= (bits & 2u) ? 1.f : 0.2f;
-                v.z *= (bits & 4u) ? 1.f : 0.2f; v.w *= (bits & 8u) ? 1.f : 0.2f;
-            } else if (d[u].saved) {
+            if (flags & (0x100u << u)) {
                 v.x *= (sv[u].x > 0.f) ? 1.f : 0.2f; v.y *= (sv[u].y > 0.f) ? 1.f : 0.2f;
                 v.z *= (sv[u].z > 0.f) ? 1.f : 0.2f; v.w *= (sv[u].w > 0.f) ? 1.f : 0.2f;
             }
-            if (d[u].acc) { v.x += old[u].x; v.y += old[u].y; v.z += old[u].z; v.w += old[u].w; }
-            *reinterpret_cast<float4*>(d[u].dst) = v;
+            if (flags & (0x10000u << u)) { v.x += old[u].x; v.y += old[u].y; v.z += old[u].z; v.w += old[u].w; }
+            *reinterpret_cast<float4*>(dst[u]) = v;
         }
-    }
-}
-
-// Forward epilogue, thread = accumulator row: sign bits of the 16 activations v[] it is about to stage (launch columns
-// [col0, col0 + 16) of row m), one byte per 8 channels, into the tensor's sign mask (launch.h OutView::mask).
-__device__ __forceinline__ void epi_store_sign_bits(const OutView& O, int pairC, int N, int b, int m, int col0, const float* v) {
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int col = col0 + 8 * g;
-        if (col >= N) continue;
-        unsigned bits = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bits |= (v[8 * g + j] > 0.f) ? (1u << j) : 0u;
-        const int h = (pairC > 0 && col >= pairC) ? 1 : 0;
-        uint8_t* mk = h ? O.mask2 : O.mask;
-        const bool ok = (pairC > 0) ? (m >= O.lo_h[h] && m < O.hi_h[h]) : (m < O.m_hi);
-        if (!ok || !mk) continue;
-        const long long off = h ? ((long long)b * O.bstride2 + (long long)m * O.rstride2 + (col - pairC))
-                                : ((long long)b * O.bstride + (long long)m * O.rstride + col);
-        mk[off >> 3] = (uint8_t)bits;
-    }
-}
-
-// dgrad epilogue, thread = accumulator row: request the sign-mask bytes of its row for the launch columns [col0, col0 + cw)
-// (cw <= 128: up to 16 independent byte loads in flight per thread, consumed after the accumulator read-out); rows / halves
-// without a mask give 0.
-__device__ __forceinline__ void epi_fetch_sign_bytes(const OutView& O, int pairC, int N, int b, int m, int col0, int cw, uint32_t* mw) {
-    mw[0] = mw[1] = mw[2] = mw[3] = 0u;
-    if (!O.smask && !(pairC > 0 && O.smask2)) return;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) {
-        const int col = col0 + 8 * g;
-        if (8 * g >= cw || col >= N) continue;
-        const int h = (pairC > 0 && col >= pairC) ? 1 : 0;
-        const uint8_t* sm = h ? O.smask2 : O.smask;
-        const bool ok = (pairC > 0) ? (m >= O.lo_h[h] && m < O.hi_h[h]) : (m < O.m_hi);
-        if (!ok || !sm) continue;
-        const long long off = h ? ((long long)b * O.bstride2 + (long long)m * O.rstride2 + (col - pairC))
-                                : ((long long)b * O.bstride + (long long)m * O.rstride + col);
-        mw[g >> 2] |= (uint32_t)__ldg(sm + (off >> 3)) << (8 * (g & 3));
     }
 }
 
@@ -462,7 +435,6 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
               ACC_FULL = 2 * kSlabMax + 2 * kBStagesMax;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_FULL + 1);
     float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // NPAD floats: this split's bias
-    uint8_t* mstage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + NPAD) + 15) & ~(uintptr_t)15);   // 128 rows x 16 sign-mask bytes (dgrad epilogue)
     for (int i = tid; i < NPAD; i += blockDim.x) {
         const int n = split * NPAD + i;
         bias_s[i] = (L.bias && n < L.N) ? __ldg(L.bias + ((L.pairC > 0 && n >= L.pairC) ? n - L.pairC : n)) : 0.f;
@@ -555,8 +527,6 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
             for (int c0 = 0; c0 < NPAD; c0 += CW) {
                 if (n0 + c0 >= L.N) break;
                 const int cw = min(CW, NPAD - c0);
-                uint32_t mw[4];
-                if (DG && L.epilogue == EPI_SLOPE) epi_fetch_sign_bytes(K.out, L.pairC, L.N, b, m_base + mt * 128 + warp * 32 + lane, n0 + c0, cw, mw);
                 // phase 1: thread = accumulator row (TMEM lane)
                 for (int cb = 0; cb < cw; cb += 16) {
                     __syncwarp();
@@ -580,13 +550,11 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                             const float y = v[j] + bias_s[c0 + cb + j];
                             v[j] = fmaxf(0.2f * y, y);
                         }
-                        if (!DG && K.out.mask) epi_store_sign_bits(K.out, L.pairC, L.N, b, m_base + mt * 128 + warp * 32 + lane, n0 + c0 + cb, v);
                     }
                     float4* dst = reinterpret_cast<float4*>(stage + (size_t)(warp * 32 + lane) * SW + cb);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
-                if (DG && L.epilogue == EPI_SLOPE) *reinterpret_cast<uint4*>(mstage + (warp * 32 + lane) * 16) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                 __syncwarp();
                 // phase 2: each warp writes out the 32 rows it staged itself (no block barrier needed); lanes run over
                 // (row, 4-column quad) pairs so that narrow layers (N = 24..48) still use every lane and a whole warp
@@ -596,10 +564,9 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
                 if (vec) {      // (pair-merged classes always take this path: the planner checks both views)
-                    if (DG) epi_write_rows_vec(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, b, n0 + c0,
-                                               L.epilogue == EPI_SLOPE, mstage);
-                    else epi_write_rows_simple(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, K.out, b, n0 + c0,
-                                               L.epilogue == EPI_SLOPE);
+                    const EpiBlock EB = epi_block<true>(K.out, b, n0 + c0, ncols >> 2, L.epilogue == EPI_SLOPE);
+                    if (DG) epi_write_rows_vec(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, EB);
+                    else epi_write_rows_simple(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, EB);
                 } else {
                     for (int it = lane; it < 32 * ncols; it += 32) {
                         const int rl = it / ncols, j = it - rl * ncols;
@@ -755,7 +722,11 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaLaunch& L, int t) {
 // NCOL = number of output-conv columns (nconv * C) of the fused output layer, 0 = plain conv.  The fused epilogue is compiled per
 // width: generic code predicated up to 8 columns was 6000 instructions (95 KB) that the four epilogue warps streamed through the
 // instruction cache once per row tile - 70k cycles per 128 rows, measured.
-template <int PT, bool DG, int NCOL>
+// EPW = epilogue warps per TMEM lane quarter (1 or 2).  The dgrad launches are bound by the instruction issue of their epilogue
+// warps, so their instantiation trades one converter team for a second epilogue group: the two groups split the
+// 16-column chunks of every staged block between them (same rows, disjoint columns of the same staging tile - no extra shared
+// memory, no synchronisation between the groups beyond the accumulator-free barrier, which now counts 128 * EPW arrivals).
+template <int PT, bool DG, int NCOL, int EPW>
 __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_tiles, const OutputFuse* FP) {
     constexpr bool OUTL = NCOL > 0;
     constexpr int NC = OUTL ? NCOL : 1;          // array extent of the per-column registers
@@ -780,7 +751,6 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
               ACC_FULL = 2 * kSlabStages + 2 * kBStagesMax, ACC_EMPTY = ACC_FULL + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + ACC_EMPTY + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_holder + 4);       // nsplit * NPAD floats
-    uint8_t* mstage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + NPAD * L.nsplit) + 15) & ~(uintptr_t)15);   // 128 rows x 16 sign-mask bytes (dgrad epilogue)
     for (int i = tid; i < NPAD * L.nsplit; i += blockDim.x)
         bias_s[i] = (L.bias && i < L.N) ? __ldg(L.bias + ((L.pairC > 0 && i >= L.pairC) ? i - L.pairC : i)) : 0.f;
     // fused output layer (OUTL): [wout (C+F) x ncol | bout ncol | dpre 128 rows x 2 halves x ncol | wacc 4 warps x (C+F+1) x ncol]
@@ -789,7 +759,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
     if (OUTL) {
         const OutputLaunch& O = FP->O;
         o_ncol = O.nconv * O.C; o_cin = O.C + O.F; o_nw = (o_cin + 1) * o_ncol;
-        wout_s = reinterpret_cast<float*>(mstage + 2048);         // (behind the 2 KB sign-mask stage)
+        wout_s = bias_s + ((NPAD * L.nsplit + 3) & ~3);
         bout_s = wout_s + o_cin * o_ncol;
         dpre_s = bout_s + ((o_ncol + 3) & ~3);
         wacc_s = dpre_s + 128 * 2 * o_ncol;
@@ -803,7 +773,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
     if (tid == 0) {
         for (int i = 0; i < kSlabStages; ++i) { mbar_init(BAR(SLAB_FULL + i), kWorkerThreads); mbar_init(BAR(SLAB_EMPTY + i), 1); }
         for (int i = 0; i < kBStagesMax; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 128 * EPW); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_holder), L.tmem_cols);
@@ -958,6 +928,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
     } else {
         // ===================== epilogue warps: TMEM lane quarter = warp & 3 =====================
         const int q4 = warp & 3;
+        const int eg = (warp - kEpiWarp0) >> 2;                // epilogue group (0 .. EPW-1)
         int k = 0;
         float o_lsum = 0.f;                                    // OUTL: this thread's share of the squared error
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
@@ -1013,11 +984,12 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                 }
                 for (int c0 = 0; c0 < NPAD; c0 += CW) {
                     const bool last_block = (mt == L.MT - 1) && (c0 == c0_last);
+                    // this group's 16-column chunks of the block: [cb_lo, cb_hi)
+                    const int nch_blk = (min(CW, NPAD - c0) + 15) >> 4;
+                    const int cb_lo = (EPW == 2 && eg == 1) ? 16 * ((nch_blk + 1) >> 1) : 0;
+                    const int cb_hi = (EPW == 2 && eg == 0) ? 16 * ((nch_blk + 1) >> 1) : 16 * nch_blk;
                     if (n0 + c0 < L.N) {
-                        const int cw = min(CW, NPAD - c0);
-                        uint32_t mw[4];
-                        if (DG && L.epilogue == EPI_SLOPE) epi_fetch_sign_bytes(K.out, L.pairC, L.N, tc.b, tc.m_base + mt * 128 + q4 * 32 + lane, n0 + c0, cw, mw);
-                        for (int cb = 0; cb < cw; cb += 16) {
+                        for (int cb = cb_lo; cb < cb_hi; cb += 16) {
                             __syncwarp();
                             float v[16];
                             tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * acc_cols + (uint32_t)mt * acc_w + (uint32_t)(c0 + cb), v);
@@ -1037,7 +1009,6 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                                     const float y = v[j] + bias_s[n0 + c0 + cb + j];
                                     v[j] = fmaxf(0.2f * y, y);
                                 }
-                                if (!DG && K.out.mask) epi_store_sign_bits(K.out, L.pairC, L.N, tc.b, tc.m_base + mt * 128 + q4 * 32 + lane, n0 + c0 + cb, v);
                             }
                             float4* dst = reinterpret_cast<float4*>(stage + (size_t)(q4 * 32 + lane) * SW + cb);
 #pragma unroll
@@ -1061,7 +1032,6 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                                 }
                             }
                         }
-                        if (DG && L.epilogue == EPI_SLOPE) *reinterpret_cast<uint4*>(mstage + (q4 * 32 + lane) * 16) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                     }
                     if (last_block) {                       // every tcgen05.ld of this buffer has completed: hand it back
                         tc_fence_before();
@@ -1138,18 +1108,18 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                             }
                         }
                     }
-                    if (n0 + c0 < L.N) {
-                        const int cw = min(CW, NPAD - c0);
+                    if (n0 + c0 + cb_lo < L.N && cb_lo < cb_hi) {
                         __syncwarp();
-                        const int ncols = min(cw, L.N - (n0 + c0));
-                        const long long tile_off = (long long)tc.b * K.out.bstride + n0 + c0;
+                        // real columns of this group's share: launch columns [n0 + c0 + cb_lo, ...)
+                        const int ncols = min(cb_hi, L.N - (n0 + c0)) - cb_lo;
+                        const long long tile_off = (long long)tc.b * K.out.bstride + n0 + c0 + cb_lo;
                         const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                          ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
+                        const EpiBlock EB = epi_block<true>(K.out, tc.b, n0 + c0 + cb_lo, ncols >> 2, L.epilogue == EPI_SLOPE);
+                        const float* stage_g = stage + cb_lo;
                         if (vec) {
-                            if (DG) epi_write_rows_vec(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tc.b, n0 + c0,
-                                                       L.epilogue == EPI_SLOPE, mstage);
-                            else epi_write_rows_simple(stage, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, K.out, tc.b, n0 + c0,
-                                                       L.epilogue == EPI_SLOPE);
+                            if (DG) epi_write_rows_vec(stage_g, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, EB);
+                            else epi_write_rows_simple(stage_g, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, EB);
                         } else {
                             for (int it = lane; it < 32 * ncols; it += 32) {
                                 const int rl = it / ncols, j = it - rl * ncols;
@@ -1157,7 +1127,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                                 const int m = tc.m_base + mt * 128 + r;
                                 if (m >= K.out.m_hi) continue;
                                 const long long roff = tile_off + (long long)m * K.out.rstride;
-                                float o = stage[(size_t)r * SW + j];
+                                float o = stage_g[(size_t)r * SW + j];
                                 if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
                                 float* dst = K.out.base + roff + j;
                                 if (m >= K.out.acc_lo && m < K.out.acc_hi) o += *dst;
@@ -1172,8 +1142,10 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                             const int Q = ncols >> 2;
                             for (int it = lane; it < 32 * Q; it += 32) {
                                 const int rl = it / Q, qd = it - rl * Q, col = 4 * qd;
-                                const EpiDst d = epi_dst<true>(K.out, tc.b, tc.m_base + mt * 128 + q4 * 32 + rl, col, false);
-                                if (!d.ok) continue;
+                                const EpiHalf& H = (qd < EB.qsplit) ? EB.h[0] : EB.h[1];
+                                const int mrow = tc.m_base + mt * 128 + q4 * 32 + rl;
+                                if (mrow < H.lo || mrow >= H.hi) continue;
+                                float* fdst = H.dst + mrow * H.rstride + 4 * qd;
                                 const bool h1 = L.pairC > 0 && col >= L.pairC;
                                 const float4 f = *reinterpret_cast<const float4*>(stage + (size_t)(q4 * 32 + rl) * SW + col);
                                 const float* dp = dpre_s + ((q4 * 32 + rl) * 2 + (h1 ? 1 : 0)) * o_ncol;
@@ -1188,7 +1160,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                                 float4 go;
                                 go.x = sx * ((f.x > 0.f) ? 1.f : 0.2f); go.y = sy * ((f.y > 0.f) ? 1.f : 0.2f);
                                 go.z = sz * ((f.z > 0.f) ? 1.f : 0.2f); go.w = sw * ((f.w > 0.f) ? 1.f : 0.2f);
-                                *reinterpret_cast<float4*>(FP->gfeat + (d.dst - O.feat)) = go;
+                                *reinterpret_cast<float4*>(FP->gfeat + (fdst - O.feat)) = go;
                             }
                             // (b) output-conv weight / bias gradients: thread = its own row again, warp-reduced, summed per warp in shared memory
                             const int r = q4 * 32 + lane;
@@ -1241,14 +1213,18 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
 
 template <int PT, bool DG>
 __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
-    persistent_body<PT, DG, 0>(L, total_tiles, nullptr);
+    persistent_body<PT, DG, 0, 1>(L, total_tiles, nullptr);
+}
+// dgrad with two epilogue warp groups and two converter teams (UmmaLaunch::epi2)
+__global__ void __launch_bounds__(2 * 128 + 64 + 256, 1) plane_conv_umma_persistent_dg2(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+    persistent_body<2, true, 0, 2>(L, total_tiles, nullptr);
 }
 // the last up block's forward conv with the output layer, the loss and the output layer's backward in its epilogue (OutputFuse);
 // NCOL = nconv * C of the output convs
 template <int NCOL>
 __global__ void __launch_bounds__(3 * 128 + 192, 1) plane_conv_umma_persistent_out(const __grid_constant__ UmmaLaunch L, int total_tiles,
                                                                                  const __grid_constant__ OutputFuse F) {
-    persistent_body<3, false, NCOL>(L, total_tiles, &F);
+    persistent_body<3, false, NCOL, 1>(L, total_tiles, &F);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1640,14 +1616,14 @@ static size_t umma_pers_smem_bytes(const UmmaLaunch& L) {
     const size_t CW = (L.NPAD < 128) ? L.NPAD : 128;
     const size_t kSlabStages = (L.nteams == 3) ? 4 : 3;
     return (size_t)kSlabStages * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD + 128u * (CW + 4) * 4 +
-           (2 * kSlabStages + 2 * kBStagesMax + 4) * 8 + 32 + 4 * (size_t)L.NPAD * L.nsplit + 16 + 2048 + 16;
+           (2 * kSlabStages + 2 * kBStagesMax + 4) * 8 + 32 + 4 * (size_t)L.NPAD * L.nsplit;
 }
 
 size_t umma_smem_bytes(const UmmaLaunch& L) {
     const size_t nslab = (L.nteams == 4) ? 6 : 3;
     const size_t pipe = nslab * 64u * L.rows_alloc + (size_t)L.nbs * L.TB * 64u * L.NPAD;
     const size_t epi = 128u * ((size_t)(L.NPAD < 128 ? L.NPAD : 128) + 4u) * 4u;
-    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * 6 + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD + 2048 + 16;
+    return ((pipe > epi ? pipe : epi) + 127) / 128 * 128 + (2 * 6 + 2 * kBStagesMax + 1) * 8 + 32 + 4 * L.NPAD;
 }
 
 template <typename KernelT>
@@ -1682,6 +1658,7 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream, con
         if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<2>, 220 * 1024);
         if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<4>, 220 * 1024);
         if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<6>, 220 * 1024);
+        if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_dg2, 220 * 1024);
         if (e0 != cudaSuccess) return e0;
         cudaError_t e = set_smem_limit(plane_conv_umma_kernel<2, false>, 200 * 1024);
         if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<2, true>, 200 * 1024);
@@ -1719,6 +1696,11 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream, con
                 case 6: plane_conv_umma_persistent_out<6><<<grid, 3 * 128 + 192, smem_o, stream>>>(L, total, *fuse); break;
                 default: return cudaErrorInvalidValue;
             }
+            return cudaGetLastError();
+        }
+        if (dg && L.epi2) {
+            if (L.nteams != 2) return cudaErrorInvalidValue;
+            plane_conv_umma_persistent_dg2<<<grid, 2 * 128 + 64 + 256, smem, stream>>>(L, total);
             return cudaGetLastError();
         }
         if (L.nteams == 3) {
@@ -2196,6 +2178,7 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
     const int nchunks = g1 - g0;
 
     if (warp == 0) {
+        // (all 32 lanes issuing the stage's up to 64 bulk copies was tried: every layer's wgrad got 10-30 % slower)
         if (elect_one()) {
             const uint8_t* baseA = swap ? S.G[gi] : S.P[gi];
             const uint8_t* baseB = swap ? S.P[gi] : S.G[gi];
@@ -2241,33 +2224,32 @@ __global__ void __launch_bounds__(kWgBulkThreads, 1) wgrad_umma_bulk_kernel(cons
                 mbar_wait(BAR(FULL + st), (ci / nst) & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + bytesA;
-                const uint64_t a_hi0 = umma_desc(sa, 128, planeA), a_lo0 = umma_desc(sa + atomsA * planeA, 128, planeA);
-                const uint64_t b_hi0 = umma_desc(sb, 128, planeB), b_lo0 = umma_desc(sb + atomsB * planeB, 128, planeB);
+                // descriptors as (low word, high word): along the taps and K steps only the start-address field of the low word moves
+                // (+1 per row), so the issuing thread advances them with one 32-bit add per MMA (the same lean form as the conv kernels)
+                const uint32_t hiA = (planeA >> 4) | (1u << 14), hiB = (planeB >> 4) | (1u << 14);
+                const uint32_t a_hi0 = umma_desc_lo(sa, 128), a_lo0 = umma_desc_lo(sa + atomsA * planeA, 128);
+                const uint32_t b_hi0 = umma_desc_lo(sb, 128), b_lo0 = umma_desc_lo(sb + atomsB * planeB, 128);
                 for (int t = 0; t < ntap; ++t) {
-                    const uint64_t shift = (uint64_t)(uint32_t)(Gp.d[tap0 + t] - dmin);
-                    const uint64_t sha = swap ? 0ull : shift, shb = swap ? shift : 0ull;
+                    const uint32_t shift = (uint32_t)(Gp.d[tap0 + t] - dmin);
+                    const uint32_t sha = swap ? 0u : shift, shb = swap ? shift : 0u;
                     const uint32_t td = tmem_base + (uint32_t)t * accw;
                     if (Gp.fuse) {
                         // fused-N: the B stage keeps the lo atom planes right behind the hi atom planes at the same stride, so one
                         // descriptor with N = 2*NT covers [B_hi | B_lo]: 2 MMAs per product, halves summed in the epilogue
 #pragma unroll
                         for (int ks = 0; ks < kWgRK / 16; ++ks) {
-                            const uint64_t koff = (uint64_t)(16 * ks);
-                            const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
-                            const uint64_t b_hi = b_hi0 + shb + koff;
-                            umma_bf16(td, a_hi, b_hi, idesc2, (ks == 0) ? accum : 1u);
-                            umma_bf16(td, a_lo, b_hi, idesc, 1u);
+                            const uint32_t koff = (uint32_t)(16 * ks);
+                            umma_bf16_w(td, a_hi0 + sha + koff, hiA, b_hi0 + shb + koff, hiB, idesc2, (ks == 0) ? accum : 1u);
+                            umma_bf16_w(td, a_lo0 + sha + koff, hiA, b_hi0 + shb + koff, hiB, idesc, 1u);
                         }
                     } else {
 #pragma unroll
-                    for (int ks = 0; ks < kWgRK / 16; ++ks) {
-                        const uint64_t koff = (uint64_t)(16 * ks);
-                        const uint64_t a_hi = a_hi0 + sha + koff, a_lo = a_lo0 + sha + koff;
-                        const uint64_t b_hi = b_hi0 + shb + koff, b_lo = b_lo0 + shb + koff;
-                        umma_bf16(td, a_lo, b_hi, idesc, (ks == 0) ? accum : 1u);
-                        umma_bf16(td, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(td, a_hi, b_hi, idesc, 1u);
-                    }
+                        for (int ks = 0; ks < kWgRK / 16; ++ks) {
+                            const uint32_t koff = (uint32_t)(16 * ks);
+                            umma_bf16_w(td, a_lo0 + sha + koff, hiA, b_hi0 + shb + koff, hiB, idesc, (ks == 0) ? accum : 1u);
+                            umma_bf16_w(td, a_hi0 + sha + koff, hiA, b_lo0 + shb + koff, hiB, idesc, 1u);
+                            umma_bf16_w(td, a_hi0 + sha + koff, hiA, b_hi0 + shb + koff, hiB, idesc, 1u);
+                        }
                     }
                 }
                 accum = 1u;
@@ -2634,13 +2616,19 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
                 const char* envt = getenv("WUN_PERS_TEAMS");
                 ch->nteams = (envt && envt[0] == '2') ? 2 : 3;
             }
+            {   // dgrad: two epilogue warp groups + two converter teams (WUN_EPI2=0: one group, three teams)
+                const char* enve = getenv("WUN_EPI2");
+                ch->epi2 = (L.epilogue == EPI_SLOPE && !(enve && enve[0] == '0')) ? 1 : 0;
+                if (ch->epi2) ch->nteams = 2;
+            }
             // one CTA per SM: a deeper weight ring fits next to the slab stages and the epilogue staging tile
             const long long cw = (ch->NPAD < 128) ? ch->NPAD : 128;
-            long long left = 218 * 1024 - (long long)(ch->nteams + 1) * 64 * ch->rows_alloc - 128 * (cw + 4) * 4 - 1024 - 2080 - 4LL * ch->NPAD * ch->nsplit;
+            long long left = 218 * 1024 - (long long)(ch->nteams + 1) * 64 * ch->rows_alloc - 128 * (cw + 4) * 4 - 1024 - 4LL * ch->NPAD * ch->nsplit;
             if (left > 98304) left = 98304;
             ch->nbs = (int)(left / (TB * blk));
             if (ch->nbs > kBStagesMax) ch->nbs = kBStagesMax;
             if (ch->nbs < 2) { ch->nbs = 2; ch->nteams = 2; }
+            if (ch->nteams != 2) ch->epi2 = 0;
             int tm2 = 32;
             while (tm2 < 2 * MT * ch->NPAD * (ch->fuse ? 2 : 1)) tm2 *= 2;
             ch->tmem_cols = tm2;
@@ -2673,7 +2661,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     for (int p = 0; p < L.nplanes; ++p) U.planes[p] = L.planes[p];
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
     U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.fuse = ch.fuse; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
-    U.folded = ch.folded; U.ksplit = ch.ksplit;
+    U.folded = ch.folded; U.ksplit = ch.ksplit; U.epi2 = ch.epi2;
     {   // A/B switches of the folded kernel: WUN_FOLD_COMPACT (bit 0: one-row converter passes), WUN_FOLD_PREFETCH (bit 1: L2 prefetch)
         static const int flags = [] {
             const char* a = getenv("WUN_FOLD_COMPACT"); const char* b = getenv("WUN_FOLD_PREFETCH");

@@ -48,6 +48,7 @@ struct UmmaLaunch {
     int epilogue;
     int batch;
     int pairC;              // > 0: pair-merged classes (launch.h OutView::pairC); the bias repeats with this period
+    int epi2;               // persistent dgrad: two epilogue warp groups (and two converter teams) - plane_conv_umma_persistent_dg2
 };
 
 constexpr int kUmmaMaxPackJobs = kMaxClasses * kUmmaMaxSplit;
@@ -74,6 +75,7 @@ struct UmmaPackLaunch {
 struct UmmaChoice {         // tiling decisions for one ConvLaunch
     int NPAD, nsplit, MT, rows_alloc, tmem_cols, TB, nbs, persistent, nteams, fuse;
     int folded, ksplit;     // batch-folded cluster split-K kernel (sparse launches)
+    int epi2;               // see UmmaLaunch
     size_t pack_bytes;      // arena bytes the packed weights of this launch need
 };
 

@@ -60,11 +60,6 @@ struct OutView {
     const float* saved2;
     int acc_lo2, acc_hi2;
     int lo_h[2], hi_h[2];
-    // LeakyReLU sign masks (1 bit per element, bit (e & 7) of byte (e >> 3), e = element offset from `base` / `base2`):
-    //   mask / mask2   forward launches: the epilogue also stores the sign bits of what it writes (null = do not);
-    //   smask / smask2 dgrad launches: when non-null the slope is read from these bits instead of from `saved` / `saved2`.
-    uint8_t *mask, *mask2;
-    const uint8_t *smask, *smask2;
 };
 
 struct Term {

@@ -50,7 +50,6 @@ static int add_tensor(Plan* p, const std::string& name, int64_t rows, int C, boo
     t.name = name; t.rows = rows; t.C = C; t.per_batch = per_batch; t.training_only = training_only;
     p->tensors.push_back(t);
     p->grad_twin.push_back(-2);
-    p->mask_twin.push_back(-2);
     return (int)p->tensors.size() - 1;
 }
 
@@ -59,17 +58,6 @@ static int add_act(Plan* p, const std::string& name, int64_t rows, int C) {
     int g = add_tensor(p, "g_" + name, rows, C, true, true);
     p->grad_twin[t] = g;
     return t;
-}
-
-// LeakyReLU sign mask of a saved activation: bit (e & 7) of byte (e >> 3) for element offset e = (b*rows + row)*C + c.  The dgrad
-// epilogue needs only the SIGN of the saved output (slope 1 or 0.2); reading 1 bit instead of 4 bytes per element takes the
-// dependent DRAM read-back out of it (measured upper bound: -0.4 ms of the 6.1 ms M4 batch-16 step).
-static void add_mask(Plan* p, int t) {
-    const TensorSpec& ts = p->tensors[t];
-    if (ts.C % 8 != 0 || ts.rows <= 0) return;
-    const int64_t floats = (ts.rows * ts.C / 8 + 3) / 4;          // bytes -> fp32 slots of the workspace
-    const int m = add_tensor(p, "mask_" + ts.name, floats, 1, true, true);
-    p->mask_twin[t] = m;
 }
 
 static void sort_terms(ClassSpec* c) {
@@ -187,8 +175,6 @@ int build_plan(const WunConfig& cfg, int64_t t_in_frames, Plan* P, std::string* 
     for (int i = 0; i < L; ++i) {
         t_dec[i] = add_act(P, "dec" + std::to_string(i), Td[i], F0 * (i + 1));
         t_odd[i] = add_act(P, "odd" + std::to_string(i), std::max(0, mo_hi[i] - mo_lo[i]), F0 * (i + 1));
-        add_mask(P, t_dec[i]);
-        add_mask(P, t_odd[i]);
     }
     const int t_z = add_act(P, "z", Tb, F0 * (L + 1));
     for (int i = 0; i < L; ++i) t_up[i] = add_act(P, "up" + std::to_string(i), Nup[i + 1], F0 * (L - i));

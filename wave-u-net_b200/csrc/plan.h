@@ -71,7 +71,6 @@ struct Plan {
     std::vector<int> out_w_param, out_b_param;
     std::vector<TensorSpec> tensors;
     std::vector<int> grad_twin;          // tensor id -> id of its gradient tensor (or -2)
-    std::vector<int> mask_twin;          // tensor id -> id of its LeakyReLU sign-mask tensor (1 bit per element, training only) or -2
     std::vector<ConvOp> down, up;        // L each
     ConvOp bottleneck;
     std::vector<UpsampleSpec> ups;
