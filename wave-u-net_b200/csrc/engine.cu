@@ -633,11 +633,11 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
         ++h->launches;
         const size_t split_need = h->bulk_wgrad ? umma_plan_wgrad_split(U, 1, nullptr, nullptr, nullptr) : 0;
         const bool bulk = split_need > 0;                 // 0: too many distinct views for one split pass -> converter-fed kernel
-        // WUN_SPLIT_COLSUM=1: bias column sums inside the split pass instead of their own launches.  Isolated, the wgrad family
-        // is 10 % faster that way (2.38 vs 2.66 ms at M4 B=16), but the whole step was 0.05 ms slower in the same-box A/B (the
-        // small colsum launches fill SMs the big-shared-memory kernels leave thread slots on), so it stays optional.
-        // WUN_SPLIT_COLSUM=2: fused only for the layers with few rows (their colsum launches are pure launch latency on the wgrad stream)
-        static const int colsum_mode = [] { const char* e = getenv("WUN_SPLIT_COLSUM"); return e ? atoi(e) : 0; }();
+        // Bias column sums inside the split pass instead of their own launches (WUN_SPLIT_COLSUM: 1 = default, 0 = separate colsum
+        // launches, 2 = fused only for the layers with few rows).  History: while the dgrad chain was the critical path the separate
+        // launches were 0.05 ms faster per step (they fill SMs the big-shared-memory kernels leave thread slots on); since the epilogue
+        // work of round 2 the wgrad stream is the critical path and the fused form wins (5.45 -> 5.39 ms, wgrad family 2.52 -> 2.24 ms).
+        static const int colsum_mode = [] { const char* e = getenv("WUN_SPLIT_COLSUM"); return e ? atoi(e) : 1; }();
         int max_rows_g = 0;
         for (const auto& dp : class_dpre) max_rows_g = std::max(max_rows_g, dp.r_hi - dp.r_lo);
         const bool fused_colsum = colsum_mode == 1 || (colsum_mode == 2 && max_rows_g <= 4096);

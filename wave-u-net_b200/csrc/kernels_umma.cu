@@ -508,8 +508,11 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 if (tid == 0) T_ADD(7, T_NOW() - t_fill);
             }
         }
-        // ===================== epilogue (team 0: TMEM lane quarter = warp id) =====================
-        if (team == 0) {
+        // ===================== epilogue (teams 0 and 1: TMEM lane quarter = warp & 3) =====================
+        // Both teams are idle once their slabs are converted, and the epilogue is instruction-issue bound: the
+        // two teams split the 16-column chunks of every staged block between them (same rows, disjoint columns).
+        if (team < L.epi_teams) {
+        const int q4 = warp & 3, eg = (L.epi_teams == 2) ? team : 2;       // eg 2 = the only group: every chunk
         if (tid == 0) { T_WAIT(8, mbar_wait_bg(BAR(ACC_FULL), 0)); }
         else mbar_wait_bg(BAR(ACC_FULL), 0);
         tc_fence_after();
@@ -523,22 +526,28 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
         float* stage = reinterpret_cast<float*>(smem);
         const int CW = (NPAD < 128) ? NPAD : 128;          // columns staged at a time
         const int SW = CW + 4;                              // padded row stride (floats): conflict-free float4 rows
+        // each team owns a FIXED column range of the staging tile (its k-th chunk of any block goes to stage_ofs + 16k): the split
+        // of a block's chunks differs from block to block, and a team that runs ahead must never overwrite staged data the
+        // other team has not written out yet
+        const int stage_ofs = (eg == 1) ? 16 * (((CW >> 4) + 1) >> 1) : 0;
         for (int mt = 0; mt < L.MT; ++mt) {
             for (int c0 = 0; c0 < NPAD; c0 += CW) {
                 if (n0 + c0 >= L.N) break;
                 const int cw = min(CW, NPAD - c0);
+                const int nch_blk = (cw + 15) >> 4;
+                const int cb_lo = (eg == 1) ? 16 * ((nch_blk + 1) >> 1) : 0, cb_hi = (eg == 0) ? 16 * ((nch_blk + 1) >> 1) : 16 * nch_blk;
                 // phase 1: thread = accumulator row (TMEM lane)
-                for (int cb = 0; cb < cw; cb += 16) {
+                for (int cb = cb_lo; cb < cb_hi; cb += 16) {
                     __syncwarp();
                     float v[16];
                     if (L.fuse) {
                         float v2[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 2 * NPAD + c0 + cb), v);
-                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 2 * NPAD + NPAD + c0 + cb), v2);
+                        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * 2 * NPAD + c0 + cb), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * 2 * NPAD + NPAD + c0 + cb), v2);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += v2[j];
                     } else {
-                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + c0 + cb), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * NPAD + c0 + cb), v);
                     }
                     if (!any_group) {
 #pragma unroll
@@ -551,7 +560,7 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                             v[j] = fmaxf(0.2f * y, y);
                         }
                     }
-                    float4* dst = reinterpret_cast<float4*>(stage + (size_t)(warp * 32 + lane) * SW + cb);
+                    float4* dst = reinterpret_cast<float4*>(stage + (size_t)(q4 * 32 + lane) * SW + stage_ofs + (cb - cb_lo));
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
@@ -559,27 +568,30 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 // phase 2: each warp writes out the 32 rows it staged itself (no block barrier needed); lanes run over
                 // (row, 4-column quad) pairs so that narrow layers (N = 24..48) still use every lane and a whole warp
                 // store covers several consecutive rows
-                const int ncols = min(cw, L.N - (n0 + c0));
-                const long long tile_off = (long long)b * K.out.bstride + n0 + c0;
+                const int ncols = min(cb_hi, L.N - (n0 + c0)) - cb_lo;      // real columns of this team's share
+                if (ncols > 0) {
+                const long long tile_off = (long long)b * K.out.bstride + n0 + c0 + cb_lo;
                 const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
+                const float* stage_g = stage + stage_ofs;
                 if (vec) {      // (pair-merged classes always take this path: the planner checks both views)
-                    const EpiBlock EB = epi_block<true>(K.out, b, n0 + c0, ncols >> 2, L.epilogue == EPI_SLOPE);
-                    if (DG) epi_write_rows_vec(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, EB);
-                    else epi_write_rows_simple(stage, SW, warp * 32, lane, ncols >> 2, m_base + mt * 128 + warp * 32, EB);
+                    const EpiBlock EB = epi_block<true>(K.out, b, n0 + c0 + cb_lo, ncols >> 2, L.epilogue == EPI_SLOPE);
+                    if (DG) epi_write_rows_vec(stage_g, SW, q4 * 32, lane, ncols >> 2, m_base + mt * 128 + q4 * 32, EB);
+                    else epi_write_rows_simple(stage_g, SW, q4 * 32, lane, ncols >> 2, m_base + mt * 128 + q4 * 32, EB);
                 } else {
                     for (int it = lane; it < 32 * ncols; it += 32) {
                         const int rl = it / ncols, j = it - rl * ncols;
-                        const int r = warp * 32 + rl;
+                        const int r = q4 * 32 + rl;
                         const int m = m_base + mt * 128 + r;
                         if (m >= K.out.m_hi) continue;
                         const long long roff = tile_off + (long long)m * K.out.rstride;
-                        float o = stage[(size_t)r * SW + j];
+                        float o = stage_g[(size_t)r * SW + j];
                         if (L.epilogue == EPI_SLOPE && K.out.saved) o *= (__ldg(K.out.saved + roff + j) > 0.f) ? 1.f : 0.2f;
                         float* dst = K.out.base + roff + j;
                         if (m >= K.out.acc_lo && m < K.out.acc_hi) o += *dst;
                         *dst = o;
                     }
+                }
                 }
                 __syncwarp();                                     // the warp-private staging rows are overwritten by the next block
             }
@@ -929,6 +941,9 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
         // ===================== epilogue warps: TMEM lane quarter = warp & 3 =====================
         const int q4 = warp & 3;
         const int eg = (warp - kEpiWarp0) >> 2;                // epilogue group (0 .. EPW-1)
+        // each group owns a FIXED column range of the staging tile (its k-th chunk of any block goes to stage_ofs + 16k): the chunk
+        // split differs between column blocks, and a group that runs ahead must never overwrite data the other has not written out
+        const int stage_ofs = (EPW == 2 && eg == 1) ? 16 * (((CW >> 4) + 1) >> 1) : 0;
         int k = 0;
         float o_lsum = 0.f;                                    // OUTL: this thread's share of the squared error
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
@@ -1010,7 +1025,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                                     v[j] = fmaxf(0.2f * y, y);
                                 }
                             }
-                            float4* dst = reinterpret_cast<float4*>(stage + (size_t)(q4 * 32 + lane) * SW + cb);
+                            float4* dst = reinterpret_cast<float4*>(stage + (size_t)(q4 * 32 + lane) * SW + stage_ofs + (cb - cb_lo));
 #pragma unroll
                             for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                             if (OUTL) {                      // 1x1 output convs: feature part of [crop(mix) || features] . W
@@ -1116,7 +1131,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                         const bool vec = (ncols % 4 == 0) && (K.out.rstride % 4 == 0) && (((n0 + c0) & 3) == 0) &&
                                          ((reinterpret_cast<uintptr_t>(K.out.base) & 15) == 0) && ((K.out.bstride & 3) == 0);
                         const EpiBlock EB = epi_block<true>(K.out, tc.b, n0 + c0 + cb_lo, ncols >> 2, L.epilogue == EPI_SLOPE);
-                        const float* stage_g = stage + cb_lo;
+                        const float* stage_g = stage + stage_ofs;
                         if (vec) {
                             if (DG) epi_write_rows_vec(stage_g, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, EB);
                             else epi_write_rows_simple(stage_g, SW, q4 * 32, lane, ncols >> 2, tc.m_base + mt * 128 + q4 * 32, EB);
@@ -1215,9 +1230,12 @@ template <int PT, bool DG>
 __global__ void __launch_bounds__(PT * 128 + 192, 1) plane_conv_umma_persistent(const __grid_constant__ UmmaLaunch L, int total_tiles) {
     persistent_body<PT, DG, 0, 1>(L, total_tiles, nullptr);
 }
-// dgrad with two epilogue warp groups and two converter teams (UmmaLaunch::epi2)
+// two epilogue warp groups and two converter teams (UmmaLaunch::epi2): the dgrad launches, optionally the forward ones
 __global__ void __launch_bounds__(2 * 128 + 64 + 256, 1) plane_conv_umma_persistent_dg2(const __grid_constant__ UmmaLaunch L, int total_tiles) {
     persistent_body<2, true, 0, 2>(L, total_tiles, nullptr);
+}
+__global__ void __launch_bounds__(2 * 128 + 64 + 256, 1) plane_conv_umma_persistent_fw2(const __grid_constant__ UmmaLaunch L, int total_tiles) {
+    persistent_body<2, false, 0, 2>(L, total_tiles, nullptr);
 }
 // the last up block's forward conv with the output layer, the loss and the output layer's backward in its epilogue (OutputFuse);
 // NCOL = nconv * C of the output convs
@@ -1659,6 +1677,7 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream, con
         if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<4>, 220 * 1024);
         if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_out<6>, 220 * 1024);
         if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_dg2, 220 * 1024);
+        if (e0 == cudaSuccess) e0 = set_smem_limit(plane_conv_umma_persistent_fw2, 220 * 1024);
         if (e0 != cudaSuccess) return e0;
         cudaError_t e = set_smem_limit(plane_conv_umma_kernel<2, false>, 200 * 1024);
         if (e == cudaSuccess) e = set_smem_limit(plane_conv_umma_kernel<2, true>, 200 * 1024);
@@ -1698,9 +1717,10 @@ cudaError_t launch_plane_conv_umma(const UmmaLaunch& L, cudaStream_t stream, con
             }
             return cudaGetLastError();
         }
-        if (dg && L.epi2) {
+        if (L.epi2 && !fuse) {
             if (L.nteams != 2) return cudaErrorInvalidValue;
-            plane_conv_umma_persistent_dg2<<<grid, 2 * 128 + 64 + 256, smem, stream>>>(L, total);
+            if (dg) plane_conv_umma_persistent_dg2<<<grid, 2 * 128 + 64 + 256, smem, stream>>>(L, total);
+            else plane_conv_umma_persistent_fw2<<<grid, 2 * 128 + 64 + 256, smem, stream>>>(L, total);
             return cudaGetLastError();
         }
         if (L.nteams == 3) {
@@ -2618,7 +2638,8 @@ bool umma_plan_from_conv(const ConvLaunch& L, UmmaChoice* ch) {
             }
             {   // dgrad: two epilogue warp groups + two converter teams (WUN_EPI2=0: one group, three teams)
                 const char* enve = getenv("WUN_EPI2");
-                ch->epi2 = (L.epilogue == EPI_SLOPE && !(enve && enve[0] == '0')) ? 1 : 0;
+                const char* envf = getenv("WUN_EPI2_FWD");          // forward launches too (experiment; the fused-output conv keeps one group)
+                ch->epi2 = ((L.epilogue == EPI_SLOPE && !(enve && enve[0] == '0')) || (L.epilogue != EPI_SLOPE && envf && envf[0] == '1')) ? 1 : 0;
                 if (ch->epi2) ch->nteams = 2;
             }
             // one CTA per SM: a deeper weight ring fits next to the slab stages and the epilogue staging tile
@@ -2662,6 +2683,7 @@ cudaError_t umma_build(const ConvLaunch& L, const UmmaChoice& ch, uint8_t* arena
     U.ncls = L.ncls; U.N = L.N; U.NPAD = ch.NPAD; U.nsplit = ch.nsplit; U.MT = ch.MT; U.rows_alloc = ch.rows_alloc;
     U.tmem_cols = ch.tmem_cols; U.TB = ch.TB; U.nbs = ch.nbs; U.persistent = ch.persistent; U.nteams = ch.nteams; U.fuse = ch.fuse; U.bias = L.bias; U.epilogue = L.epilogue; U.batch = L.batch;
     U.folded = ch.folded; U.ksplit = ch.ksplit; U.epi2 = ch.epi2;
+    { static const int et = [] { const char* e = getenv("WUN_EPI_TEAMS"); return (e && e[0] == '1') ? 1 : 2; }(); U.epi_teams = et; }
     {   // A/B switches of the folded kernel: WUN_FOLD_COMPACT (bit 0: one-row converter passes), WUN_FOLD_PREFETCH (bit 1: L2 prefetch)
         static const int flags = [] {
             const char* a = getenv("WUN_FOLD_COMPACT"); const char* b = getenv("WUN_FOLD_PREFETCH");

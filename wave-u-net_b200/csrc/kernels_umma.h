@@ -49,6 +49,7 @@ struct UmmaLaunch {
     int batch;
     int pairC;              // > 0: pair-merged classes (launch.h OutView::pairC); the bias repeats with this period
     int epi2;               // persistent dgrad: two epilogue warp groups (and two converter teams) - plane_conv_umma_persistent_dg2
+    int epi_teams;          // 2-CTA / sparse kernel: converter teams that share the epilogue (2; WUN_EPI_TEAMS=1 = team 0 alone)
 };
 
 constexpr int kUmmaMaxPackJobs = kMaxClasses * kUmmaMaxSplit;
