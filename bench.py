@@ -422,14 +422,24 @@ def dp_check(run):
     tgs = [torch.empty_like(tg_l) for _ in range(world)]
     dist.all_gather(mixes, mix_l)
     dist.all_gather(tgs, tg_l)
-    rel = None
+    rel = rel_sum = None
     if run.rank == 0:
+        # (b1) communication alone: the same shards, each at the per-rank batch size, summed on ONE GPU - identical kernels, so only
+        #      the summation order of the all-reduce differs (fp32 noise)
+        g_sum = torch.zeros_like(g_dp)
+        for m_r, t_r in zip(mixes, tgs):
+            sep.loss_and_gradients(m_r.contiguous(), t_r.contiguous(), grad_scale=1.0 / world)
+            g_sum += sep.grads
+        rel_sum = float(((g_dp - g_sum).double().norm() / g_sum.double().norm()).item())
+        # (b2) the concatenated batch in one call: other tilings (the planner's choices depend on the batch), so a pre-activation
+        #      within rounding noise of zero can take the other LeakyReLU slope - the bar is the parity tests' 1e-3 (tests/test_gpu_parity.py)
         sep.loss_and_gradients(torch.cat(mixes, 0).contiguous(), torch.cat(tgs, 1).contiguous(), grad_scale=1.0)
         g_one = sep.grads
         rel = float(((g_dp - g_one).double().norm() / g_one.double().norm()).item())
     dist.barrier()
-    return {"replicas_identical_after_adam": identical, "allreduced_grad_vs_single_gpu_rel_l2": rel,
-            "windows_per_rank": nb, "ok": bool(identical and (rel is None or rel < 1e-4))}
+    return {"replicas_identical_after_adam": identical, "allreduced_grad_vs_sum_of_shard_grads_rel_l2": rel_sum,
+            "allreduced_grad_vs_single_gpu_rel_l2": rel, "windows_per_rank": nb,
+            "ok": bool(identical and (rel is None or (rel < 1e-3 and rel_sum < 1e-5)))}
 
 
 def predict_bench(rank, world, dev, dist, reps=2):

@@ -8,7 +8,13 @@ F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppre
 for v in "$@"; do
   case $v in
     eb8) D="-DWUN_EPI_BATCH=8";;
+    krb2) D="-DWUN_KRB=2";;
+    krb4) D="-DWUN_KRB=4";;
+    eb1) D="-DWUN_EPI_BATCH=1";;
     eb2) D="-DWUN_EPI_BATCH=2";;
+    eb4) D="-DWUN_EPI_BATCH=4";;
+    eb3) D="-DWUN_EPI_BATCH=3";;
+    eb6) D="-DWUN_EPI_BATCH=6";;
     noslope) D="-DWUN_EXP_NOSLOPE";;
     *) echo "unknown variant $v"; exit 1;;
   esac

@@ -63,6 +63,13 @@ struct WunHandle {
     int debug_iters = 0;                 // > 0: wun_debug_run_conv - pack once, enqueue the conv kernel this many times
     // weight-gradient kernels run on an internal side stream, concurrently with the dgrad chain on the caller's stream
     cudaStream_t side = nullptr;
+    // A dgrad with two launches (the up blocks: skip pair and upsampled pair have different widths) runs the second one on this
+    // helper stream, concurrently with the first: both read the same gradient planes and write different tensors, and in the deep
+    // layers neither fills the GPU (WUN_DGRAD_PAR=0 disables)
+    cudaStream_t side2 = nullptr;
+    std::vector<cudaEvent_t> par_events;      // fork / join pairs, one pair per use inside a call (graph capture needs distinct events)
+    int par_used = 0;
+    bool dgrad_par = true;
     std::vector<cudaEvent_t> fork_events;
     cudaEvent_t join_event = nullptr;
     int fork_used = 0;
@@ -503,6 +510,17 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
     }
     // classes may differ in channel count (skip vs upsampled planes): launch per distinct N
     std::vector<int> done(L.ncls, 0);
+    int n_launched = 0;
+    cudaEvent_t ev_fork = nullptr;          // recorded on the caller's stream before the first launch (see `par` below)
+    if (h->dgrad_par && !h->dry && h->phase != 1 && h->use_side && h->side != nullptr && h->debug_iters == 0 && !h->packs_pending && L.ncls > 2) {
+        while ((int)h->par_events.size() < h->par_used + 2) {
+            cudaEvent_t e;
+            WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->par_events.push_back(e);
+        }
+        ev_fork = h->par_events[h->par_used];
+        WUN_CUDA_OK(cudaEventRecord(ev_fork, h->stream));
+    }
     for (int k = 0; k < L.ncls; ++k) {
         if (done[k]) continue;
         const int N = op.planes[ob.dgrad[k].plane].C;
@@ -540,9 +558,34 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
                 if (pair_on && !ch0.folded && pair_worthwhile(h, M, ch)) S = M;
             }
         }
+        // second (third ...) launch of this dgrad: on the helper stream, forked from the point the first launch was enqueued at
+        const bool par = ev_fork != nullptr && n_launched > 0 && !h->dry && h->phase != 1 && h->use_side && h->side != nullptr &&
+                         h->debug_iters == 0 && !h->packs_pending;
+        cudaStream_t main_stream = h->stream;
+        cudaEvent_t ev_join = nullptr;
+        if (par) {
+            if (!h->side2) WUN_CUDA_OK(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+            while ((int)h->par_events.size() < h->par_used + 2) {
+                cudaEvent_t e;
+                WUN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->par_events.push_back(e);
+            }
+            ev_join = h->par_events[h->par_used + 1];
+            WUN_CUDA_OK(cudaStreamWaitEvent(h->side2, ev_fork, 0));
+            h->stream = h->side2;
+        }
         int rc = launch_conv(h, S);
         h->pack_floor = 0;
+        if (par) {
+            h->stream = main_stream;
+            if (rc == WUN_OK) {
+                WUN_CUDA_OK(cudaEventRecord(ev_join, h->side2));
+                WUN_CUDA_OK(cudaStreamWaitEvent(main_stream, ev_join, 0));
+            }
+            h->par_used += 2;
+        }
         if (rc != WUN_OK) return rc;
+        ++n_launched;
     }
     return WUN_OK;
 }
@@ -879,7 +922,7 @@ static int begin_call(WunHandle* h, const float* params, const float* mix, int64
     h->dry = dry;
     h->launches = 0;
     h->batch = (int)batch;
-    h->bw_grads = nullptr; h->bw_scale = 1.f; h->fuse_out = nullptr; h->out_fused = false;
+    h->bw_grads = nullptr; h->bw_scale = 1.f; h->fuse_out = nullptr; h->out_fused = false; h->par_used = 0;
     if (dry) return WUN_OK;
     { int rc0 = check_device(); if (rc0 != WUN_OK) return rc0; }
     if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
@@ -924,6 +967,7 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* v = getenv("WUN_PACK_EVENTS"); h->pack_events_on = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_PAIR_DGRAD"); h->pair_dgrad = v ? atoi(v) : 4; }
+    { const char* v = getenv("WUN_DGRAD_PAR"); h->dgrad_par = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_PAIR_MIN_CTAS"); h->pair_min_ctas = v ? atoi(v) : 120; }
     { const char* v = getenv("WUN_OUT_FUSE"); h->out_fuse_mode = v ? atoi(v) : 1; }
     { const char* v = getenv("WUN_PAIR_FWD"); h->pair_fwd = !(v && v[0] == '0'); }
@@ -951,6 +995,8 @@ int wun_destroy(WunHandle* h) {
         for (auto e : h->pack_events) cudaEventDestroy(e);
         for (auto e : h->bucket_events) cudaEventDestroy(e);
         if (h->side) cudaStreamDestroy(h->side);
+        if (h->side2) cudaStreamDestroy(h->side2);
+        for (auto e : h->par_events) cudaEventDestroy(e);
         delete h;
     }
     return WUN_OK;

@@ -289,8 +289,11 @@ __device__ __forceinline__ bool group_is_empty(const UmmaLaunch& L, const UmmaGr
 // destination (dgrad) are issued for kEpiBatch items BEFORE any of them is used: the dgrad epilogue is a chain of dependent
 // global loads (measured: down1 dgrad 410 us with one load in flight per lane vs 175 us for the forward of the same layer,
 // whose epilogue only stores), so memory-level parallelism is what it needs.
+#ifndef WUN_KRB
+#define WUN_KRB 3            // slab rows a converter thread loads before converting any (loads in flight per thread)
+#endif
 #ifndef WUN_EPI_BATCH
-#define WUN_EPI_BATCH 4
+#define WUN_EPI_BATCH 2      // measured with the lean addressing (same box, ms/step): 6 -> 5.82, 4 -> 5.38, 3 -> 5.23, 2 -> 5.21
 #endif
 constexpr int kEpiBatch = WUN_EPI_BATCH;
 // forward launches (nothing to read back) keep the straight loop; the two forms live in separate kernel instantiations
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(NTEAMS * 128 + 64, (NTEAMS == 2) ? 2 : 1) plan
                 const long long t_fill = T_NOW();
                 // Loads of up to kRB rows per thread are issued together and BEFORE the stage-free wait, so their
                 // latency overlaps the wait; only the convert + st.shared part needs the stage.
-                constexpr int kRB = 3;
+                constexpr int kRB = WUN_KRB;
                 bool waited = false;
                 for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
                     float x[kRB][16];
@@ -813,7 +816,7 @@ __device__ __forceinline__ void persistent_body(const UmmaLaunch& L, int total_t
                     const int st = jg % kSlabStages;
                     uint8_t* S = slab0 + st * slab_bytes;
                     const uint32_t atom_stride = 16u * L.rows_alloc;
-                    constexpr int kRB = 3;
+                    constexpr int kRB = WUN_KRB;
                     bool waited = false;
                     for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
                         float x[kRB][16];
@@ -1353,7 +1356,7 @@ __global__ void __launch_bounds__(kFoldTeams * 128 + 64, 1) plane_conv_umma_fold
                 uint8_t* Sl = slab0 + st * slab_bytes;
                 const uint32_t atom_stride = 16u * L.rows_alloc;
                 if (!(L.fold_flags & 1)) {
-                constexpr int kRB = 3;
+                constexpr int kRB = WUN_KRB;
                 bool waited = false;
                 for (int rbase = 0; rbase < L.rows_alloc; rbase += kRB * kWorkerThreads) {
                     float x[kRB][16];
