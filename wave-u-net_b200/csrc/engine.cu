@@ -91,6 +91,14 @@ struct WunHandle {
                                          // 3 up blocks only, 4 (default) down blocks whose merged width still takes the fused-N MMAs (2C <= 64)
     size_t split_item_bytes = 0;         // per batch item: largest split arena any layer's wgrad needs (dry run)
     cudaStream_t wstream = nullptr;      // stream the wgrad-side launches go to (side or main)
+    // split passes run one layer AHEAD of the wgrad kernels, on their own stream, into a double-buffered arena: the split pass is
+    // DRAM-bound, the wgrad kernel L2 / tensor bound, so they overlap well (WUN_SPLIT_AHEAD=0: same stream, one arena half)
+    cudaStream_t split_stream = nullptr;
+    std::vector<cudaEvent_t> split_done, wg_done;
+    int wg_index = 0;
+    bool split_ahead = true;
+    cudaEvent_t first_done = nullptr;     // first-layer weight gradient on the split stream
+    bool first_pending = false;
     // weight packs are hoisted off the critical path: phase 1 enqueues every pack kernel of the step on the side stream
     // (they only depend on the parameters), phase 2 enqueues everything else; phase 0 = inline (inference, debug hook)
     int phase = 0;
@@ -590,6 +598,10 @@ static int conv_dgrad(WunHandle* h, const ConvOp& op, const OpBackward& ob, int 
     return WUN_OK;
 }
 
+static int64_t split_arena_half_bytes(const WunHandle* h, int64_t batch) {
+    return (int64_t)h->split_item_bytes * batch + 256 * (kSplitMaxJobs + 1);
+}
+
 static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale, int layer_index) {
     const Plan& P = h->plan;
     h->cur_layer = layer_index;
@@ -604,7 +616,15 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
                 FW.dW = grads + P.params[op.w_param].offset;
                 FW.db = grads + P.params[op.b_param].offset;
                 FW.scale = scale; FW.rows_per_cta = 0;
-                launch_first_wgrad(FW, P.cfg.num_channels, op.cout, h->wstream);
+                // the CUDA-core first-layer gradient is the tail of the step: on the split stream it runs next to the second
+                // block's tensor-core wgrad instead of behind it (joined at the end of run_backward)
+                const bool tail_par = h->split_ahead && h->split_stream != nullptr && h->wstream != h->stream;
+                launch_first_wgrad(FW, P.cfg.num_channels, op.cout, tail_par ? h->split_stream : h->wstream);
+                if (tail_par) {
+                    if (!h->first_done) WUN_CUDA_OK(cudaEventCreateWithFlags(&h->first_done, cudaEventDisableTiming));
+                    WUN_CUDA_OK(cudaEventRecord(h->first_done, h->split_stream));
+                    h->first_pending = true;
+                }
             }
             return WUN_OK;
         }
@@ -689,7 +709,9 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
         if (!h->dry) {
             cudaError_t e;
             if (bulk) {
+                const bool ahead = h->split_ahead && h->split_stream != nullptr && h->wstream != h->stream;
                 uint8_t* arena = reinterpret_cast<uint8_t*>(h->ws + h->lay.total) + h->arena_sum;
+                if (ahead && (h->wg_index & 1)) arena += split_arena_half_bytes(h, h->batch);
                 arena += (256 - (reinterpret_cast<uintptr_t>(arena) & 255)) & 255;
                 WgSplit S; SplitJobs J;
                 umma_plan_wgrad_split(U, h->batch, arena, &S, &J);
@@ -701,8 +723,24 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
                         if (memcmp(&J.job[j].V, &dp, sizeof(PlaneView)) == 0) { J.job[j].colsum = bias_grad; ++matched; break; }
                 if (!fused_colsum) for (int j = 0; j < J.njobs; ++j) J.job[j].colsum = nullptr;
                 if (matched != class_dpre.size()) return set_err(WUN_E_INVALID, "wgrad split pass: class gradient view not among the split jobs");
-                e = launch_split_views(J, h->wstream);      // same stream as the wgrad: the arena is reused layer after layer
-                if (e == cudaSuccess) e = launch_wgrad_umma_bulk(U, S, h->wstream);
+                if (ahead) {
+                    const int k = h->wg_index++;
+                    while ((int)h->split_done.size() <= k) {
+                        cudaEvent_t e1, e2;
+                        WUN_CUDA_OK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+                        WUN_CUDA_OK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+                        h->split_done.push_back(e1); h->wg_done.push_back(e2);
+                    }
+                    if (k >= 2) WUN_CUDA_OK(cudaStreamWaitEvent(h->split_stream, h->wg_done[k - 2], 0));     // its arena half is free again
+                    e = launch_split_views(J, h->split_stream);
+                    if (e == cudaSuccess) e = cudaEventRecord(h->split_done[k], h->split_stream);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->wstream, h->split_done[k], 0);
+                    if (e == cudaSuccess) e = launch_wgrad_umma_bulk(U, S, h->wstream);
+                    if (e == cudaSuccess) e = cudaEventRecord(h->wg_done[k], h->wstream);
+                } else {
+                    e = launch_split_views(J, h->wstream);      // same stream as the wgrad: the arena is reused layer after layer
+                    if (e == cudaSuccess) e = launch_wgrad_umma_bulk(U, S, h->wstream);
+                }
             } else {
                 e = launch_wgrad_umma(U, h->wstream);
             }
@@ -738,6 +776,10 @@ static int fork_side(WunHandle* h) {
     cudaEvent_t ev = h->fork_events[h->fork_used++];
     WUN_CUDA_OK(cudaEventRecord(ev, h->stream));
     WUN_CUDA_OK(cudaStreamWaitEvent(h->side, ev, 0));
+    if (h->split_ahead) {
+        if (!h->split_stream) WUN_CUDA_OK(cudaStreamCreateWithFlags(&h->split_stream, cudaStreamNonBlocking));
+        WUN_CUDA_OK(cudaStreamWaitEvent(h->split_stream, ev, 0));
+    }
     return WUN_OK;
 }
 
@@ -894,6 +936,7 @@ static int run_backward(WunHandle* h, const float* targets, float* grads, float 
     if (!h->dry && h->phase != 1 && h->wstream != h->stream) {       // join: the caller's stream continues only after all wgrads
         WUN_CUDA_OK(cudaEventRecord(h->join_event, h->side));
         WUN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->join_event, 0));
+        if (h->first_pending) { WUN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->first_done, 0)); h->first_pending = false; }
     }
     if ((rc = mark_grads_ready(h, 0, h->stream)) != WUN_OK) return rc;    // whatever is left: final after the join
     return WUN_OK;
@@ -911,7 +954,7 @@ static int check_device() {
 
 // bytes of the split arena behind the weight packs (bulk-fed wgrad only; per-item size from the dry run at create time)
 static int64_t split_arena_bytes(const WunHandle* h, int64_t batch) {
-    return (h && h->bulk_wgrad && h->split_item_bytes) ? (int64_t)h->split_item_bytes * batch + 256 * (kSplitMaxJobs + 1) : 0;
+    return (h && h->bulk_wgrad && h->split_item_bytes) ? 2 * ((int64_t)h->split_item_bytes * batch + 256 * (kSplitMaxJobs + 1)) : 0;     // two halves
 }
 
 static int begin_call(WunHandle* h, const float* params, const float* mix, int64_t batch, bool training, void* ws,
@@ -922,7 +965,7 @@ static int begin_call(WunHandle* h, const float* params, const float* mix, int64
     h->dry = dry;
     h->launches = 0;
     h->batch = (int)batch;
-    h->bw_grads = nullptr; h->bw_scale = 1.f; h->fuse_out = nullptr; h->out_fused = false; h->par_used = 0;
+    h->bw_grads = nullptr; h->bw_scale = 1.f; h->fuse_out = nullptr; h->out_fused = false; h->par_used = 0; h->wg_index = 0; h->first_pending = false;
     if (dry) return WUN_OK;
     { int rc0 = check_device(); if (rc0 != WUN_OK) return rc0; }
     if (!params || !mix || !ws) return set_err(WUN_E_INVALID, "null device pointer");
@@ -968,6 +1011,7 @@ int wun_create_for_input(const WunConfig* cfg, int64_t input_frames, WunHandle**
     { const char* v = getenv("WUN_BULK_WGRAD"); h->bulk_wgrad = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_PAIR_DGRAD"); h->pair_dgrad = v ? atoi(v) : 4; }
     { const char* v = getenv("WUN_DGRAD_PAR"); h->dgrad_par = !(v && v[0] == '0'); }
+    { const char* v = getenv("WUN_SPLIT_AHEAD"); h->split_ahead = !(v && v[0] == '0'); }
     { const char* v = getenv("WUN_PAIR_MIN_CTAS"); h->pair_min_ctas = v ? atoi(v) : 120; }
     { const char* v = getenv("WUN_OUT_FUSE"); h->out_fuse_mode = v ? atoi(v) : 1; }
     { const char* v = getenv("WUN_PAIR_FWD"); h->pair_fwd = !(v && v[0] == '0'); }
@@ -996,6 +1040,10 @@ int wun_destroy(WunHandle* h) {
         for (auto e : h->bucket_events) cudaEventDestroy(e);
         if (h->side) cudaStreamDestroy(h->side);
         if (h->side2) cudaStreamDestroy(h->side2);
+        if (h->split_stream) cudaStreamDestroy(h->split_stream);
+        for (auto e : h->split_done) cudaEventDestroy(e);
+        for (auto e : h->wg_done) cudaEventDestroy(e);
+        if (h->first_done) cudaEventDestroy(h->first_done);
         for (auto e : h->par_events) cudaEventDestroy(e);
         delete h;
     }

@@ -290,7 +290,7 @@ __device__ __forceinline__ bool group_is_empty(const UmmaLaunch& L, const UmmaGr
 // global loads (measured: down1 dgrad 410 us with one load in flight per lane vs 175 us for the forward of the same layer,
 // whose epilogue only stores), so memory-level parallelism is what it needs.
 #ifndef WUN_KRB
-#define WUN_KRB 3            // slab rows a converter thread loads before converting any (loads in flight per thread)
+#define WUN_KRB 2            // slab rows a converter thread loads before converting any; measured (ms/step, same box): 4 -> 5.31, 3 -> 5.12, 2 -> 5.09
 #endif
 #ifndef WUN_EPI_BATCH
 #define WUN_EPI_BATCH 2      // measured with the lean addressing (same box, ms/step): 6 -> 5.82, 4 -> 5.38, 3 -> 5.23, 2 -> 5.21
