@@ -498,7 +498,7 @@ def run_ours(args, rank, world, local_rank):
         clocks.start()                       # samples are time-stamped; only those inside the timed region are reported
     run = TrainingRun(PRESET, BATCH_PER_GPU, BATCH_PER_GPU * world, rank, world, dev, dist, overlap=not args.no_overlap)
     graphed = run.prepare(use_graph=not args.no_graph)
-    ms_total, t_begin, t_end = run.time_steps(args.steps, args.warmup, prewarm_s=1.5)
+    ms_total, t_begin, t_end = run.time_steps(args.steps, args.warmup, prewarm_s=0.0 if args.no_prewarm else 1.5)
     clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     e_steps = max(3, min(args.steps, 10))
     e2e = run.e2e(e_steps, args.warmup)
@@ -529,7 +529,7 @@ def run_ours(args, rank, world, local_rank):
                    "global_batch": run.B * world, "parallelism": "dp%d" % world,
                    "l2_policy": "per-step working set (~1.2 GB activations + gradients) exceeds the 126 MB L2",
                    "cuda_graph": graphed, "cuda_graph_error": run.graph_error,
-                   "untimed_prewarm_steps": int(1.5 / 0.006),
+                   "untimed_prewarm_steps": 0 if args.no_prewarm else int(1.5 / 0.006),
                    "allreduce": (("bucketed (%d buckets) on a comm stream, overlapped with backward" % len(run.ar.views))
                                  if run.ar is not None else "one flat all-reduce after backward") if world > 1 else None,
                    "arithmetic": "fp32 in/out; tensor-core layers split every fp32 operand into bf16 hi+lo and issue "
@@ -630,6 +630,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: one flat all-reduce after backward")
     ap.add_argument("--no-extras", action="store_true", help="skip the M5 / M6 / Predict measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prewarm", action="store_true", help="skip the untimed pre-warm replays (profiler runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

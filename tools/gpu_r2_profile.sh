@@ -5,6 +5,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "=== gpu tests"
 timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+echo "=== warm-up bench (discarded)"
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > /dev/null 2>&1
 echo "=== bench (full line)"
 timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 tail -2 gpurun_out/r2_bench_n1.err
@@ -18,12 +20,12 @@ print("cpu", d.get("cpu_baseline"))
 PY
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/r2_launches_bench_step.csv \
-   python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-extras > gpurun_out/r2_ncu_bench.log 2>&1
+   python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-extras --no-prewarm > gpurun_out/r2_ncu_bench.log 2>&1
 python tools/launch_summary.py gpurun_out/r2_launches_bench_step.csv > gpurun_out/r2_launches_bench_step_summary.txt 2>&1
 head -30 gpurun_out/r2_launches_bench_step_summary.txt
 echo "=== ncu --set full"
-timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -c 14 -o gpurun_out/r2_full -f \
-   python tools/profile_passes.py ${PASSES:-1:2 3:2 1:1 3:0 8:0 22:1} > gpurun_out/r2_ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -c 16 -o gpurun_out/r2_full -f \
+   python tools/profile_passes.py ${PASSES:-1:2 3:2 1:1 3:0 8:0 24:1} > gpurun_out/r2_ncu_full.log 2>&1
 tail -8 gpurun_out/r2_ncu_full.log
 ncu -i gpurun_out/r2_full.ncu-rep --page raw --csv > gpurun_out/r2_full_raw.csv 2>/dev/null
 ls -la gpurun_out | head -30

@@ -618,7 +618,8 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
                 FW.scale = scale; FW.rows_per_cta = 0;
                 // the CUDA-core first-layer gradient is the tail of the step: on the split stream it runs next to the second
                 // block's tensor-core wgrad instead of behind it (joined at the end of run_backward)
-                const bool tail_par = h->split_ahead && h->split_stream != nullptr && h->wstream != h->stream;
+                static const bool tail_on = [] { const char* e = getenv("WUN_FIRST_TAIL"); return !(e && e[0] == '0'); }();
+                const bool tail_par = tail_on && h->split_ahead && h->split_stream != nullptr && h->wstream != h->stream;
                 launch_first_wgrad(FW, P.cfg.num_channels, op.cout, tail_par ? h->split_stream : h->wstream);
                 if (tail_par) {
                     if (!h->first_done) WUN_CUDA_OK(cudaEventCreateWithFlags(&h->first_done, cudaEventDisableTiming));
