@@ -614,10 +614,22 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "host_logical_cpus": r["host_logical_cpus"],
                                     "host_physical_cores": r["host_physical_cores"], "sample": r["sample"]}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    # Teardown.  The step graph holds captured NCCL kernels: it goes first, then the process group.  A watchdog ends the process if
+    # the teardown itself gets stuck (seen once at N=2: both workers idle after rank 0 had printed its line, until the caller's
+    # timeout) - the measurement is complete and printed at this point.
+    watchdog = threading.Timer(45.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        run.graph = None
+        run.ar = None
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    finally:
+        watchdog.cancel()
 
 
 def main():
