@@ -194,6 +194,25 @@ def test_plan_audit_matches_the_measured_configuration():
     assert len({d["layer"] for d in lines if d["op"] == "wgrad"}) == 24
 
 
+def test_round2_planner_decisions_for_the_benchmark():
+    """What bench.py times at M4 batch 16: pair-merged forward classes for the up blocks that still fill the GPU,
+    the pair-merged dgrad only where the merged width keeps the fused-N MMAs (down1), the output layer riding in the last up
+    block's persistent forward conv - and no forward merge / fused output at batch 1, where those launches do not fill the GPU."""
+    lines = [d for d in _audit("baseline_stereo", 16) if d["op"] == "conv"]
+    fwd = {d["layer"]: d for d in lines if d["pass"] == 0}
+    dg = [d for d in lines if d["pass"] == 1]
+    assert sorted(l for l, d in fwd.items() if d["pair"]) == [21, 22, 23, 24]            # up8 .. up11
+    assert all(fwd[l]["N"] == 2 * fwd[l]["pair"] for l in (21, 22, 23, 24))
+    assert [(d["layer"], d["N"]) for d in dg if d["pair"]] == [(1, 48)]                    # down1: 2 x 24 columns, fused-N
+    assert [d["layer"] for d in lines if d.get("outfuse")] == [24] and fwd[24]["kernel"] == "persistent"
+    assert sum(1 for d in dg if d["kernel"] == "persistent") >= 6
+    small = [d for d in _audit("baseline_stereo", 1) if d["op"] == "conv"]
+    assert not any((d["pair"] and d["pass"] == 0) or d.get("outfuse") for d in small)       # (down1's dgrad still has 144 tiles at batch 1)
+    # every model family of BASELINE.json gets the fused output layer at its benchmark batch
+    for preset, batch in (("full", 16), ("full_multi_instrument", 32), ("baseline", 16)):
+        assert any(d.get("outfuse") for d in _audit(preset, batch) if d["op"] == "conv"), preset
+
+
 def test_long_window_mode_plans_and_amortises_the_context():
     """any num_frames builds a plan (engines are cached per input length); the 131054-frame context of M4 is
     paid once per window, so live FLOPs per OUTPUT frame fall as the window grows."""
