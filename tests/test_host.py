@@ -146,7 +146,7 @@ def _audit(preset, batch, overrides=None):
 
 
 @pytest.mark.parametrize("preset", ["baseline", "baseline_context", "baseline_stereo", "full", "full_multi_instrument", "full_44KHz"])
-@pytest.mark.parametrize("batch", [1, 2, 4, 16, 32])
+@pytest.mark.parametrize("batch", [1, 2, 4, 8, 16, 32])
 def test_planned_tcgen05_launches_respect_hardware_limits(preset, batch):
     lines = _audit(preset, batch)
     convs = [d for d in lines if d["op"] == "conv"]
@@ -164,6 +164,12 @@ def test_planned_tcgen05_launches_respect_hardware_limits(preset, batch):
         assert d["nteams"] == {"dense2": 2, "sparse4": 4}.get(d["kernel"], d["nteams"]) and d["nteams"] in (2, 3, 4), d
         assert d["smem"] <= SMEM_LIMIT[d["kernel"]], d
         assert d["tiles"] >= 1 and d["span"] <= 24, d
+        if d["pair"]:                                      # pair-merged class: two halves of `pair` columns, never the folded kernel
+            assert d["N"] == 2 * d["pair"] and d["pair"] % 4 == 0 and d["N"] <= 256 and d["kernel"] != "fold", d
+        if d["epi2"]:                                      # two epilogue groups: the persistent dgrad with two converter teams
+            assert d["kernel"] == "persistent" and d["pass"] == 1 and d["nteams"] == 2, d
+        if d["outfuse"]:                                   # output layer in the epilogue: persistent forward conv, one column block
+            assert d["kernel"] == "persistent" and d["pass"] == 0 and d["nteams"] == 3 and d["NPAD"] <= 128 and d["nsplit"] == 1, d
         if d["kernel"] == "fold":                          # cluster of ksplit CTAs per tile: portable size, one wave of clusters
             assert 1 <= d["ksplit"] <= 8 and d["tiles"] <= [0, 148, 74, 45, 33, 26, 22, 15, 15][d["ksplit"]], d   # tools/cluster_probe on B200
             assert d["nteams"] == 4 and not d["fuse"], d

@@ -294,11 +294,11 @@ static int launch_conv(WunHandle* h, const ConvLaunch& L) {
                 }
                 char line[512];
                 snprintf(line, sizeof(line), "conv layer=%d pass=%d kernel=%s N=%d NPAD=%d nsplit=%d MT=%d rows_alloc=%d span=%d tmem=%d "
-                         "TB=%d nbs=%d nteams=%d fuse=%d ksplit=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu pair=%d outfuse=%d",
+                         "TB=%d nbs=%d nteams=%d fuse=%d ksplit=%d tiles=%lld mmas=%lld max_rows=%d smem=%zu pack_bytes=%zu pair=%d outfuse=%d epi2=%d",
                          h->cur_layer, h->cur_pass, ch.folded ? "fold" : (ch.persistent ? "persistent" : (ch.nteams == 4 ? "sparse4" : "dense2")), L.N,
                          ch.NPAD, ch.nsplit, ch.MT, ch.rows_alloc, span, ch.tmem_cols, ch.TB, ch.nbs, ch.nteams, ch.fuse, ch.ksplit, tiles, mmas,
                          max_rows, umma_choice_smem_bytes(ch), ch.pack_bytes, L.pairC,
-                         (h->fuse_out && umma_output_fusable(L, ch, h->fuse_out->O)) ? 1 : 0);
+                         (h->fuse_out && umma_output_fusable(L, ch, h->fuse_out->O)) ? 1 : 0, ch.epi2);
                 h->audit->push_back(line);
             }
             return WUN_OK;
