@@ -18,7 +18,10 @@
  *     WUN_E_NOTIMPL mirrors the reference's NotImplementedError (:136, :144), WUN_E_SHAPE its
  *     AssertionError (:55, :121, Utils.py:114-117).
  *   - no hidden synchronisation, allocation or host<->device copy inside forward / backward / adam:
- *     everything is enqueued on `stream`, so a whole step can be captured in a CUDA graph.
+ *     everything is enqueued on `stream` - or, in wun_forward_backward, on internal streams of the handle that are forked
+ *     from `stream` and joined back into it with events before the call returns (weight-gradient kernels, the split passes
+ *     that feed them one layer ahead, the second launch of an up block's dgrad) - so a whole step can be captured in a
+ *     CUDA graph.  The workspace pointers are baked into such a graph: keep the workspace alive as long as the graph.
  */
 #ifndef WUN_H
 #define WUN_H

@@ -17,9 +17,20 @@
 //   * B operand (weights): pre-packed once per optimizer step into the exact K-step streaming order, hi/lo
 //     bf16, core-matrix layout; streamed with cp.async.bulk (UBLKCP) through an mbarrier ring.
 //   * accumulators: MT row tiles x NPAD fp32 columns in TMEM; epilogue tcgen05.ld -> bias/LeakyReLU (fwd)
-//     or LeakyReLU-slope / accumulate (dgrad) -> global.
-// Warp roles: warps 0-3 converter + epilogue (TMEM lane quarter = warp id), warp 4 TMEM alloc + MMA issue
-// (one elected lane), warp 5 weight loader (one elected lane).
+//     or LeakyReLU-slope / accumulate (dgrad) -> a shared-memory staging tile -> coalesced global stores.
+// Kernels in this file:
+//   plane_conv_umma_kernel<NTEAMS, DG>       one 128/256-row tile per CTA; 2 CTAs per SM (NTEAMS = 2) or one with 4 converter teams;
+//                                            both converter teams share the epilogue
+//   plane_conv_umma_persistent<PT, DG>       one CTA per SM loops over tiles, double-buffered TMEM accumulators, dedicated epilogue warps;
+//   plane_conv_umma_persistent_dg2           its dgrad form with two epilogue warp groups; plane_conv_umma_persistent_out<NCOL>: its
+//                                            forward form with the output layer + loss + dL/dpre + feature gradient in the epilogue
+//   plane_conv_umma_fold                     batch-folded row tiles + split-K over a thread-block cluster (deep, few-row layers)
+//   split_views_kernel, wgrad_umma_bulk_kernel   hi/lo split arrays of a layer's wgrad operands (+ bias column sums) and the
+//                                            bulk-copy-fed tcgen05 wgrad;  wgrad_umma_kernel<CW>: the converter-fed form (A/B switch)
+//   umma_pack_kernel                         fp32 weights -> hi/lo bf16 blocks in K-step streaming order (pair-merged classes: two taps
+//                                            side by side per row shift)
+// Warp roles of the conv kernels: converter teams of 4 warps (slab fill), one warp = TMEM alloc + single-thread MMA issue (elect.sync),
+// one warp = weight loader (cp.async.bulk through an mbarrier ring), epilogue warps (TMEM lane quarter = warp & 3).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
