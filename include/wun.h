@@ -181,6 +181,10 @@ int64_t wun_describe(const WunHandle* h, char* buf, int64_t capacity);
  * tiling the planner picks (kernel variant, NPAD, tile height, TMEM columns, ring depth, dynamic shared memory, grid) -
  * tests/test_host.py checks every preset against the hardware limits.  Returns the bytes the full text needs. */
 int64_t wun_debug_plan(const WunHandle* h, int64_t batch, char* buf, int64_t capacity);
+/* The same dry run, but the FULL description of every plane-convolution launch (planes, classes incl. pair-merged halves, terms)
+ * as text, with addresses relative to fake bases (workspace 1 << 40, parameters 1 << 41, mix 1 << 42).  Host-only; the numpy
+ * interpreter of tests/test_launch_semantics.py checks the planner's launch algebra with it. */
+int64_t wun_debug_launches(const WunHandle* h, int64_t batch, char* buf, int64_t capacity);
 /* Where a saved activation / activation-gradient lives inside the caller's workspace (tests: per-layer parity).
  * Names: dec<i>, odd<i> (live even / odd rows of down block i), z (bottleneck), up<i>, and g_<name> twins. */
 int wun_debug_tensor(const WunHandle* h, const char* name, int64_t batch, int training, int64_t* offset_floats,

@@ -1,0 +1,170 @@
+"""Host-only check of the planner's launch algebra (no GPU): the engine exports the full description of every plane-convolution
+launch of a training step (wun_debug_launches: planes, classes, terms - csrc/launch.h), and a numpy interpreter executes those
+descriptions on a random workspace.  A pair-merged launch (launch.h OutView::pairC: two classes of equal width issued as one class
+of 2C columns, round 2) must write exactly what the two-class form of the same launch writes - forward (bias + LeakyReLU with the
+bias repeated per half) and dgrad (slope from the saved activation, skip-window accumulate ranges, per-half row ranges), for
+context ('valid'), 'same'-padding and learned-upsampling nets.  The interpreter follows plane_conv_kernel (csrc/kernels_simt.cu),
+the exact-fp32 reference form of a ConvLaunch."""
+import numpy as np
+import pytest
+
+import Config
+import wun
+from oracle import wave_unet_oracle as O
+
+WS_BASE, PAR_BASE, MIX_BASE = 1 << 40, 1 << 41, 1 << 42
+SLACK = 1 << 38
+
+
+def decode(addr):
+    """raw exported address -> (buffer name, element offset); offsets may be negative (views that start before their tensor)."""
+    if addr >= MIX_BASE - SLACK:
+        return "mix", (addr - MIX_BASE) // 4
+    if addr >= PAR_BASE - SLACK:
+        return "par", (addr - PAR_BASE) // 4
+    return "ws", (addr - WS_BASE) // 4
+
+
+def plane_rows(mem, P, b, rows):
+    """[len(rows), C] float64: plane rows `rows` of batch item b, zero outside [r_lo, r_hi); MID planes blend two tensor rows
+    (plane_load, kernels_simt.cu)."""
+    name, base = decode(P["base"])
+    buf = mem[name]
+    C = P["C"]
+    out = np.zeros((len(rows), C))
+    ok = (rows >= P["r_lo"]) & (rows < P["r_hi"])
+    r = rows[ok]
+    idx = base + b * P["bstride"] + r[:, None] * P["rstride"] + np.arange(C)[None, :]
+    x = buf[idx]
+    if P["kind"] == 1:                                   # PLANE_MID
+        if P["mid_mode"] == 0:                           # MID_VALID: r + 1 always exists
+            nx = buf[idx + P["rstride"]]
+        else:
+            has_next = (r + 1 < P["xrows"])[:, None]
+            nxt = buf[np.where(has_next, idx + P["rstride"], idx)]
+            nx = np.where(has_next, nxt, x if P["mid_mode"] == 1 else 0.0)      # MID_CLAMP / MID_ZERO
+        if P["blend"] >= 0:
+            bname, boff = decode(P["blend"])
+            w = mem[bname][boff + np.arange(C)][None, :]
+            x = w * x + (1.0 - w) * nx
+        else:
+            x = x + (nx - x) * 0.5
+    out[ok] = x
+    return out
+
+
+def run_launch(mem, D):
+    """Execute one exported ConvLaunch on mem = {"ws", "par", "mix"} (float64 arrays); writes go to mem["ws"]."""
+    L, planes, classes, terms = D["launch"], D["planes"], D["cls"], D["terms"]
+    N, pairC = L["N"], L["pairC"]
+    wname, wbase = decode(L["W"])
+    W = mem[wname]
+    ws = mem["ws"]
+    for q in classes:
+        if q["m_hi"] <= q["m_lo"]:
+            continue
+        rows = np.arange(q["m_lo"], q["m_hi"])
+        for b in range(L["batch"]):
+            acc = np.zeros((len(rows), N))
+            for t in terms[q["term_begin"]:q["term_end"]]:
+                P = planes[t["plane"]]
+                X = plane_rows(mem, P, b, rows + t["d"])
+                Wt = np.zeros((P["C"], N))
+                c = np.arange(P["C"])[:, None]
+                if pairC == 0:
+                    Wt[:] = W[wbase + t["woff"] + c * L["w_sk"] + np.arange(N)[None, :] * L["w_sn"]]
+                else:
+                    n = np.arange(pairC)[None, :]
+                    if t["woff"] >= 0:
+                        Wt[:, :pairC] = W[wbase + t["woff"] + c * L["w_sk"] + n * L["w_sn"]]
+                    if t["woff2"] >= 0:
+                        Wt[:, pairC:] = W[wbase + t["woff2"] + c * L["w_sk"] + n * L["w_sn"]]
+                acc += X @ Wt
+            halves = [(0, N, q["base"], q["bstride"], q["rstride"], q["saved"], q["acc_lo"], q["acc_hi"], q["m_lo"], q["m_hi"])]
+            if pairC > 0:
+                assert q["pairC"] == pairC and N == 2 * pairC
+                halves = [(0, pairC, q["base"], q["bstride"], q["rstride"], q["saved"], q["acc_lo"], q["acc_hi"], q["lo0"], q["hi0"]),
+                          (pairC, N, q["base2"], q["bstride2"], q["rstride2"], q["saved2"], q["acc_lo2"], q["acc_hi2"], q["lo1"], q["hi1"])]
+            for (n0, n1, base, bstride, rstride, saved, acc_lo, acc_hi, lo, hi) in halves:
+                sel = (rows >= lo) & (rows < hi)
+                m = rows[sel]
+                v = acc[sel][:, n0:n1].copy()
+                _, dbase = decode(base)
+                didx = dbase + b * bstride + m[:, None] * rstride + np.arange(n1 - n0)[None, :]
+                if L["epilogue"] == 0:                                   # EPI_BIAS_LRELU
+                    if L["bias"] >= 0:
+                        bname, boff = decode(L["bias"])
+                        v += mem[bname][boff + np.arange(n1 - n0)][None, :]      # pair: the bias repeats per half
+                    v = np.maximum(0.2 * v, v)
+                elif L["epilogue"] == 1 and saved >= 0:                  # EPI_SLOPE
+                    sname, sbase = decode(saved)
+                    sidx = sbase + b * bstride + m[:, None] * rstride + np.arange(n1 - n0)[None, :]
+                    v *= np.where(mem[sname][sidx] > 0.0, 1.0, 0.2)
+                accum = ((m >= acc_lo) & (m < acc_hi))[:, None]
+                v = np.where(accum, v + ws[didx], v)
+                ws[didx] = v
+
+
+CASES = [
+    ("context_stereo", ["baseline_stereo"], dict(num_layers=4), 2, 700),
+    ("same_padding_mono", ["baseline"], dict(num_layers=4), 2, 512),
+    ("learned_upsampling", ["full"], dict(num_layers=3, num_initial_filters=16), 2, 500),
+    ("same_learned_stereo", ["baseline_diff"], dict(num_layers=3, upsampling="learned", mono_downmix=False), 3, 256),
+]
+
+
+@pytest.mark.parametrize("name,named,ov,batch,nf", CASES, ids=[c[0] for c in CASES])
+def test_pair_merged_launches_compute_what_the_two_class_launches_do(name, named, ov, batch, nf, monkeypatch):
+    cfg = Config.build_config(named, ov, experiment_id=0)["model_config"]
+    t_in, _ = O.get_padding(cfg, nf)
+    wcfg = wun.config_from_model_config(cfg)
+    for k, v in (("WUN_FOLD", "0"), ("WUN_PAIR_FWD", "0"), ("WUN_PAIR_DGRAD", "0")):
+        monkeypatch.setenv(k, v)
+    plain = wun.Engine(wcfg, input_frames=t_in)
+    LA = plain.launch_descriptions(batch)
+    for k, v in (("WUN_PAIR_FWD", "1"), ("WUN_PAIR_DGRAD", "1"), ("WUN_PAIR_MIN_CTAS", "1")):
+        monkeypatch.setenv(k, v)
+    merged = wun.Engine(wcfg, input_frames=t_in)
+    LB = merged.launch_descriptions(batch)
+    assert [(d["launch"]["layer"], d["launch"]["pass"]) for d in LA] == [(d["launch"]["layer"], d["launch"]["pass"]) for d in LB]
+    n_pair_fwd = sum(1 for d in LB if d["launch"]["pairC"] and d["launch"]["pass"] == 0)
+    n_pair_dg = sum(1 for d in LB if d["launch"]["pairC"] and d["launch"]["pass"] == 1)
+    assert n_pair_fwd >= 2 and n_pair_dg >= 2, (n_pair_fwd, n_pair_dg)
+    assert not any(d["launch"]["pairC"] for d in LA)
+
+    rng = np.random.default_rng(5)
+    n_ws = plain.workspace_bytes(batch, True) // 4
+    margin = 1 << 14                                     # views may start a few rows before their tensor: keep indices in range
+    mem0 = {"ws": rng.standard_normal(n_ws + 2 * margin), "par": rng.standard_normal(plain.param_numel + 64) * 0.1,
+            "mix": rng.standard_normal(batch * t_in * wcfg.num_channels + 64)}
+    # sigmoid(interp) blend vectors live in the workspace: keep them in (0, 1) like the engine does - any value tests the algebra
+    checked = 0
+    for a, b in zip(LA, LB):
+        if not b["launch"]["pairC"]:
+            continue
+        ma = {k: v.copy() for k, v in mem0.items()}
+        mb = {k: v.copy() for k, v in mem0.items()}
+        for m in (ma, mb):                               # shift the workspace so that small negative offsets stay valid
+            m["ws"] = m["ws"][margin:]
+        run_launch(ma, a)
+        run_launch(mb, b)
+        changed = np.flatnonzero(ma["ws"] != mem0["ws"][margin:])
+        assert changed.size > 0, a["launch"]
+        np.testing.assert_allclose(mb["ws"], ma["ws"], rtol=1e-9, atol=1e-9, err_msg=str(a["launch"]))
+        checked += 1
+    assert checked == n_pair_fwd + n_pair_dg
+
+
+def test_exported_launches_cover_the_step():
+    """One forward + one dgrad description per tensor-core conv layer (the first layer has its own kernels), in execution order."""
+    cfg = Config.build_config(["baseline_stereo"], dict(num_layers=3), experiment_id=0)["model_config"]
+    t_in, _ = O.get_padding(cfg, 300)
+    eng = wun.Engine(wun.config_from_model_config(cfg), input_frames=t_in)
+    L = eng.launch_descriptions(2)
+    fwd = [d["launch"]["layer"] for d in L if d["launch"]["pass"] == 0]
+    assert fwd == list(range(1, 2 * 3 + 1))
+    dg_layers = sorted({d["launch"]["layer"] for d in L if d["launch"]["pass"] == 1})
+    assert dg_layers == list(range(1, 2 * 3 + 1))        # no input gradient for the first layer
+    for d in L:
+        assert len(d["planes"]) == d["launch"]["nplanes"] and len(d["cls"]) == d["launch"]["ncls"]
+        assert all(0 <= t["plane"] < d["launch"]["nplanes"] for t in d["terms"])

@@ -114,6 +114,7 @@ struct WunHandle {
     std::vector<cudaEvent_t> pack_events;
     int pack_idx = 0;                    // forward tensor-core conv counter of the current phase
     std::vector<std::string>* audit = nullptr;   // dry runs: one line per tensor-core launch (wun_debug_plan)
+    std::vector<std::string>* export_launches = nullptr;   // dry runs: the full description of every plane-convolution launch (wun_debug_launches)
     // data-parallel overlap: gradient buckets in PRODUCTION order (output layer first, down0 last); bucket k = flat offsets
     // >= bucket_first[k] (and below bucket k-1's).  bucket_events[k] is recorded once every gradient of the bucket is final.
     std::vector<int64_t> bucket_first;
@@ -256,8 +257,41 @@ static long long view_bstride(const WunHandle* h, const ViewSpec& v) {
     return rows * C;
 }
 
+// wun_debug_launches: one plane-convolution launch as text (addresses are raw integers relative to the fake bases the dry run
+// installs: workspace 1 << 40, parameters 1 << 41, mix 1 << 42 - nothing is dereferenced).  tests/test_launch_semantics.py
+// interprets these descriptions in numpy: the pair-merged form of a launch must compute exactly what its two-class form does.
+static void export_launch(WunHandle* h, const ConvLaunch& L) {
+    char line[768];
+    auto addr = [](const void* p) { return (long long)reinterpret_cast<uintptr_t>(p); };
+    snprintf(line, sizeof(line), "launch layer=%d pass=%d N=%d pairC=%d w_sk=%d w_sn=%d W=%lld bias=%lld epilogue=%d batch=%d nplanes=%d ncls=%d",
+             h->cur_layer, h->cur_pass, L.N, L.pairC, L.w_sk, L.w_sn, addr(L.W), L.bias ? addr(L.bias) : -1LL, L.epilogue, L.batch, L.nplanes, L.ncls);
+    h->export_launches->push_back(line);
+    for (int p = 0; p < L.nplanes; ++p) {
+        const PlaneView& P = L.planes[p];
+        snprintf(line, sizeof(line), "plane i=%d base=%lld bstride=%lld rstride=%d r_lo=%d r_hi=%d C=%d kind=%d mid_mode=%d xrows=%d blend=%lld",
+                 p, addr(P.base), P.bstride, P.rstride, P.r_lo, P.r_hi, P.C, P.kind, P.mid_mode, P.xrows, P.blend ? addr(P.blend) : -1LL);
+        h->export_launches->push_back(line);
+    }
+    int nterm = 0;
+    for (int q = 0; q < L.ncls; ++q) {
+        const OutView& O = L.cls[q];
+        nterm = std::max(nterm, O.term_end);
+        snprintf(line, sizeof(line), "cls i=%d base=%lld bstride=%lld rstride=%d m_lo=%d m_hi=%d saved=%lld acc_lo=%d acc_hi=%d term_begin=%d term_end=%d "
+                 "pairC=%d base2=%lld bstride2=%lld rstride2=%d saved2=%lld acc_lo2=%d acc_hi2=%d lo0=%d hi0=%d lo1=%d hi1=%d",
+                 q, addr(O.base), O.bstride, O.rstride, O.m_lo, O.m_hi, O.saved ? addr(O.saved) : -1LL, O.acc_lo, O.acc_hi, O.term_begin, O.term_end,
+                 O.pairC, O.pairC ? addr(O.base2) : -1LL, O.bstride2, O.rstride2, (O.pairC && O.saved2) ? addr(O.saved2) : -1LL, O.acc_lo2, O.acc_hi2,
+                 O.lo_h[0], O.hi_h[0], O.lo_h[1], O.hi_h[1]);
+        h->export_launches->push_back(line);
+    }
+    for (int t = 0; t < nterm; ++t) {
+        snprintf(line, sizeof(line), "term i=%d plane=%d d=%d woff=%d woff2=%d", t, L.terms[t].plane, L.terms[t].d, L.terms[t].woff, L.pairC ? L.terms[t].woff2 : -1);
+        h->export_launches->push_back(line);
+    }
+}
+
 // Every plane convolution goes through here: tcgen05 when the launch is eligible, CUDA cores otherwise.
 static int launch_conv(WunHandle* h, const ConvLaunch& L) {
+    if (h->dry && h->export_launches) export_launch(h, L);
     UmmaChoice ch;
     const bool use_umma = h->umma_enabled && h->umma_pass[h->cur_pass] && umma_plan_from_conv(L, &ch);
     const size_t slot = (size_t)h->cur_layer * 3 + h->cur_pass;
@@ -1254,6 +1288,31 @@ int64_t wun_debug_plan(const WunHandle* hc, int64_t batch, char* buf, int64_t ca
     run_forward(h, nullptr, nullptr, nullptr, 1);
     run_backward(h, nullptr, nullptr, 1.f);
     h->audit = nullptr;
+    h->arena_sum = keep_sum; h->arena_bytes = keep_max; h->kernel_used = keep_used;
+    std::string s;
+    for (const auto& l : lines) { s += l; s += "\n"; }
+    if (buf && capacity > 0) {
+        int64_t n = std::min<int64_t>(capacity - 1, (int64_t)s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int64_t wun_debug_launches(const WunHandle* hc, int64_t batch, char* buf, int64_t capacity) {
+    WunHandle* h = const_cast<WunHandle*>(hc);
+    if (!h || batch < 1) return -1;
+    std::vector<std::string> lines;
+    const size_t keep_sum = h->arena_sum, keep_max = h->arena_bytes;
+    const std::vector<std::string> keep_used = h->kernel_used;
+    if (begin_call(h, nullptr, nullptr, batch, true, nullptr, 0, nullptr, true) != WUN_OK) return -1;
+    h->export_launches = &lines; h->phase = 0;
+    // fake, far-apart bases (never dereferenced in a dry run): every exported address identifies its buffer
+    h->ws = reinterpret_cast<float*>((uintptr_t)1 << 40); h->params = reinterpret_cast<const float*>((uintptr_t)1 << 41);
+    h->mix = reinterpret_cast<const float*>((uintptr_t)1 << 42);
+    run_forward(h, nullptr, nullptr, nullptr, 1);
+    run_backward(h, nullptr, nullptr, 1.f);
+    h->export_launches = nullptr; h->ws = nullptr; h->params = nullptr; h->mix = nullptr;
     h->arena_sum = keep_sum; h->arena_bytes = keep_max; h->kernel_used = keep_used;
     std::string s;
     for (const auto& l : lines) { s += l; s += "\n"; }

@@ -18,7 +18,7 @@ SYMBOLS = [
     "wun_forward_flops", "wun_forward_backward_flops", "wun_launches_forward",
     "wun_launches_forward_backward", "wun_forward", "wun_forward_backward", "wun_adam_step", "wun_adam_step_device", "wun_set_grad_buckets", "wun_stream_wait_grad_bucket",
     "wun_gather_windows", "wun_scatter_windows", "wun_feed_batch", "wun_last_error", "wun_version", "wun_describe",
-    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_debug_run_layer", "wun_crc32c", "wun_debug_plan",
+    "wun_layer_kernel", "wun_debug_tensor", "wun_debug_run_conv", "wun_debug_run_layer", "wun_crc32c", "wun_debug_plan", "wun_debug_launches",
 ]
 
 
@@ -83,6 +83,8 @@ def _load():
     lib.wun_layer_kernel.restype = ctypes.c_char_p
     lib.wun_debug_plan.argtypes = [H, I64, ctypes.c_char_p, I64]
     lib.wun_debug_plan.restype = I64
+    lib.wun_debug_launches.argtypes = [H, I64, ctypes.c_char_p, I64]
+    lib.wun_debug_launches.restype = I64
     lib.wun_crc32c.argtypes = [ctypes.c_uint32, VP, ctypes.c_uint64]
     lib.wun_crc32c.restype = ctypes.c_uint32
     return lib
@@ -202,6 +204,24 @@ class Engine(object):
                 k, v = kv.split("=", 1)
                 d[k] = int(v) if v.lstrip("-").isdigit() else v
             out.append(d)
+        return out
+
+    def launch_descriptions(self, batch):
+        """Every plane-convolution launch of a training step at `batch` as a list of dicts {"launch": {...}, "planes": [...],
+        "cls": [...], "terms": [...]} (wun_debug_launches; host only)."""
+        n = lib.wun_debug_launches(self._h, int(batch), None, 0)
+        if n < 0:
+            raise RuntimeError("wun_debug_launches failed: %s" % lib.wun_last_error().decode())
+        buf = ctypes.create_string_buffer(int(n))
+        lib.wun_debug_launches(self._h, int(batch), buf, n)
+        out = []
+        for line in buf.value.decode().splitlines():
+            parts = line.split()
+            d = {k: int(v) for k, v in (kv.split("=", 1) for kv in parts[1:])}
+            if parts[0] == "launch":
+                out.append({"launch": d, "planes": [], "cls": [], "terms": []})
+            else:
+                out[-1][{"plane": "planes", "cls": "cls", "term": "terms"}[parts[0]]].append(d)
         return out
 
     def layer_kernel(self, layer, pass_):
