@@ -168,3 +168,184 @@ def test_exported_launches_cover_the_step():
     for d in L:
         assert len(d["planes"]) == d["launch"]["nplanes"] and len(d["cls"]) == d["launch"]["ncls"]
         assert all(0 <= t["plane"] < d["launch"]["nplanes"] for t in d["terms"])
+
+
+def _tensor_view(eng, name, batch, training=True):
+    import ctypes
+    off, rows, ch = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+    wun.check(wun.lib.wun_debug_tensor(eng._h, name.encode(), int(batch), 1 if training else 0, ctypes.byref(off), ctypes.byref(rows),
+                                       ctypes.byref(ch)))
+    return off.value, rows.value, ch.value
+
+
+FWD_CASES = [
+    ("m4_like", ["baseline_stereo"], dict(num_layers=4), 2, 500),
+    ("m1_like_same_padding", ["baseline"], dict(num_layers=4), 2, 512),
+    ("m5_like_learned", ["full"], dict(num_layers=3, num_initial_filters=16), 2, 400),
+    ("m6_like_multi_instrument", ["full_multi_instrument"], dict(num_layers=3), 2, 300),
+    ("same_learned_stereo", ["baseline_diff"], dict(num_layers=3, upsampling="learned", mono_downmix=False), 2, 256),
+]
+
+
+@pytest.mark.parametrize("pairs", [0, 1], ids=["two_class", "pair_merged"])
+@pytest.mark.parametrize("name,named,ov,batch,nf", FWD_CASES, ids=[c[0] for c in FWD_CASES])
+def test_exported_forward_launches_reproduce_the_oracle(name, named, ov, batch, nf, pairs, monkeypatch):
+    """The planner's forward pass - live rows only, decimation / skip crop / upsampling folded into plane views, pair-merged
+    classes - executed by the numpy interpreter on the host must reproduce every activation the engine keeps (dec_i, odd_i, z,
+    up_i at their live rows, tests/helpers.py) of the oracle's get_output (UnetAudioSeparator.py:97-125) in float64."""
+    import torch
+    from helpers import live_rows
+    for k, v in (("WUN_FIRST_LAYER", "0"), ("WUN_FOLD", "0"), ("WUN_PAIR_FWD", str(pairs)), ("WUN_PAIR_MIN_CTAS", "1")):
+        monkeypatch.setenv(k, v)
+    cfg = Config.build_config(named, ov, experiment_id=0)["model_config"]
+    t_in, t_out = O.get_padding(cfg, nf)
+    params = O.init_params(cfg, seed=3)
+    rng = np.random.default_rng(4)
+    for k in params:
+        if k.endswith("/bias") or "interp" in k:
+            params[k] = rng.uniform(-0.5, 0.5, size=params[k].shape).astype(np.float32)
+    mix, _ = O.synthetic_batch(cfg, batch, t_in, t_out, seed=9)
+    eng = wun.Engine(wun.config_from_model_config(cfg), input_frames=t_in)
+    fwd = [d for d in eng.launch_descriptions(batch) if d["launch"]["pass"] == 0]
+    L = cfg["num_layers"]
+    assert [d["launch"]["layer"] for d in fwd] == list(range(2 * L + 1))           # incl. the first layer (generic path)
+    if pairs:
+        assert any(d["launch"]["pairC"] for d in fwd)
+    par = np.zeros(eng.param_numel + 64)
+    for pname, shape, off, numel in eng.param_table:
+        par[off:off + numel] = np.asarray(params[pname], np.float64).reshape(-1)
+    margin = 1 << 14
+    n_ws = eng.workspace_bytes(batch, True) // 4
+    ws_full = np.zeros(n_ws + 2 * margin)
+    mem = {"ws": ws_full[margin:], "par": par, "mix": np.concatenate([mix.astype(np.float64).reshape(-1), np.zeros(64)])}
+    if cfg["upsampling"] == "learned":                                           # sigmoid(interp_<level>) - launch_sigmoid in the engine
+        for i in range(L):
+            off, rows, ch = _tensor_view(eng, "wsig%d" % i, batch)
+            var = np.asarray(params["separator/interp_%d" % i], np.float64).reshape(-1)
+            mem["ws"][off:off + var.size] = 1.0 / (1.0 + np.exp(-var))
+    for d in fwd:
+        run_launch(mem, d)
+    _, inter = O.forward(cfg, O._as_torch(params, torch.float64, False), torch.as_tensor(mix).to(torch.float64), False,
+                         return_intermediates=True)
+    keys = ["down%d" % i for i in range(L)] + ["bottleneck"] + ["up%d" % i for i in range(L)]
+    checked = 0
+    for idx, views in live_rows(cfg, t_in).items():
+        want_full = inter[keys[idx]].numpy()
+        for tname, rows in views:
+            off, trows, ch = _tensor_view(eng, tname, batch)
+            assert trows == len(rows) and ch == want_full.shape[2], (tname, trows, len(rows))
+            got = mem["ws"][off:off + batch * trows * ch].reshape(batch, trows, ch)
+            np.testing.assert_allclose(got, want_full[:, rows, :], rtol=1e-9, atol=1e-11, err_msg=tname)
+            checked += 1
+    assert checked == 2 * L + 1 + L
+
+
+
+def _upsample_bwd(mem, eng, batch, up_i, L_layers, dg_launches, fwd_launch):
+    """upsample_bwd_kernel (kernels_simt.cu) on the host: gradient w.r.t. the PRE-activation of the tensor that up block `up_i`
+    upsamples, from the gradients w.r.t. its copied rows (g_ue) and interpolated rows (g_mid)."""
+    views = []                                            # (base, bstride, rows) of g_ue and g_mid, from the dgrad launch that wrote them
+    d = dg_launches[-1]                                   # second launch of the layer: the upsampled pair
+    if d["launch"]["pairC"]:
+        q = d["cls"][0]
+        views = [(q["base"], q["bstride"], q["hi0"]), (q["base2"], q["bstride2"], q["hi1"])]
+    else:
+        views = [(q["base"], q["bstride"], q["m_hi"]) for q in d["cls"]]
+    mid = [P for P in fwd_launch["planes"] if P["kind"] == 1][0]
+    C = mid["C"]
+    (ue_base, ue_bs, N), (gm_base, gm_bs, nmid) = views
+    _, ue = decode(ue_base)
+    _, gm = decode(gm_base)
+    src = "z" if up_i == 0 else "up%d" % (up_i - 1)
+    xoff, xrows, xc = _tensor_view(eng, src, batch)
+    goff, _, _ = _tensor_view(eng, "g_" + src, batch)
+    assert xrows == N and xc == C and ue_bs == N * C and gm_bs == nmid * C
+    ws = mem["ws"]
+    w = np.full(C, 0.5)
+    if mid["blend"] >= 0:
+        _, boff = decode(mid["blend"])
+        w = ws[boff:boff + C].copy()
+    for b in range(batch):
+        x = ws[xoff + b * N * C: xoff + (b + 1) * N * C].reshape(N, C)
+        due = ws[ue + b * N * C: ue + (b + 1) * N * C].reshape(N, C)
+        dmid = ws[gm + b * nmid * C: gm + (b + 1) * nmid * C].reshape(nmid, C)
+        dm = np.zeros((N, C)); dm[:nmid] = dmid
+        dmp = np.zeros((N, C)); dmp[1:min(N, nmid + 1)] = dmid[:min(N, nmid + 1) - 1]
+        g = due + w * dm + (1.0 - w) * dmp
+        if mid["mid_mode"] == 1:                          # MID_CLAMP: the last row's "next" row is itself
+            g[N - 1] += (1.0 - w) * dm[N - 1]
+        ws[goff + b * N * C: goff + (b + 1) * N * C] = (g * np.where(x > 0.0, 1.0, 0.2)).reshape(-1)
+
+
+@pytest.mark.parametrize("pairs", [0, 1], ids=["two_class", "pair_merged"])
+@pytest.mark.parametrize("name,named,ov,batch,nf", FWD_CASES, ids=[c[0] for c in FWD_CASES])
+def test_exported_dgrad_chain_reproduces_the_oracle(name, named, ov, batch, nf, pairs, monkeypatch):
+    """The backward data path on the host: starting from the oracle's gradient at the last up block, the exported dgrad launches
+    (roles swapped: class gradients are the planes; skip-window accumulate ranges; row ranges written first by the up block and
+    then by the down block) plus the upsampling backward must reproduce dL/d(pre-activation) of EVERY saved activation at its live
+    rows - torch autograd through the oracle's get_output, float64."""
+    import torch
+    from helpers import live_rows
+    for k, v in (("WUN_FIRST_LAYER", "0"), ("WUN_FOLD", "0"), ("WUN_PAIR_FWD", str(pairs)), ("WUN_PAIR_DGRAD", str(pairs)),
+                 ("WUN_PAIR_MIN_CTAS", "1")):
+        monkeypatch.setenv(k, v)
+    cfg = Config.build_config(named, ov, experiment_id=0)["model_config"]
+    t_in, t_out = O.get_padding(cfg, nf)
+    params = O.init_params(cfg, seed=3)
+    rng = np.random.default_rng(4)
+    for k in params:
+        if k.endswith("/bias") or "interp" in k:
+            params[k] = rng.uniform(-0.5, 0.5, size=params[k].shape).astype(np.float32)
+    mix, targets = O.synthetic_batch(cfg, batch, t_in, t_out, seed=9)
+    eng = wun.Engine(wun.config_from_model_config(cfg), input_frames=t_in)
+    desc = eng.launch_descriptions(batch)
+    fwd = [d for d in desc if d["launch"]["pass"] == 0]
+    dg = [d for d in desc if d["launch"]["pass"] == 1]
+    L = cfg["num_layers"]
+    if pairs:
+        assert any(d["launch"]["pairC"] for d in dg)
+    par = np.zeros(eng.param_numel + 64)
+    for pname, shape, off, numel in eng.param_table:
+        par[off:off + numel] = np.asarray(params[pname], np.float64).reshape(-1)
+    margin = 1 << 14
+    ws_full = np.zeros(eng.workspace_bytes(batch, True) // 4 + 2 * margin)
+    mem = {"ws": ws_full[margin:], "par": par, "mix": np.concatenate([mix.astype(np.float64).reshape(-1), np.zeros(64)])}
+    if cfg["upsampling"] == "learned":
+        for i in range(L):
+            off, rows, ch = _tensor_view(eng, "wsig%d" % i, batch)
+            var = np.asarray(params["separator/interp_%d" % i], np.float64).reshape(-1)
+            mem["ws"][off:off + var.size] = 1.0 / (1.0 + np.exp(-var))
+    for d in fwd:
+        run_launch(mem, d)
+    # oracle: dL/d(pre-activation) of every layer output = autograd gradient w.r.t. the activation x LeakyReLU slope
+    tp = O._as_torch(params, torch.float64, True)
+    outs, inter = O.forward(cfg, tp, torch.as_tensor(mix).to(torch.float64), True, return_intermediates=True)
+    loss = O.mse_loss(cfg, outs, {k: torch.as_tensor(v).to(torch.float64) for k, v in targets.items()})
+    keys = ["down%d" % i for i in range(L)] + ["bottleneck"] + ["up%d" % i for i in range(L)]
+    grads = torch.autograd.grad(loss, [inter[k] for k in keys])
+    dpre = {k: g.detach().numpy() * np.where(inter[k].detach().numpy() > 0.0, 1.0, 0.2) for k, g in zip(keys, grads)}      # (float64 0.2)
+    # seed: the gradient at the features (what output_dgrad / the fused epilogue writes)
+    goff, grows, gch = _tensor_view(eng, "g_up%d" % (L - 1), batch)
+    mem["ws"][goff:goff + batch * grows * gch] = dpre["up%d" % (L - 1)].reshape(-1)
+    # the chain, in the engine's order: up blocks from the last to the first (each followed by the upsampling backward), bottleneck, down blocks
+    by_layer = {}
+    for d in dg:
+        by_layer.setdefault(d["launch"]["layer"], []).append(d)
+    for i in range(L - 1, -1, -1):
+        launches = by_layer[L + 1 + i]
+        for d in launches:
+            run_launch(mem, d)
+        _upsample_bwd(mem, eng, batch, i, L, launches, fwd[L + 1 + i])
+    for layer in range(L, 0, -1):
+        for d in by_layer[layer]:
+            run_launch(mem, d)
+    checked = 0
+    for idx, views in live_rows(cfg, t_in).items():
+        want_full = dpre[keys[idx]]
+        for tname, rows in views:
+            off, trows, ch = _tensor_view(eng, "g_" + tname, batch)
+            got = mem["ws"][off:off + batch * trows * ch].reshape(batch, trows, ch)
+            scale = max(1e-30, float(np.abs(want_full).max()))
+            np.testing.assert_allclose(got / scale, want_full[:, rows, :] / scale, rtol=1e-8, atol=1e-10, err_msg="g_" + tname)
+            checked += 1
+    assert checked == 3 * L + 1
