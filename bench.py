@@ -127,6 +127,50 @@ class ClockSampler(object):
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class LineGuard(object):
+    """Multi-rank runs only.  Once the timed measurement exists, nothing that follows it (per-layer table, DP check, the extra
+    configurations - each holds collectives) may cost the line: if those phases do not finish within `seconds`, rank 0 prints
+    the line as it stood after the last finished phase, with "aborted_in" naming the phase that did not return, and every rank
+    leaves through os._exit (a rank blocked in a collective cannot unwind)."""
+
+    def __init__(self, rank, world, seconds):
+        self.rank, self.active, self.seconds = rank, world > 1, seconds
+        self.lock = threading.Lock()
+        self.snapshot, self.phase, self.done, self.timer = None, None, False, None
+
+    def update(self, line, next_phase):
+        """Record the line as it stands (serialised now - the caller keeps filling it) and the phase that starts next."""
+        if not self.active:
+            return
+        snap = json.dumps(line)
+        with self.lock:
+            self.snapshot, self.phase = snap, next_phase
+        if self.timer is None:
+            self.timer = threading.Timer(self.seconds, self._fire)
+            self.timer.daemon = True
+            self.timer.start()
+
+    def _fire(self):
+        with self.lock:
+            if self.done:
+                return
+            if self.rank == 0 and self.snapshot is not None:
+                d = json.loads(self.snapshot)
+                d["aborted_in"] = self.phase
+                print(json.dumps(d), flush=True)
+            sys.stderr.write("bench.py: rank %d: phase %r did not finish within %.0f s - leaving\n" % (self.rank, self.phase, self.seconds))
+            sys.stderr.flush()
+            os._exit(0)
+
+    def disarm(self):
+        if not self.active:
+            return
+        with self.lock:
+            self.done = True
+        if self.timer is not None:
+            self.timer.cancel()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle restatement; the only place bench.py executes oracle/ compute)
 # ----------------------------------------------------------------------------------------------------------------------
@@ -512,14 +556,6 @@ def run_ours(args, rank, world, local_rank):
     flops = run.eng.forward_backward_flops(run.B)
     step_tf = flops / (ms_step * 1e-3) * 1e-12
 
-    # ---- per-layer / per-family table: every conv layer and pass timed alone (rank 0; the others wait) -----------------
-    rows, fam = None, None
-    if rank == 0:
-        rows, fam = layer_table(run)
-    if world > 1:
-        dist.barrier()
-    dpc = dp_check(run) if world > 1 else None
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -548,6 +584,16 @@ def run_ours(args, rank, world, local_rank):
                           "scope": "whole step: %.1f algorithmic GFLOP (fwd+bwd, live positions) / step time; peak = bf16 "
                                    "sustained, %s; the fp32-accurate 3-MMA scheme caps frac at 1/3" % (flops * 1e-9, peaks["source"])},
     }
+    guard = LineGuard(rank, world, 240.0)
+    guard.update(line, "per-layer table")
+    # ---- per-layer / per-family table: every conv layer and pass timed alone (rank 0; the others wait) -----------------
+    rows, fam = None, None
+    if rank == 0:
+        rows, fam = layer_table(run)
+    if world > 1:
+        dist.barrier()
+    guard.update(line, "dp_check")
+    dpc = dp_check(run) if world > 1 else None
     if dpc is not None:
         line["dp_check"] = dpc
     if rank == 0 and fam:
@@ -581,6 +627,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the other BASELINE.json configurations, briefly, in the same run ----------------------------------------------
     if not args.no_extras:
+        guard.update(line, "extra_configs: M6 full_multi_instrument, global batch 32")
         extras = {}
         del run.graph
         run.graph = None
@@ -599,14 +646,18 @@ def run_ours(args, rank, world, local_rank):
             return out
 
         try:
+            line["extra_configs"] = extras
             if 32 % world == 0:
                 extras["m6_full_multi_instrument_b32"] = train_extra("full_multi_instrument", 32 // world, 32, "strong")
+            guard.update(line, "extra_configs: M5 full, batch 16 per GPU")
             extras["m5_full_learned_b16"] = train_extra("full", 16, 16 * world, "weak")
+            guard.update(line, "extra_configs: Predict 3 min 44.1 kHz")
             extras["predict_3min_44k"] = predict_bench(rank, world, dev, dist)
         except Exception as ex:                                                    # noqa: BLE001
             extras["error"] = "%s: %s" % (type(ex).__name__, str(ex)[:300])
         line["extra_configs"] = extras
 
+    guard.disarm()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cfg = run.cfg
@@ -630,6 +681,12 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
     finally:
         watchdog.cancel()
+    if world > 1:
+        # multi-rank: leave without the interpreter's exit handlers (NCCL / CUDA-graph destructors at shutdown are the other place
+        # a finished run could sit until the launcher's timeout); everything is printed and flushed, the process group is gone.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -277,15 +277,10 @@ def _upsample_bwd(mem, eng, batch, up_i, L_layers, dg_launches, fwd_launch):
         ws[goff + b * N * C: goff + (b + 1) * N * C] = (g * np.where(x > 0.0, 1.0, 0.2)).reshape(-1)
 
 
-@pytest.mark.parametrize("pairs", [0, 1], ids=["two_class", "pair_merged"])
-@pytest.mark.parametrize("name,named,ov,batch,nf", FWD_CASES, ids=[c[0] for c in FWD_CASES])
-def test_exported_dgrad_chain_reproduces_the_oracle(name, named, ov, batch, nf, pairs, monkeypatch):
-    """The backward data path on the host: starting from the oracle's gradient at the last up block, the exported dgrad launches
-    (roles swapped: class gradients are the planes; skip-window accumulate ranges; row ranges written first by the up block and
-    then by the down block) plus the upsampling backward must reproduce dL/d(pre-activation) of EVERY saved activation at its live
-    rows - torch autograd through the oracle's get_output, float64."""
+def _host_backward(named, ov, batch, nf, pairs, monkeypatch):
+    """Forward launches, then the dgrad chain seeded with the oracle's gradient at the last up block, all on the host.
+    Returns (cfg, eng, mem, dpre, param_grads, keys, t_in): dpre / param_grads are torch autograd through the oracle in float64."""
     import torch
-    from helpers import live_rows
     for k, v in (("WUN_FIRST_LAYER", "0"), ("WUN_FOLD", "0"), ("WUN_PAIR_FWD", str(pairs)), ("WUN_PAIR_DGRAD", str(pairs)),
                  ("WUN_PAIR_MIN_CTAS", "1")):
         monkeypatch.setenv(k, v)
@@ -322,8 +317,10 @@ def test_exported_dgrad_chain_reproduces_the_oracle(name, named, ov, batch, nf, 
     outs, inter = O.forward(cfg, tp, torch.as_tensor(mix).to(torch.float64), True, return_intermediates=True)
     loss = O.mse_loss(cfg, outs, {k: torch.as_tensor(v).to(torch.float64) for k, v in targets.items()})
     keys = ["down%d" % i for i in range(L)] + ["bottleneck"] + ["up%d" % i for i in range(L)]
-    grads = torch.autograd.grad(loss, [inter[k] for k in keys])
+    pnames = sorted(tp)
+    grads = torch.autograd.grad(loss, [inter[k] for k in keys] + [tp[k] for k in pnames], allow_unused=True)
     dpre = {k: g.detach().numpy() * np.where(inter[k].detach().numpy() > 0.0, 1.0, 0.2) for k, g in zip(keys, grads)}      # (float64 0.2)
+    param_grads = {k: (None if g is None else g.detach().numpy()) for k, g in zip(pnames, grads[len(keys):])}
     # seed: the gradient at the features (what output_dgrad / the fused epilogue writes)
     goff, grows, gch = _tensor_view(eng, "g_up%d" % (L - 1), batch)
     mem["ws"][goff:goff + batch * grows * gch] = dpre["up%d" % (L - 1)].reshape(-1)
@@ -339,6 +336,19 @@ def test_exported_dgrad_chain_reproduces_the_oracle(name, named, ov, batch, nf, 
     for layer in range(L, 0, -1):
         for d in by_layer[layer]:
             run_launch(mem, d)
+    return cfg, eng, mem, dpre, param_grads, keys, t_in
+
+
+@pytest.mark.parametrize("pairs", [0, 1], ids=["two_class", "pair_merged"])
+@pytest.mark.parametrize("name,named,ov,batch,nf", FWD_CASES, ids=[c[0] for c in FWD_CASES])
+def test_exported_dgrad_chain_reproduces_the_oracle(name, named, ov, batch, nf, pairs, monkeypatch):
+    """The backward data path on the host: starting from the oracle's gradient at the last up block, the exported dgrad launches
+    (roles swapped: class gradients are the planes; skip-window accumulate ranges; row ranges written first by the up block and
+    then by the down block) plus the upsampling backward must reproduce dL/d(pre-activation) of EVERY saved activation at its live
+    rows - torch autograd through the oracle's get_output, float64."""
+    from helpers import live_rows
+    cfg, eng, mem, dpre, _, keys, t_in = _host_backward(named, ov, batch, nf, pairs, monkeypatch)
+    L = cfg["num_layers"]
     checked = 0
     for idx, views in live_rows(cfg, t_in).items():
         want_full = dpre[keys[idx]]
@@ -349,3 +359,52 @@ def test_exported_dgrad_chain_reproduces_the_oracle(name, named, ov, batch, nf, 
             np.testing.assert_allclose(got / scale, want_full[:, rows, :] / scale, rtol=1e-8, atol=1e-10, err_msg="g_" + tname)
             checked += 1
     assert checked == 3 * L + 1
+
+
+def run_wgrad_group(mem, G, dW):
+    """One exported (class, plane) weight-gradient group (launch.h WgradLaunch; plane_wgrad_kernel, kernels_simt.cu):
+    dW[woff_t + c * w_sk + n * w_sn] += sum_{b, m in [m_lo, m_hi)} plane[b, m + d_t, c] * dpre[b, m, n]."""
+    g = G["wgrad"]
+    rows = np.arange(g["m_lo"], g["m_hi"])
+    C, N = G["plane"]["C"], g["N"]
+    c, n = np.arange(C)[:, None], np.arange(N)[None, :]
+    for b in range(g["batch"]):
+        Y = plane_rows(mem, G["dpre"], b, rows)[:, :N]
+        for t in G["terms"]:
+            X = plane_rows(mem, G["plane"], b, rows + t["d"])
+            dW[g["dW"] + t["woff"] + c * g["w_sk"] + n * g["w_sn"]] += X.T @ Y
+
+
+@pytest.mark.parametrize("name,named,ov,batch,nf", FWD_CASES, ids=[c[0] for c in FWD_CASES])
+def test_exported_wgrad_groups_reproduce_the_oracle(name, named, ov, batch, nf, monkeypatch):
+    """The weight-gradient groups the engine builds per layer ((class, plane) pairs with up to 8 taps each - what the split pass
+    and the tcgen05 wgrad kernel consume), executed on the host on the activations and pre-activation gradients the exported
+    forward / dgrad launches produced, must give dL/dW of every convolution; the column sums of each class's gradient view give
+    dL/db (fused into the split pass on the device).  Reference: torch autograd through the oracle (UnetAudioSeparator.py:97-125), float64."""
+    cfg, eng, mem, _, param_grads, keys, t_in = _host_backward(named, ov, batch, nf, 1, monkeypatch)
+    L = cfg["num_layers"]
+    groups = eng.wgrad_groups
+    assert sorted({G["wgrad"]["layer"] for G in groups}) == list(range(2 * L + 1))
+    got = np.zeros(eng.param_numel + 64)
+    seen = set()
+    for G in groups:
+        g = G["wgrad"]
+        assert 1 <= g["nterms"] == len(G["terms"]) <= 8 and g["batch"] == batch
+        assert max(t["d"] for t in G["terms"]) - min(t["d"] for t in G["terms"]) <= 15      # one staged slab serves every tap of the group
+        run_wgrad_group(mem, G, got)
+        key = (g["layer"], G["dpre"]["base"], G["dpre"]["r_lo"], G["dpre"]["r_hi"])
+        if key not in seen:                                                       # bias: once per class
+            seen.add(key)
+            rows = np.arange(g["m_lo"], g["m_hi"])
+            for b in range(batch):
+                got[g["db"]:g["db"] + g["N"]] += plane_rows(mem, G["dpre"], b, rows)[:, :g["N"]].sum(0)
+    conv_offsets = {G["wgrad"]["dW"] for G in groups} | {G["wgrad"]["db"] for G in groups}
+    checked = []
+    for pname, shape, off, numel in eng.param_table:
+        if off not in conv_offsets:
+            continue                                  # interp_<i> and the 1x1 output layer have their own kernels (OutputLayer.py:5-23)
+        want = np.asarray(param_grads[pname], np.float64).reshape(-1)
+        scale = max(1e-30, float(np.abs(want).max()))
+        np.testing.assert_allclose(got[off:off + numel] / scale, want / scale, rtol=1e-8, atol=1e-10, err_msg=pname)
+        checked.append(pname)
+    assert len(checked) == 2 * (2 * L + 1), checked

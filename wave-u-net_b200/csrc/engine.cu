@@ -691,6 +691,28 @@ static int conv_wgrad(WunHandle* h, const ConvOp& op, float* grads, float scale,
             groups.push_back(W);
         }
     }
+    if (h->dry && h->export_launches) {      // wun_debug_launches: the (class, plane) groups of this layer's weight gradient
+        char line[512];
+        auto addr = [](const void* p) { return (long long)reinterpret_cast<uintptr_t>(p); };
+        for (size_t g = 0; g < groups.size(); ++g) {
+            const WgradLaunch& W = groups[g];
+            snprintf(line, sizeof(line), "wgrad layer=%d group=%d N=%d w_sk=%d w_sn=%d dW=%lld db=%lld m_lo=%d m_hi=%d nterms=%d batch=%d",
+                     layer_index, (int)g, W.N, W.w_sk, W.w_sn, (long long)P.params[op.w_param].offset, (long long)P.params[op.b_param].offset,
+                     W.m_lo, W.m_hi, W.nterms, W.batch);
+            h->export_launches->push_back(line);
+            const PlaneView* V[2] = {&W.plane, &W.dpre};
+            for (int k = 0; k < 2; ++k) {
+                snprintf(line, sizeof(line), "%s base=%lld bstride=%lld rstride=%d r_lo=%d r_hi=%d C=%d kind=%d mid_mode=%d xrows=%d blend=%lld",
+                         k == 0 ? "wplane" : "wdpre", addr(V[k]->base), V[k]->bstride, V[k]->rstride, V[k]->r_lo, V[k]->r_hi, V[k]->C, V[k]->kind,
+                         V[k]->mid_mode, V[k]->xrows, V[k]->blend ? addr(V[k]->blend) : -1LL);
+                h->export_launches->push_back(line);
+            }
+            for (int t = 0; t < W.nterms; ++t) {
+                snprintf(line, sizeof(line), "wterm i=%d d=%d woff=%d", t, W.d[t], W.woff[t]);
+                h->export_launches->push_back(line);
+            }
+        }
+    }
     // tensor cores: all groups of the layer in ONE launch
     bool use_umma = h->umma_enabled && h->umma_pass[2] && !groups.empty() && groups.size() <= (size_t)kWgMaxGroups;
     UmmaWgradLaunch U;

@@ -214,14 +214,21 @@ class Engine(object):
             raise RuntimeError("wun_debug_launches failed: %s" % lib.wun_last_error().decode())
         buf = ctypes.create_string_buffer(int(n))
         lib.wun_debug_launches(self._h, int(batch), buf, n)
-        out = []
+        out, wg = [], []
         for line in buf.value.decode().splitlines():
             parts = line.split()
             d = {k: int(v) for k, v in (kv.split("=", 1) for kv in parts[1:])}
             if parts[0] == "launch":
                 out.append({"launch": d, "planes": [], "cls": [], "terms": []})
+            elif parts[0] == "wgrad":
+                wg.append({"wgrad": d, "plane": None, "dpre": None, "terms": []})
+            elif parts[0] in ("wplane", "wdpre"):
+                wg[-1]["plane" if parts[0] == "wplane" else "dpre"] = d
+            elif parts[0] == "wterm":
+                wg[-1]["terms"].append(d)
             else:
                 out[-1][{"plane": "planes", "cls": "cls", "term": "terms"}[parts[0]]].append(d)
+        self.wgrad_groups = wg          # the weight-gradient (class, plane) groups of the same dry run
         return out
 
     def layer_kernel(self, layer, pass_):
