@@ -443,6 +443,71 @@ def layer_table(run, iters=6):
     return rows, fam
 
 
+def account_launch(d):
+    """(FLOPs, input elements, output elements) PER BATCH ITEM of one exported forward plane-convolution launch
+    (Engine.launch_descriptions): 2 FLOP per MAC over the rows the classes write; input = the rows of every distinct plane view the
+    terms actually read, once; output = the rows written, once - SURVEY 8(d)'s "minimal HBM bytes = read input once + write live
+    output once" (tests/test_bench_contract.py checks the M4 table against SURVEY's per-layer figures)."""
+    L, planes, pairC = d["launch"], d["planes"], d["launch"]["pairC"]
+    flops, out_el, span = 0, 0, {}
+    for q in d["cls"]:
+        if q["m_hi"] <= q["m_lo"]:
+            continue
+        out_el += (((q["hi0"] - q["lo0"]) + (q["hi1"] - q["lo1"])) * pairC) if pairC else (q["m_hi"] - q["m_lo"]) * L["N"]
+        for t in d["terms"][q["term_begin"]:q["term_end"]]:
+            P = planes[t["plane"]]
+            if pairC:
+                rows = (q["hi0"] - q["lo0"] if t["woff"] >= 0 else 0) + (q["hi1"] - q["lo1"] if t["woff2"] >= 0 else 0)
+                flops += 2 * P["C"] * pairC * rows
+            else:
+                flops += 2 * P["C"] * L["N"] * (q["m_hi"] - q["m_lo"])
+            a, b = max(P["r_lo"], q["m_lo"] + t["d"]), min(P["r_hi"], q["m_hi"] + t["d"])
+            if b > a:
+                b += 1 if P["kind"] == 1 else 0                  # an interpolated row reads its successor too
+                key = (P["base"], P["rstride"])                  # the copied and the interpolated plane of an up block share their tensor
+                lo, hi, _ = span.get(key, (a, b, 0))
+                span[key] = (min(lo, a), max(hi, b), P["C"])
+    return flops, sum((hi - lo) * C for lo, hi, C in span.values()), out_el
+
+
+def stack_roofline(eng, batch, peaks, cfg):
+    """"the stack bound is the sum over layers of max(FLOPs / peak, bytes / BW)" - the per-layer conv arithmetic
+    roofline of one training step (forward, dgrad, wgrad of every conv layer + the Adam pass), from the planner's own launch
+    descriptions (host-only dry run).  Bytes per layer and pass: forward in + out, dgrad out + 2 in (gradient in, saved activation
+    for the slope, gradient out), wgrad in + out; Adam reads p, g, m, v and writes p, m, v."""
+    import ctypes
+    import wun
+    fwd = {d["launch"]["layer"]: account_launch(d) for d in eng.launch_descriptions(batch) if d["launch"]["pass"] == 0}
+    n_layers = 2 * cfg["num_layers"] + 1
+    if 0 not in fwd:                                             # the first layer has its own kernels: no plane-convolution launch
+        rows_out = 0
+        for name in ("dec0", "odd0"):
+            off, rows, ch = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+            wun.check(wun.lib.wun_debug_tensor(eng._h, name.encode(), int(batch), 1, ctypes.byref(off), ctypes.byref(rows), ctypes.byref(ch)))
+            rows_out += rows.value * ch.value
+        c_in = 1 if cfg["mono_downmix"] else 2
+        f0 = 2 * rows_out * cfg["filter_size"] * c_in
+        fwd[0] = (f0, eng.T_in * c_in, rows_out)
+    p_tensor, bw = peaks["tf_sustained"] * 1e12, peaks["hbm_gbs"] * 1e9
+    items, t_sum, t_sum3, f_sum = [], 0.0, 0.0, 0.0
+    for layer in range(n_layers):
+        f, i_el, o_el = (x * batch for x in fwd[layer])
+        for pname, fl, by in (("fwd", f, 4 * (i_el + o_el)), ("dgrad", f if layer > 0 else 0, 4 * (o_el + 2 * i_el) if layer > 0 else 0),
+                              ("wgrad", f, 4 * (i_el + o_el))):
+            t_f, t_b = fl / p_tensor, by / bw
+            items.append({"layer": layer, "pass": pname, "gflop": fl * 1e-9, "mbytes": by * 1e-6, "bound": "hbm" if t_b > t_f else "tensor",
+                          "us": max(t_f, t_b) * 1e6})
+            t_sum += max(t_f, t_b)
+            t_sum3 += max(3.0 * t_f, t_b)                        # the fp32-accurate scheme issues 3 bf16 MMAs per product
+            f_sum += fl
+    adam_bytes = 7 * 4 * eng.param_numel
+    items.append({"layer": "adam", "pass": "update", "gflop": 0.0, "mbytes": adam_bytes * 1e-6, "bound": "hbm", "us": adam_bytes / bw * 1e6})
+    t_sum += adam_bytes / bw
+    t_sum3 += adam_bytes / bw
+    return {"bound_ms": t_sum * 1e3, "bound_ms_3mma": t_sum3 * 1e3, "gflop": f_sum * 1e-9,
+            "hbm_bound_passes": sum(1 for it in items if it["bound"] == "hbm"), "passes": len(items), "items": items}
+
+
 def dp_check(run):
     """Hardware data-parallel correctness, run on the benchmark's own replicas:
       (a) the replicas are still bit-identical after all the Adam steps of this run;
@@ -560,6 +625,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        "input_frames_per_s": value * run.t_in / run.t_out,      # the same rate counted in input frames (x 8.997 for M4)
         "config": {"workload": "M4 baseline_stereo L=12, 147443-in/16389-out stereo, batch %d per GPU, "
                                "fwd+loss+bwd+Adam%s" % (run.B, "+NCCL all-reduce" if world > 1 else ""),
                    "global_batch": run.B * world, "parallelism": "dp%d" % world,
@@ -596,6 +662,21 @@ def run_ours(args, rank, world, local_rank):
     dpc = dp_check(run) if world > 1 else None
     if dpc is not None:
         line["dp_check"] = dpc
+    if rank == 0:
+        try:                                  # host-only accounting; never worth losing the line for
+            import wun
+            acct = wun.Engine(wun.config_from_model_config(run.cfg), input_frames=run.t_in)      # its own handle: a dry run only
+            sr = stack_roofline(acct, run.B, peaks, run.cfg)
+            del acct
+            line["stack_roofline"] = {
+                "bound_ms": sr["bound_ms"], "frac": sr["bound_ms"] / ms_step, "bound_ms_3mma": sr["bound_ms_3mma"],
+                "frac_3mma": sr["bound_ms_3mma"] / ms_step, "gflop": sr["gflop"],
+                "hbm_bound_passes": sr["hbm_bound_passes"], "passes": sr["passes"],
+                "definition": "SURVEY 8(d): sum over the conv layers x (fwd, dgrad, wgrad) + Adam of max(algorithmic FLOPs / bf16 "
+                              "sustained peak, algorithmic bytes / HBM bandwidth), %s; frac = that bound / measured step time; "
+                              "_3mma: tensor terms x 3 (the fp32-accurate scheme issues 3 bf16 MMAs per product)" % peaks["source"]}
+        except Exception as ex:               # noqa: BLE001
+            line["stack_roofline"] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
     if rank == 0 and fam:
         dom = max((k for k in fam if k != "first_layer"), key=lambda k: fam[k]["us"])
         top = max(rows, key=lambda r: r["us"])

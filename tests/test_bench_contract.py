@@ -34,7 +34,9 @@ class FakeRun(object):
 
     def __init__(self, preset, local_batch, global_batch, rank, world, dev, dist, overlap=True, seed=1337):
         self.preset, self.B, self.global_batch, self.rank, self.world = preset, local_batch, global_batch, rank, world
-        self.cfg = {"num_layers": 12, "num_frames": 16384}
+        import Config
+        self.cfg = Config.build_config([preset], experiment_id=0)["model_config"]
+        self.t_in, self.t_out = 147443, 16389
         self.eng = FakeEngine()
         self.graph, self.graph_error = object(), None
         self.ar = types.SimpleNamespace(views=[0, 1, 2, 3]) if (world > 1 and overlap) else None
@@ -115,9 +117,13 @@ def test_single_gpu_line_has_the_contract_keys(stubbed, capsys, tmp_path, monkey
     assert line["n_gpus"] == 1 and line["steps"] == 20 and line["warmup"] == 5 and line["higher_is_better"] is True
     assert abs(line["ms_per_step"] - 4.8) < 1e-9
     assert abs(line["value"] - 16 * 16389 / 4.8e-3) < 1e-3
+    assert abs(line["input_frames_per_s"] - 16 * 147443 / 4.8e-3) < 1e-3
     assert line["e2e"]["h2d_bytes_per_step"] == 1000 and line["e2e"]["d2h_bytes_per_step"] == 4
     assert line["e2e"]["value"] < line["value"]                 # host copies inside the timed region
     assert line["gpu_launches"] == (183 + 2) * 20
+    sr = line["stack_roofline"]                                 # host-side accounting on a real engine handle (dry run)
+    assert "error" not in sr and abs(sr["gflop"] - 666.0) < 0.5 and sr["passes"] == 76
+    assert abs(sr["frac"] - sr["bound_ms"] / 4.8) < 1e-12 and sr["bound_ms"] < sr["bound_ms_3mma"] < 3 * sr["bound_ms"]
     assert line["roofline"]["bound"] == "tensor" and "wgrad" in line["roofline"]["kernel"]      # the time-dominant family, not the best one
     assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
     assert line["roofline"]["traffic"] is None and "no ncu capture" in line["roofline"]["traffic_note"]
@@ -199,3 +205,46 @@ def test_reference_arm_prints_from_rank_zero_only(monkeypatch, capsys):
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+
+
+# SURVEY 8(d), per-layer live forward at M4 batch 16: GFLOP | minimal HBM MB (read input once + write live output once)
+SURVEY_M4_B16 = {0: (1.887, 144.7), 1: (22.644, 239.0), 2: (33.959, 207.5), 3: (33.944, 147.7), 4: (28.262, 95.8), 5: (21.159, 58.8),
+                 6: (14.759, 34.8), 7: (9.770, 20.0), 8: (6.191, 11.2), 9: (3.757, 6.1), 10: (2.159, 3.2), 11: (1.131, 1.6),
+                 12: (0.388, 0.6), 13: (0.359, 0.7), 14: (0.490, 1.0), 15: (0.716, 1.6), 16: (1.087, 2.5), 17: (1.667, 4.3),
+                 18: (2.526, 7.3), 19: (3.716, 12.4), 20: (5.216, 20.6), 21: (6.811, 33.2), 22: (7.937, 50.4), 23: (7.554, 69.3),
+                 24: (4.531, 75.5)}
+
+
+@pytest.mark.parametrize("first_layer", ["1", "0"], ids=["dedicated_first_layer", "generic_first_layer"])
+def test_stack_roofline_accounting_reproduces_the_survey_table(first_layer, monkeypatch):
+    """The algorithmic FLOPs and bytes behind `stack_roofline` come from the planner's own launch descriptions; for the benchmark
+    configuration they must be the per-layer figures SURVEY 8(d) derived by hand from the reference's shapes - pair-merged
+    launches included (the up blocks at batch 16)."""
+    import Config
+    import wun
+    from oracle import wave_unet_oracle as O
+    monkeypatch.setenv("WUN_FIRST_LAYER", first_layer)
+    cfg = Config.build_config(["baseline_stereo"], experiment_id=0)["model_config"]
+    t_in, _ = O.get_padding(cfg, cfg["num_frames"])
+    eng = wun.Engine(wun.config_from_model_config(cfg), input_frames=t_in)
+    assert any(d["launch"]["pairC"] for d in eng.launch_descriptions(16) if d["launch"]["pass"] == 0)
+    peaks = {"tf_sustained": 1414.5, "hbm_gbs": 6579.6}
+    sr = bench.stack_roofline(eng, 16, peaks, cfg)
+    fwd = {it["layer"]: it for it in sr["items"] if it["pass"] == "fwd"}
+    assert sorted(fwd) == list(range(25))
+    for layer, (gf, mb) in SURVEY_M4_B16.items():
+        assert abs(fwd[layer]["gflop"] - gf) < 6e-4, (layer, fwd[layer]["gflop"], gf)
+        assert abs(fwd[layer]["mbytes"] - mb) < 0.06, (layer, fwd[layer]["mbytes"], mb)
+    conv_fwd = sum(it["gflop"] for it in fwd.values())
+    assert abs(conv_fwd + 0.027 - eng.forward_backward_flops(16) * 1e-9 / 3 - 1.887 / 3) < 0.02      # 666.1 = 3 x 222.65 - dgrad(down0)
+    dg0 = [it for it in sr["items"] if it["layer"] == 0 and it["pass"] == "dgrad"][0]
+    assert dg0["gflop"] == 0.0 and dg0["mbytes"] == 0.0         # no gradient w.r.t. the input waveform
+    # every item is the larger of its two bounds, and the sum is what the line reports
+    total = 0.0
+    for it in sr["items"]:
+        t_f, t_b = it["gflop"] * 1e9 / 1414.5e12, it["mbytes"] * 1e6 / 6579.6e9
+        assert abs(it["us"] * 1e-6 - max(t_f, t_b)) < 1e-12 and it["bound"] == ("hbm" if t_b > t_f else "tensor")
+        total += max(t_f, t_b)
+    assert abs(sr["bound_ms"] - total * 1e3) < 1e-9
+    adam = sr["items"][-1]
+    assert adam["layer"] == "adam" and abs(adam["mbytes"] - 7 * 4 * 10263390 * 1e-6) < 1e-6      # SURVEY a15: 10 263 390 parameters
