@@ -152,6 +152,23 @@ def test_micro_upsample_linear():
     assert O.upsample_linear(x, False)[0, :, 0].tolist() == [0., 1., 2., 5., 8., 8.]      # 2N, clamp
 
 
+def test_upsample_linear_context_vs_an_independent_align_corners_resize():
+    """A second, independent implementation of the align_corners=True bilinear resize the context model uses
+    (UnetAudioSeparator.py:115: tf.image.resize_bilinear(..., [1, 2N-1], align_corners=True)): torch's own
+    F.interpolate(mode="linear", align_corners=True) - sample positions i * (N-1)/(2N-2) = i/2, the definition both libraries
+    document.  The oracle, the golden fixtures' stand-in (tests/golden/tf_shim.py) and torch must agree."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import tf_shim
+    rng = np.random.default_rng(11)
+    for n, c in ((2, 1), (9, 3), (64, 5), (517, 2)):
+        x = torch.as_tensor(rng.standard_normal((2, n, c)))
+        want = torch.nn.functional.interpolate(x.transpose(1, 2), size=2 * n - 1, mode="linear", align_corners=True).transpose(1, 2)
+        np.testing.assert_allclose(O.upsample_linear(x, True).numpy(), want.numpy(), rtol=0, atol=1e-14)
+        shim = tf_shim._resize_bilinear(tf_shim.T(x.unsqueeze(1)), [1, 2 * n - 1], align_corners=True).t[:, 0]
+        np.testing.assert_allclose(shim.numpy(), want.numpy(), rtol=0, atol=1e-14)
+
+
 def test_micro_upsample_learned():
     x = t64([[[1., 10.], [3., 30.], [5., 50.]]])
     var = t64([0.0, np.log(3.0)])                             # sigmoid -> 0.5, 0.75
@@ -196,6 +213,28 @@ def test_micro_adam_tf_form():
     lr_t = 1e-4 * np.sqrt(1 - 0.999) / (1 - 0.9)
     assert abs(m1[0] - m) < 1e-15 and abs(v1[0] - v) < 1e-15
     assert abs(p1[0] - (1.0 - lr_t * m / (np.sqrt(v) + 1e-8))) < 1e-15
+
+
+def test_adam_tf_form_vs_torch_adam_through_the_epsilon_identity():
+    """Independent check of the TF-form Adam (tf.train.AdamOptimizer, Training.py:77): torch.optim.Adam's update
+    lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) equals TF's lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps_tf) exactly when
+    eps_tf = eps * sqrt(1-b2^t).  Five steps with that per-step epsilon must reproduce torch's trajectory; with the SAME epsilon
+    the two differ (the epsilon placement is what the restatement has to get right)."""
+    rng = np.random.default_rng(3)
+    p0 = rng.standard_normal(64)
+    grads = [rng.standard_normal(64) * 10.0 ** rng.integers(-9, 1, size=64) for _ in range(5)]      # tiny gradients make eps matter
+    eps = 1e-8
+    tp = torch.nn.Parameter(torch.as_tensor(p0.copy()))
+    opt = torch.optim.Adam([tp], lr=1e-3, betas=(0.9, 0.999), eps=eps)
+    p, m, v = p0.copy(), np.zeros(64), np.zeros(64)
+    q, mq, vq = p0.copy(), np.zeros(64), np.zeros(64)
+    for t, g in enumerate(grads, 1):
+        tp.grad = torch.as_tensor(g.copy())
+        opt.step()
+        p, m, v = O.adam_update(p, g, m, v, t, 1e-3, eps=eps * np.sqrt(1 - 0.999 ** t))
+        q, mq, vq = O.adam_update(q, g, mq, vq, t, 1e-3, eps=eps)
+    np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-12, atol=1e-15)
+    assert np.abs(q - tp.detach().numpy()).max() > 1e-6
 
 
 def test_conv_vs_numpy_im2col():
