@@ -1,0 +1,113 @@
+"""Racecheck of the engine's multi-stream schedule on the host (no GPU).
+
+The engine's REAL host code (csrc/engine.cu: launch sequencing, the weight-pack / weight-gradient / split-pass / helper streams,
+every event fork and join, the gradient-bucket events of the data-parallel overlap) is built a second time with
+`nvcc --cudart none` against a recording stand-in for the CUDA runtime (tests/hostsim/fake_cudart.cpp) and run for two
+consecutive training steps with made-up device addresses.  Every launch is decoded from its by-value parameter block into the
+exact words it reads, writes or atomically accumulates into; tests/hostsim/schedule.py replays the trace with vector clocks over
+streams and events and a shadow memory at 4-byte granularity.  Any pair of conflicting accesses that the events do not order is
+a race the GPU parity tests could only catch by luck.
+
+Covered: the planner's default choices and the GPU-filling kernel variants forced onto mid-size nets (persistent / two-epilogue
+dgrad / pair-merged / fused output epilogue) for the five model families, every A/B switch of the stream structure in its other
+position, inference, the bucketed all-reduce on a communication stream (wun/parallel.py) followed by Adam and the NEXT step's
+weight packs - and the checker itself: dropping any single necessary stream wait from a trace must be reported."""
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "hostsim"))
+import schedule  # noqa: E402
+
+pytestmark = pytest.mark.skipif(schedule.build() is None, reason="needs nvcc and g++ to build the host simulation of the engine")
+
+FORCED = {"WUN_PERS_MIN": "0", "WUN_FOLD": "0", "WUN_PAIR_MIN_CTAS": "1", "WUN_PAIR_DGRAD": "1"}      # as tests/test_gpu_parity.py
+FAMILIES = [
+    ("m4_like_L5", ["baseline_stereo"], dict(num_layers=5), 3, 2000),
+    ("m5_like_L4", ["full"], dict(num_layers=4, num_initial_filters=16), 2, 1500),
+    ("m6_like_L4", ["full_multi_instrument"], dict(num_layers=4), 2, 1200),
+    ("m1_like_L5", ["baseline"], dict(num_layers=5), 3, 4096),
+    ("same_learned_stereo", ["baseline_diff"], dict(num_layers=4, upsampling="learned", mono_downmix=False), 2, 2048),
+]
+
+
+def kernels(ops):
+    return {o[2].split("(")[0].replace("void_", "").replace("wun::", "") for o in ops if o[0] == "L"}
+
+
+def assert_race_free(meta, ops):
+    violations, stats = schedule.check(meta, ops)
+    assert not violations, "\n".join("%(name)s [%(mode)s %(region)s, %(words)d words] is not ordered after %(other_name)s" % v
+                                     for v in violations)
+    return stats
+
+
+@pytest.mark.parametrize("name,named,ov,batch,nf", FAMILIES, ids=[c[0] for c in FAMILIES])
+def test_forced_gpu_filling_variants_are_race_free_incl_bucketed_allreduce(name, named, ov, batch, nf):
+    meta, ops = schedule.trace("train_dp", named, ov, batch, nf, FORCED)
+    stats = assert_race_free(meta, ops)
+    ks = kernels(ops)
+    assert "plane_conv_umma_persistent_dg2" in ks and any(k.startswith("plane_conv_umma_persistent_out<") for k in ks), sorted(ks)
+    assert {"split_views_kernel", "wgrad_umma_bulk_kernel", "umma_pack_kernel", "upsample_bwd_kernel"} <= ks
+    assert len(stats["per_stream"]) == 5 and min(stats["per_stream"]) > 0      # caller, packs + wgrad, split passes, helper, comm
+    # the launch count the library reports (bench.py's gpu_launches) is what was launched: 2 steps of (step + 2 memsets + 2 Adam)
+    lib_launches = sum(1 for o in ops if o[0] == "L" and not o[2].startswith("nccl"))
+    assert lib_launches == 2 * (meta["launches_reported"] + 4)
+
+
+@pytest.mark.parametrize("name,named,ov,batch,nf", FAMILIES[:3], ids=[c[0] for c in FAMILIES[:3]])
+def test_default_planner_choices_are_race_free(name, named, ov, batch, nf):
+    meta, ops = schedule.trace("train_dp", named, ov, batch, nf)
+    assert_race_free(meta, ops)
+    assert "plane_conv_umma_fold" in kernels(ops)                 # what the planner picks for launches that do not fill the GPU
+
+
+SWITCHES = ["WUN_SPLIT_AHEAD=0", "WUN_SIDE_STREAM=0", "WUN_DGRAD_PAR=0", "WUN_FIRST_TAIL=0", "WUN_BULK_WGRAD=0", "WUN_PACK_EVENTS=0",
+            "WUN_OUT_FUSE=0", "WUN_OUT_FUSE=2", "WUN_FIRST_LAYER=0", "WUN_SPLIT_COLSUM=0", "WUN_DISABLE_UMMA=1", "WUN_UMMA_WGRAD=0",
+            "WUN_EPI2=0", "WUN_PERSISTENT=0"]
+
+
+@pytest.mark.parametrize("switch", SWITCHES)
+def test_every_switch_of_the_stream_structure_in_its_other_position(switch):
+    env = dict(FORCED)
+    k, v = switch.split("=")
+    env[k] = v
+    meta, ops = schedule.trace("train", ["baseline_stereo"], dict(num_layers=4), 2, 1500, env)
+    assert_race_free(meta, ops)
+
+
+def test_inference_and_training_with_estimates_share_a_handle_without_races():
+    for scenario in ("infer", "train_out"):
+        meta, ops = schedule.trace(scenario, ["full"], dict(num_layers=4, num_initial_filters=16), 2, 1500, FORCED)
+        assert_race_free(meta, ops)
+
+
+def test_the_checker_reports_every_necessary_wait_when_it_is_dropped():
+    """Teeth: remove one cudaStreamWaitEvent at a time from a race-free trace.  Most waits are the only ordering between two
+    conflicting launches - the checker must name that pair; the rest are implied by other event chains.  The named pairs must
+    include each kind of cross-stream dependency the engine has."""
+    meta, ops = schedule.trace("train_dp", ["baseline_stereo"], dict(num_layers=3), 1, 300, FORCED)
+    assert_race_free(meta, ops)
+    waits = [i for i, o in enumerate(ops) if o[0] == "S"]
+    pairs = set()
+    necessary = 0
+    for i in waits:
+        v, _ = schedule.check(meta, ops[:i] + ops[i + 1:], max_reports=1)
+        if v:
+            necessary += 1
+            short = lambda n: str(n).split("(")[0].replace("void_", "").replace("wun::", "").split("<")[0]      # noqa: E731
+            pairs.add((short(v[0]["name"]), short(v[0]["other_name"])))
+    assert necessary >= 0.6 * len(waits), (necessary, len(waits))
+    expected = {
+        ("wgrad_umma_bulk_kernel", "split_views_kernel"),          # a wgrad kernel reads the split arrays of its layer
+        ("split_views_kernel", "wgrad_umma_bulk_kernel"),          # the arena half is rewritten two layers later
+        ("umma_pack_kernel", "adam_kernel"),                       # the next step's packs read the updated parameters
+        ("adam_kernel", "nccl_all_reduce_bucket3"),                # Adam after the last bucket's all-reduce
+    }
+    assert expected <= pairs, sorted(pairs)
+    assert any(a.startswith("plane_conv_umma") and b == "umma_pack_kernel" for a, b in pairs)          # a conv waits for its own pack
+    assert any(a.startswith("nccl_all_reduce") and b in ("wgrad_umma_bulk_kernel", "split_views_kernel", "first_wgrad_kernel",
+                                                         "output_wgrad_kernel", "upsample_bwd_kernel", "memset") for a, b in pairs)
+    assert any(a == "split_views_kernel" and (b.startswith("plane_conv_umma") or b == "upsample_bwd_kernel") for a, b in pairs)
