@@ -9,6 +9,7 @@
 //
 // Trace lines (text, one operation each):
 //   C <stream>                                   stream created
+//   N <event>                                    event created
 //   E <event> <stream>                           cudaEventRecord
 //   S <stream> <event>                           cudaStreamWaitEvent
 //   L <stream> <kernel name> <accesses...>       kernel launch / memset; accesses:
@@ -409,9 +410,12 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) {
 cudaError_t cudaStreamDestroy(cudaStream_t s) { (void)s; return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags) {
     (void)flags;
-    std::lock_guard<std::mutex> lk(g_mu);
-    *e = reinterpret_cast<cudaEvent_t>(g_next_event);
-    g_next_event += 0x10;
+    uintptr_t id;
+    { std::lock_guard<std::mutex> lk(g_mu); id = g_next_event; g_next_event += 0x10; }
+    *e = reinterpret_cast<cudaEvent_t>(id);
+    char b[64];
+    snprintf(b, sizeof(b), "N %llu", (unsigned long long)id);
+    emit(b);
     return cudaSuccess;
 }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { (void)e; return cudaSuccess; }

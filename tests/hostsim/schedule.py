@@ -72,8 +72,8 @@ def trace(scenario, named, overrides, batch, num_frames, env=None):
     ops = []
     for ln in lines[1:]:
         f = ln.split(" ")
-        if f[0] == "C":
-            ops.append(("C", int(f[1])))
+        if f[0] in ("C", "N"):
+            ops.append((f[0], int(f[1])))
         elif f[0] == "E":
             ops.append(("E", int(f[1]), int(f[2])))
         elif f[0] == "S":
@@ -168,7 +168,7 @@ def check(meta, ops, max_reports=20):
     violations = []
     n_launch = 0
     for i, op in enumerate(ops):
-        if op[0] == "C":
+        if op[0] in ("C", "N"):
             continue
         if op[0] == "E":
             s = sid(op[2])

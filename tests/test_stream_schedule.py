@@ -111,3 +111,17 @@ def test_the_checker_reports_every_necessary_wait_when_it_is_dropped():
     assert any(a.startswith("nccl_all_reduce") and b in ("wgrad_umma_bulk_kernel", "split_views_kernel", "first_wgrad_kernel",
                                                          "output_wgrad_kernel", "upsample_bwd_kernel", "memset") for a, b in pairs)
     assert any(a == "split_views_kernel" and (b.startswith("plane_conv_umma") or b == "upsample_bwd_kernel") for a, b in pairs)
+
+
+def test_steady_state_steps_create_no_streams_or_events():
+    """include/wun.h: "no hidden synchronisation, allocation or host<->device copy inside forward / backward / adam".  The
+    internal streams and events are created by the first call (before a CUDA graph of the step would be captured); the second
+    step of a trace must consist of launches, event records and stream waits only - and issue exactly what the first one did."""
+    meta, ops = schedule.trace("train", ["baseline_stereo"], dict(num_layers=4), 2, 1500, FORCED)
+    adam = [i for i, o in enumerate(ops) if o[0] == "L" and "adam_advance_kernel" in o[2]]
+    assert len(adam) == 2
+    first, second = ops[:adam[0] + 1], ops[adam[0] + 1:]
+    assert any(o[0] == "C" for o in first) and any(o[0] == "N" for o in first)
+    assert not any(o[0] in ("C", "N") for o in second)
+    shape = lambda part: [(o[0], o[2].split("(")[0]) if o[0] == "L" else (o[0],) for o in part if o[0] in ("L", "E", "S")]      # noqa: E731
+    assert shape(first) == shape(second)
