@@ -327,9 +327,9 @@ cudaError_t record_launch(const void* func, void** args, void* stream) {
         auto it = g_kernels.find(func);
         name = it == g_kernels.end() ? "?unregistered" : it->second;
     }
-    for (char& c : name) if (c == ' ') c = '_';
     bool known = false;
     std::string acc = decode(name, args, &known);
+    for (char& c : name) if (c == ' ') c = '_';                // one token per field in the trace line
     char head[64];
     snprintf(head, sizeof(head), "L %llu ", (unsigned long long)(uintptr_t)stream);
     emit(std::string(head) + (known ? "" : "UNKNOWN:") + name + acc);

@@ -8,6 +8,8 @@ check()  - replays the trace: vector clocks over streams and events give the hap
            stream.  A launch that reads a word must be ordered after its last writer and after the last atomic accumulation of every
            stream; a write after all of those and after the last read of every stream; an atomic accumulation (red.add - they
            commute with each other) after the last writer and the last readers.  Anything else is a race, reported with both launches.
+           The same pass checks that every access lies inside its buffer (Shadow.locate) and that no launch reads a workspace /
+           gradient / loss word before some launch has written it (an initcheck at launch granularity).
 """
 import json
 import os
@@ -143,8 +145,10 @@ def _sel(arr, idx):
     return np.lib.stride_tricks.as_strided(arr[w0:], shape=(rows, C), strides=(rstride * arr.itemsize, arr.itemsize))
 
 
-def check(meta, ops, max_reports=20):
-    """-> (violations, stats).  A violation: dict(op, name, stream, mode, region, other_stream, other_seq, other_name, words)."""
+def check(meta, ops, max_reports=20, init_regions=("ws", "ws_infer", "grads", "loss")):
+    """-> (violations, stats).  A violation: dict(op, name, stream, mode, region, other_stream, other_seq, other_name, words).
+    Reads of words of `init_regions` that no launch has written yet are violations too (mode "uninitialised": the workspace,
+    the gradient buffer and the loss are produced by the library itself - everything else is the caller's input)."""
     streams = {}
 
     def sid(handle):
@@ -206,6 +210,12 @@ def check(meta, ops, max_reports=20):
             for acc in by_mode[mode]:
                 for region, st, idx in shadow.windows(acc):
                     ws, wq = _sel(st["w_stream"], idx), _sel(st["w_seq"], idx)
+                    if mode in ("R", "A") and region in init_regions:
+                        never = ws < 0
+                        if never.any() and len(violations) < max_reports:
+                            violations.append({"op": i, "name": name, "stream": s, "mode": "uninitialised-" + mode, "region": region,
+                                               "other_stream": None, "other_op": None, "other_name": "(no launch wrote these words)",
+                                               "words": int(never.sum())})
                     bad = wq > vc_ext[ws]
                     if bad.any():
                         o = int(ws[bad].max())
@@ -232,5 +242,9 @@ def check(meta, ops, max_reports=20):
                     else:
                         _sel(st["w_stream"], idx)[...] = s
                         _sel(st["w_seq"], idx)[...] = seq[s]
-    stats = {"launches": n_launch, "streams": {h: k for h, k in streams.items()}, "per_stream": [int(x) for x in seq]}
+    main = streams.get(meta["main"], 0)
+    # fork / join discipline (what CUDA-graph capture of the step requires): when the trace ends, everything every other
+    # stream has been given happens-before the caller's stream position
+    stats = {"launches": n_launch, "streams": {h: k for h, k in streams.items()}, "per_stream": [int(x) for x in seq],
+             "joined_into_caller": bool((clk[main] >= seq).all())}
     return violations, stats

@@ -52,6 +52,7 @@ def test_forced_gpu_filling_variants_are_race_free_incl_bucketed_allreduce(name,
     assert "plane_conv_umma_persistent_dg2" in ks and any(k.startswith("plane_conv_umma_persistent_out<") for k in ks), sorted(ks)
     assert {"split_views_kernel", "wgrad_umma_bulk_kernel", "umma_pack_kernel", "upsample_bwd_kernel"} <= ks
     assert len(stats["per_stream"]) == 5 and min(stats["per_stream"]) > 0      # caller, packs + wgrad, split passes, helper, comm
+    assert stats["joined_into_caller"]          # every forked stream is joined back: the step is capturable as one CUDA graph
     # the launch count the library reports (bench.py's gpu_launches) is what was launched: 2 steps of (step + 2 memsets + 2 Adam)
     lib_launches = sum(1 for o in ops if o[0] == "L" and not o[2].startswith("nccl"))
     assert lib_launches == 2 * (meta["launches_reported"] + 4)
@@ -81,7 +82,17 @@ def test_every_switch_of_the_stream_structure_in_its_other_position(switch):
 def test_inference_and_training_with_estimates_share_a_handle_without_races():
     for scenario in ("infer", "train_out"):
         meta, ops = schedule.trace(scenario, ["full"], dict(num_layers=4, num_initial_filters=16), 2, 1500, FORCED)
-        assert_race_free(meta, ops)
+        assert assert_race_free(meta, ops)["joined_into_caller"]
+
+
+def test_an_unjoined_stream_is_noticed():
+    """Drop the last wait of the caller's stream (the join of the weight-gradient stream): the trace no longer ends joined."""
+    meta, ops = schedule.trace("train", ["baseline_stereo"], dict(num_layers=3), 1, 300, FORCED)
+    assert schedule.check(meta, ops)[1]["joined_into_caller"]
+    last_adam = max(i for i, o in enumerate(ops) if o[0] == "L" and "adam_kernel" in o[2])
+    main_waits = [i for i, o in enumerate(ops) if o[0] == "S" and o[1] == meta["main"] and i < last_adam]
+    cut = [o for i, o in enumerate(ops) if i < last_adam and i not in main_waits[-3:]]
+    assert not schedule.check(meta, cut, init_regions=())[1]["joined_into_caller"]
 
 
 def test_the_checker_reports_every_necessary_wait_when_it_is_dropped():

@@ -4,7 +4,7 @@
 The unit tests (tests/test_stream_schedule.py) run mid-size nets; this tool runs the exact configurations bench.py times -
 M4 baseline_stereo batch 16, M5 full batch 16, M6 full_multi_instrument at the per-GPU batches of the 8-/2-GPU runs, M1 batch 16,
 and the Predict window batch - through the engine's real host code on the recording CUDA runtime and prints, per case, the
-launches per stream and the races found.  Output of the last run: profiles/r2_schedule_racecheck.txt."""
+launches per stream and the races / out-of-bounds accesses / uninitialised reads found.  Output of the last run: profiles/r2_schedule_racecheck.txt."""
 import os
 import sys
 import time
@@ -43,9 +43,9 @@ def main():
             if o[0] == "L":
                 k = o[2].split("(")[0].replace("void_", "").replace("wun::", "")
                 kinds[k] = kinds.get(k, 0) + 1
-        print("%s\n   workspace %.2f GB, %d launches on %d streams (%s), %d event records, %d stream waits: %d race(s), %.0f s"
+        print("%s\n   workspace %.2f GB, %d launches on %d streams (%s), %d event records, %d stream waits: %d race(s) / out-of-bounds / uninitialised reads, joined back into the caller's stream: %s, %.0f s"
               % (title, meta["regions"]["ws" if scenario != "infer" else "ws_infer"][1] / 1e9, stats["launches"], len(stats["per_stream"]),
-                 streams, sum(1 for o in ops if o[0] == "E"), sum(1 for o in ops if o[0] == "S"), len(violations), time.time() - t0))
+                 streams, sum(1 for o in ops if o[0] == "E"), sum(1 for o in ops if o[0] == "S"), len(violations), stats["joined_into_caller"], time.time() - t0))
         print("   kernels: " + ", ".join("%s x%d" % kv for kv in sorted(kinds.items())))
         for v in violations:
             print("   RACE: %(name)s [%(mode)s %(region)s, %(words)d words] is not ordered after %(other_name)s" % v)
