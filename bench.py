@@ -142,7 +142,10 @@ class LineGuard(object):
         """Record the line as it stands (serialised now - the caller keeps filling it) and the phase that starts next."""
         if not self.active:
             return
-        snap = json.dumps(line)
+        try:
+            snap = json.dumps(line)
+        except Exception:                    # noqa: BLE001 - the guard must never be the reason a run fails
+            snap = self.snapshot
         with self.lock:
             self.snapshot, self.phase = snap, next_phase
         if self.timer is None:
