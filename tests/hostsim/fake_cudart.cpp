@@ -12,7 +12,7 @@
 //   N <event>                                    event created
 //   E <event> <stream>                           cudaEventRecord
 //   S <stream> <event>                           cudaStreamWaitEvent
-//   L <stream> <kernel name> <accesses...>       kernel launch / memset; accesses:
+//   L <stream> <kernel name> [G:gx:gy:gz:bx:by:bz:smem:opted_in_smem:cluster_x] <accesses...>   kernel launch / memset; accesses:
 //        V:<R|W|A>:<byte address>:<batch>:<bstride>:<row lo>:<row hi>:<rstride>:<C>     fp32 view (strides in elements)
 //        F:<R|W|A>:<byte address>:<bytes>                                                 flat range
 #include <cuda_runtime.h>
@@ -40,6 +40,7 @@ std::vector<std::string> g_trace;
 std::map<const void*, std::string> g_kernels;      // host stub address -> demangled kernel name
 uintptr_t g_next_stream = 0x1000, g_next_event = 0x100000;
 struct CallCfg { dim3 grid, block; size_t smem; void* stream; };
+std::map<const void*, int> g_max_dyn_smem;          // cudaFuncSetAttribute(cudaFuncAttributeMaxDynamicSharedMemorySize)
 std::vector<CallCfg> g_cfg_stack;
 
 std::string demangle(const char* name) {
@@ -320,19 +321,24 @@ std::string decode(const std::string& name, void** args, bool* known) {
     return a.s;
 }
 
-cudaError_t record_launch(const void* func, void** args, void* stream) {
+cudaError_t record_launch(const void* func, void** args, void* stream, dim3 grid, dim3 block, size_t smem, unsigned cluster_x) {
     std::string name;
+    int attr = -1;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_kernels.find(func);
         name = it == g_kernels.end() ? "?unregistered" : it->second;
+        auto at = g_max_dyn_smem.find(func);
+        if (at != g_max_dyn_smem.end()) attr = at->second;
     }
     bool known = false;
     std::string acc = decode(name, args, &known);
     for (char& c : name) if (c == ' ') c = '_';                // one token per field in the trace line
-    char head[64];
+    char head[64], geo[160];
     snprintf(head, sizeof(head), "L %llu ", (unsigned long long)(uintptr_t)stream);
-    emit(std::string(head) + (known ? "" : "UNKNOWN:") + name + acc);
+    // launch geometry: grid, block, dynamic shared memory asked for, the kernel's opted-in maximum (-1 = never set), cluster width
+    snprintf(geo, sizeof(geo), " G:%u:%u:%u:%u:%u:%u:%zu:%d:%u", grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, attr, cluster_x);
+    emit(std::string(head) + (known ? "" : "UNKNOWN:") + name + geo + acc);
     return cudaSuccess;
 }
 
@@ -384,11 +390,13 @@ cudaError_t __cudaPopCallConfiguration(dim3* gridDim, dim3* blockDim, size_t* sh
 
 // ---- runtime API -----------------------------------------------------------------------------------------------------------
 cudaError_t cudaLaunchKernel(const void* func, dim3 gridDim, dim3 blockDim, void** args, size_t sharedMem, cudaStream_t stream) {
-    (void)gridDim; (void)blockDim; (void)sharedMem;
-    return record_launch(func, args, stream);
+    return record_launch(func, args, stream, gridDim, blockDim, sharedMem, 1);
 }
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* config, const void* func, void** args) {
-    return record_launch(func, args, config->stream);
+    unsigned cx = 1;
+    for (unsigned i = 0; i < config->numAttrs; ++i)
+        if (config->attrs[i].id == cudaLaunchAttributeClusterDimension) cx = config->attrs[i].val.clusterDim.x;
+    return record_launch(func, args, config->stream, config->gridDim, config->blockDim, config->dynamicSmemBytes, cx);
 }
 cudaError_t cudaMemsetAsync(void* devPtr, int value, size_t count, cudaStream_t stream) {
     (void)value;
@@ -432,7 +440,14 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags) {
     emit(b);
     return cudaSuccess;
 }
-cudaError_t cudaFuncSetAttribute(const void* func, cudaFuncAttribute attr, int value) { (void)func; (void)attr; (void)value; return cudaSuccess; }
+cudaError_t cudaFuncSetAttribute(const void* func, cudaFuncAttribute attr, int value) {
+    if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+        if (value > 232448) return cudaErrorInvalidValue;          // 227 KB: the opt-in limit per CTA on sm_100
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_max_dyn_smem[func] = value;
+    }
+    return cudaSuccess;
+}
 cudaError_t cudaGetDeviceCount(int* count) { *count = 1; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { (void)e; return "fake cudart: no error"; }

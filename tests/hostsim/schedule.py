@@ -82,15 +82,19 @@ def trace(scenario, named, overrides, batch, num_frames, env=None):
             ops.append(("S", int(f[1]), int(f[2])))
         elif f[0] == "L":
             acc = []
+            geo = None
             for a in f[3:]:
                 p = a.split(":")
+                if p[0] == "G":
+                    geo = tuple(int(x) for x in p[1:])
+                    continue
                 if p[0] == "V":
                     acc.append(("V", p[1]) + tuple(int(x) for x in p[2:]))
                 elif p[0] == "F":
                     acc.append(("F", p[1], int(p[2]), int(p[3])))
                 else:                                   # part of a kernel name that contained a blank
                     raise ValueError("bad access token %r in %r" % (a, ln[:200]))
-            ops.append(("L", int(f[1]), f[2], acc))
+            ops.append(("L", int(f[1]), f[2], acc, geo))
         elif ln.strip():
             raise ValueError("bad trace line %r" % ln[:200])
     return meta, ops
@@ -184,7 +188,7 @@ def check(meta, ops, max_reports=20, init_regions=("ws", "ws_infer", "grads", "l
                 raise AssertionError("stream waits for event %d that was never recorded (trace line %d)" % (op[2], i))
             clk[s] = np.maximum(clk[s], events[op[2]])
             continue
-        _, handle, name, accs = op
+        _, handle, name, accs = op[:4]
         if name.startswith("UNKNOWN:"):
             raise AssertionError("fake_cudart.cpp cannot decode kernel %s" % name)
         s = sid(handle)
@@ -248,3 +252,30 @@ def check(meta, ops, max_reports=20, init_regions=("ws", "ws_infer", "grads", "l
     stats = {"launches": n_launch, "streams": {h: k for h, k in streams.items()}, "per_stream": [int(x) for x in seq],
              "joined_into_caller": bool((clk[main] >= seq).all())}
     return violations, stats
+
+
+def launch_limit_violations(ops):
+    """Launch geometry against the sm_100 limits (the real values the engine passes to the runtime, not the planner's audit):
+    <= 1024 threads per CTA, grid y / z <= 65535, dynamic shared memory <= 227 KB and - above the 48 KB default - within what the
+    kernel opted in to with cudaFuncSetAttribute, cluster width <= 8 dividing grid.x, non-empty grids."""
+    bad = []
+    for op in ops:
+        if op[0] != "L" or len(op) < 5 or op[4] is None:
+            continue
+        gx, gy, gz, bx, by, bz, smem, opted, cluster = op[4]
+        why = []
+        if min(gx, gy, gz, bx, by, bz) < 1:
+            why.append("empty grid or block")
+        if bx * by * bz > 1024:
+            why.append("%d threads per CTA" % (bx * by * bz))
+        if gy > 65535 or gz > 65535 or gx > 2147483647:
+            why.append("grid (%d, %d, %d)" % (gx, gy, gz))
+        if smem > 232448:
+            why.append("%d B of dynamic shared memory" % smem)
+        if smem > 49152 and opted < smem:
+            why.append("%d B of dynamic shared memory but the kernel opted in to %d" % (smem, opted))
+        if cluster < 1 or cluster > 8 or gx % max(cluster, 1) != 0:
+            why.append("cluster width %d on grid.x %d" % (cluster, gx))
+        if why:
+            bad.append((op[2].split("(")[0], op[4], why))
+    return bad

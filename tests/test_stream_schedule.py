@@ -161,3 +161,36 @@ def test_steady_state_steps_create_no_streams_or_events():
     assert not any(o[0] in ("C", "N") for o in second)
     shape = lambda part: [(o[0], o[2].split("(")[0]) if o[0] == "L" else (o[0],) for o in part if o[0] in ("L", "E", "S")]      # noqa: E731
     assert shape(first) == shape(second)
+
+
+BENCHMARK_SIZES = [("baseline_stereo", 16, "train"), ("full", 16, "train"), ("full_multi_instrument", 32, "train"),
+                   ("full_multi_instrument", 4, "train"), ("baseline", 16, "train"), ("full_44KHz", 16, "infer")]
+
+
+@needs_sim
+@pytest.mark.parametrize("preset,batch,scenario", BENCHMARK_SIZES, ids=["%s_b%d" % (p, b) for p, b, _ in BENCHMARK_SIZES])
+def test_launch_geometry_at_the_benchmark_sizes_respects_the_hardware_limits(preset, batch, scenario):
+    """The grid, block, dynamic shared memory and cluster width the engine REALLY passes to the runtime for every launch of the
+    configurations bench.py times (full windows; trace only, no shadow memory): within the sm_100 limits, and every launch above
+    the 48 KB default opted in to its shared memory with cudaFuncSetAttribute first."""
+    import Config
+    cfg = Config.build_config([preset], experiment_id=0)["model_config"]
+    meta, ops = schedule.trace(scenario, [preset], {}, batch, cfg["num_frames"])
+    assert schedule.launch_limit_violations(ops) == []
+    geos = [o[4] for o in ops if o[0] == "L" and o[4] is not None]
+    assert max(g[6] for g in geos) > 150 * 1024                       # the big tiles do use most of the 227 KB
+    assert any(g[8] > 1 for g in geos)                               # and the batch-folded kernel its thread-block clusters
+    if scenario == "train":                                          # one CTA per SM for the persistent tile loops
+        pers = [o[4] for o in ops if o[0] == "L" and "plane_conv_umma_persistent" in o[2]]
+        assert pers and all(g[0] <= 148 and g[1] == 1 and g[2] == 1 for g in pers), pers[:3]
+
+
+@needs_sim
+def test_the_limit_check_notices_an_oversized_launch():
+    meta, ops = schedule.trace("infer", ["baseline_stereo"], dict(num_layers=3), 1, 300)
+    i = next(k for k, o in enumerate(ops) if o[0] == "L" and o[4] is not None and o[4][6] > 49152)
+    g = list(ops[i][4])
+    broken = list(ops)
+    g[7] = 49152                                                     # as if the cudaFuncSetAttribute call had been forgotten
+    broken[i] = ops[i][:4] + (tuple(g),)
+    assert len(schedule.launch_limit_violations(broken)) == 1 and schedule.launch_limit_violations(ops) == []
