@@ -2,8 +2,10 @@
 
 TensorFlow cannot be installed here and the reference ships no checkpoint file, so there is no TF-written fixture:
 the format is pinned through published known answers of its primitives (RFC 3720 CRC-32C vectors, the LevelDB mask
-constant and table magic, protobuf wire bytes written out by hand below) plus round trips - "parity unpinned" for the
-container as a whole, and the module header says so too."""
+constant and table magic, protobuf wire bytes written out by hand below) plus round trips - and, at the end of this file,
+against Google's own code where this image has it: TensorBoard's TensorFlow stub (CRC-32C, mask) and the protobuf runtime over
+TensorBoard's generated TensorFlow protos (BundleEntryProto / BundleHeaderProto byte for byte, the `checkpoint` state file).
+The LevelDB table layout of the .index stays "parity unpinned", and the module header says so too."""
 import os
 import struct
 
@@ -163,3 +165,108 @@ def test_separator_variable_set_round_trips_with_either_optimizer_scope(tmp_path
     assert m4 is None and v4 is None and step4 == 0
     with pytest.raises(tfc.CheckpointError):
         tfc.split_separator_tensors({k: a for k, a in only.items() if k != names[3]}, names)
+
+
+# ---- pinned against Google's own code where it is available here: TensorBoard's TensorFlow stub ---------------------------------
+def _bundle_messages():
+    """BundleHeaderProto / BundleEntryProto (tensorflow/core/protobuf/tensor_bundle.proto) and CheckpointState
+    (tensorflow/python/training/checkpoint_state.proto), declared with the protobuf runtime on top of the GENUINE generated
+    TensorShapeProto, DataType and VersionDef that TensorBoard ships (tensorboard.compat.proto: compiled from TensorFlow's .proto
+    files).  The outer field numbers are restated from tensor_bundle.proto; everything nested is Google's."""
+    pytest.importorskip("tensorboard")
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    from tensorboard.compat.proto import tensor_shape_pb2, types_pb2, versions_pb2      # noqa: F401 (registers the files in the default pool)
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name = "wun_test/tensor_bundle_restated.proto"
+    fd.package = "wun_test"
+    fd.syntax = "proto3"
+    fd.dependency.extend([tensor_shape_pb2.DESCRIPTOR.name, types_pb2.DESCRIPTOR.name, versions_pb2.DESCRIPTOR.name])
+    h = fd.message_type.add(); h.name = "BundleHeaderProto"
+    for name, num, typ, tn in (("num_shards", 1, F.TYPE_INT32, None), ("endianness", 2, F.TYPE_INT32, None),
+                               ("version", 3, F.TYPE_MESSAGE, ".tensorboard.VersionDef")):
+        f = h.field.add(); f.name, f.number, f.type, f.label = name, num, typ, F.LABEL_OPTIONAL
+        if tn:
+            f.type_name = tn
+    e = fd.message_type.add(); e.name = "BundleEntryProto"
+    for name, num, typ, tn in (("dtype", 1, F.TYPE_ENUM, ".tensorboard.DataType"), ("shape", 2, F.TYPE_MESSAGE, ".tensorboard.TensorShapeProto"),
+                               ("shard_id", 3, F.TYPE_INT32, None), ("offset", 4, F.TYPE_INT64, None), ("size", 5, F.TYPE_INT64, None),
+                               ("crc32c", 6, F.TYPE_FIXED32, None)):
+        f = e.field.add(); f.name, f.number, f.type, f.label = name, num, typ, F.LABEL_OPTIONAL
+        if tn:
+            f.type_name = tn
+    c = fd.message_type.add(); c.name = "CheckpointState"
+    for name, num, label in (("model_checkpoint_path", 1, F.LABEL_OPTIONAL), ("all_model_checkpoint_paths", 2, F.LABEL_REPEATED)):
+        f = c.field.add(); f.name, f.number, f.type, f.label = name, num, F.TYPE_STRING, label
+    pool = descriptor_pool.Default()
+    try:
+        filed = pool.Add(fd) or pool.FindFileByName(fd.name)
+    except TypeError:                                        # second call in one process: already registered
+        filed = pool.FindFileByName(fd.name)
+    get = getattr(message_factory, "GetMessageClass", None)
+    return tuple((get(filed.message_types_by_name[n]) if get else message_factory.MessageFactory(pool).GetPrototype(filed.message_types_by_name[n]))
+                 for n in ("BundleHeaderProto", "BundleEntryProto", "CheckpointState"))
+
+
+def test_hand_encoded_bundle_protos_match_the_protobuf_runtime_over_tensorboards_tf_protos():
+    Header, Entry, _ = _bundle_messages()
+    from tensorboard.compat.proto import types_pb2
+    assert (types_pb2.DT_FLOAT, types_pb2.DT_INT32, types_pb2.DT_INT64, types_pb2.DT_DOUBLE) == (tfc.DT_FLOAT, tfc.DT_INT32, tfc.DT_INT64, tfc.DT_DOUBLE)
+    h = Header(num_shards=1)
+    h.version.producer = 1
+    assert h.SerializeToString(deterministic=True) == tfc.encode_header(1)
+    assert Header.FromString(tfc.encode_header(1)).version.producer == 1
+    rng = np.random.default_rng(5)
+    for dtype, shape, offset, size, crc in ((tfc.DT_FLOAT, (15, 2, 24), 300, 2880, 0x01020304), (tfc.DT_INT64, (), 0, 8, 7),
+                                            (tfc.DT_FLOAT, (312,), 2 ** 33 + 5, 1248, 0xFFFFFFFF), (tfc.DT_FLOAT, (5, 600, 288), 0, 3456000, 0),
+                                            (tfc.DT_DOUBLE, (1, 1, 1, 7), 123456789012, 56, int(rng.integers(0, 2 ** 32)))):
+        mine = tfc.encode_entry(dtype, shape, offset, size, crc)
+        m = Entry(dtype=dtype, offset=offset, size=size, crc32c=crc)
+        m.shape.SetInParent()                                # TF always writes the shape message, also for scalars
+        for d in shape:
+            m.shape.dim.add().size = d
+        assert m.SerializeToString(deterministic=True) == mine, (dtype, shape)
+        back = Entry.FromString(mine)
+        assert (back.dtype, [d.size for d in back.shape.dim], back.offset, back.size, back.crc32c) == (dtype, list(shape), offset, size, crc)
+        d = tfc.decode_entry(m.SerializeToString())          # and the reader understands what the runtime writes
+        assert (d["dtype"], d["shape"], d["offset"], d["size"], d["crc32c"]) == (dtype, list(shape), offset, size, crc)
+
+
+def test_crc32c_and_its_mask_match_tensorboards_tensorflow_stub():
+    """tensorboard.compat.tensorflow_stub.pywrap_tensorflow carries Google's pure-Python CRC-32C and TFRecord masking
+    (masked_crc32c) - the same mask the tensor bundle stores per tensor and LevelDB per table block."""
+    pytest.importorskip("tensorboard")
+    from tensorboard.compat.tensorflow_stub import pywrap_tensorflow as tb
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 3, 4, 7, 8, 9, 63, 64, 65, 1000, 4099):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert wun.crc32c(data) == (tb.crc32c(data) & 0xFFFFFFFF), n
+        assert tfc.mask_crc(wun.crc32c(data)) == (tb.masked_crc32c(data) & 0xFFFFFFFF), n
+
+
+def test_written_checkpoint_parses_with_the_protobuf_runtime(tmp_path):
+    """Every BundleEntryProto / the header of a written .index and the `checkpoint` state file (text format) through the real
+    protobuf parsers; each tensor's stored crc32c equals TensorBoard's masked CRC-32C of its bytes in the data file."""
+    Header, Entry, State = _bundle_messages()
+    from google.protobuf import text_format
+    from tensorboard.compat.tensorflow_stub import pywrap_tensorflow as tb
+    rng = np.random.default_rng(2)
+    tensors = {"separator/conv1d/kernel": rng.standard_normal((15, 2, 24)).astype(np.float32),
+               "separator/conv1d/bias": np.zeros(24, np.float32), "global_step": np.int64(1234),
+               "separator_solver/beta1_power": np.float32(0.9 ** 1234), "separator/interp_0": rng.standard_normal(312).astype(np.float32)}
+    prefix = tfc.write_checkpoint(str(tmp_path / "run" / "run-1234"), tensors)
+    table = tfc.read_table(open(prefix + ".index", "rb").read())
+    assert table[0][0] == b"" and Header.FromString(table[0][1]).num_shards == 1
+    data = open(prefix + ".data-00000-of-00001", "rb").read()
+    seen = {}
+    for key, value in table[1:]:
+        e = Entry.FromString(value)
+        raw = data[e.offset:e.offset + e.size]
+        assert e.crc32c == (tb.masked_crc32c(raw) & 0xFFFFFFFF), key
+        want = np.asarray(tensors[key.decode()])
+        assert [d.size for d in e.shape.dim] == list(want.shape) and raw == want.tobytes()
+        seen[key.decode()] = e.dtype
+    assert sorted(seen) == sorted(tensors) and seen["global_step"] == tfc.DT_INT64 and seen["separator/conv1d/bias"] == tfc.DT_FLOAT
+    st = text_format.Parse(open(os.path.join(os.path.dirname(prefix), "checkpoint")).read(), State())
+    assert st.model_checkpoint_path == "run-1234" and list(st.all_model_checkpoint_paths) == ["run-1234"]
+    assert tfc.latest_checkpoint(os.path.dirname(prefix)) == prefix

@@ -6,8 +6,10 @@ and checkpoints written here load back into the reference.  No TensorFlow needed
 Format (restated from the published TensorFlow / LevelDB sources - tensorflow/core/util/tensor_bundle,
 tensorflow/core/lib/io/{table,block,format}; TensorFlow itself is not installable here, so this module is pinned by
 known-answer vectors of its primitives (CRC-32C RFC 3720 vectors, LevelDB mask constant, varint / protobuf wire bytes,
-table magic) and by its own round trip, NOT by a checkpoint written by TensorFlow - tests/test_tf_checkpoint.py says
-the same):
+table magic), by Google's own code where this image carries it - TensorBoard's TensorFlow stub for CRC-32C and its mask, the
+protobuf runtime over TensorBoard's generated TensorShapeProto / DataType / VersionDef for the two bundle protos (byte for byte)
+and the `checkpoint` state file - and by its own round trip, NOT by a checkpoint written by TensorFlow: the table layout of the
+.index stays unpinned - tests/test_tf_checkpoint.py says the same):
 
   <prefix>.index                  a LevelDB-format sorted string table, uncompressed:
       key ""            -> BundleHeaderProto  { num_shards = 1; endianness = LITTLE; version { producer = 1 } }
@@ -119,7 +121,8 @@ def encode_entry(dtype, shape, offset, size, crc_masked, shard_id=0):
         out += b"\x20"; put_varint(out, offset)                        # 4: offset
     if size:
         out += b"\x28"; put_varint(out, size)                          # 5: size
-    out += b"\x35" + struct.pack("<I", crc_masked)                     # 6: crc32c (fixed32)
+    if crc_masked:                                                     # (proto3: a zero scalar is not serialised)
+        out += b"\x35" + struct.pack("<I", crc_masked)                 # 6: crc32c (fixed32)
     return bytes(out)
 
 
@@ -155,7 +158,7 @@ def decode_header(buf):
 
 
 def decode_entry(buf):
-    e = {"dtype": 0, "shape": [], "shard_id": 0, "offset": 0, "size": 0, "crc32c": None, "slices": 0}
+    e = {"dtype": 0, "shape": [], "shard_id": 0, "offset": 0, "size": 0, "crc32c": 0, "slices": 0}      # proto3 defaults
     for fn, _, v in _fields(buf):
         if fn == 1: e["dtype"] = v
         elif fn == 2:
@@ -373,7 +376,7 @@ def read_checkpoint(prefix, verify=True, names=None):
         raw = shards[sid][e["offset"]:e["offset"] + e["size"]]
         if raw.size != e["size"]:
             raise CheckpointError("%s: data file truncated" % name)
-        if verify and e["crc32c"] is not None and unmask_crc(e["crc32c"]) != wun.crc32c(np.asarray(raw)):
+        if verify and unmask_crc(e["crc32c"]) != wun.crc32c(np.asarray(raw)):
             raise CheckpointError("%s: tensor checksum mismatch" % name)
         out[name] = np.frombuffer(np.asarray(raw).tobytes(), dtype=dt.newbyteorder("<")).astype(dt).reshape(e["shape"])
     return out
