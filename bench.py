@@ -680,6 +680,18 @@ def run_ours(args, rank, world, local_rank):
                               "_3mma: tensor terms x 3 (the fp32-accurate scheme issues 3 bf16 MMAs per product)" % peaks["source"]}
         except Exception as ex:               # noqa: BLE001
             line["stack_roofline"] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    if rank == 0:
+        try:                                  # the launch-footprint model of tools/footprint_model.py, if it was made for these sources
+            fj = json.load(open(os.path.join(REPO, "profiles", "r2_footprint.json")))
+            if fj.get("source_hash") == kernel_source_hash() and fj.get("batch") == run.B and fj.get("preset") == PRESET:
+                floor_ms = fj["step_distinct_bytes"] / (peaks["hbm_gbs"] * 1e9) * 1e3
+                line["step_footprint_model"] = {
+                    "distinct_bytes": fj["step_distinct_bytes"], "hbm_floor_ms": floor_ms, "frac_of_step": floor_ms / ms_step,
+                    "note": "sum over the launches of one step of the distinct bytes each launch touches (decoded from the engine's real "
+                            "launch parameters on the host, tools/footprint_model.py) / measured HBM bandwidth: the HBM floor of the step AS "
+                            "IMPLEMENTED (split arrays and weight packs included); a model, not an ncu measurement"}
+        except Exception:                     # noqa: BLE001
+            pass
     if rank == 0 and fam:
         dom = max((k for k in fam if k != "first_layer"), key=lambda k: fam[k]["us"])
         top = max(rows, key=lambda r: r["us"])

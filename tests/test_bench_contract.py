@@ -133,6 +133,23 @@ def test_single_gpu_line_has_the_contract_keys(stubbed, capsys, tmp_path, monkey
     assert os.path.exists(os.path.join(str(tmp_path), "gpurun_out", "layer_table_n1.json"))
 
 
+def test_footprint_model_is_reported_only_for_the_sources_it_was_made_from(stubbed, capsys, tmp_path, monkeypatch):
+    monkeypatch.setattr(bench, "REPO", str(tmp_path))
+    os.makedirs(os.path.join(str(tmp_path), "profiles"))
+    model = {"source_hash": "a" * 16, "preset": "baseline_stereo", "batch": 16, "step_distinct_bytes": 7.95e9}
+    with open(os.path.join(str(tmp_path), "profiles", "r2_footprint.json"), "w") as f:
+        json.dump(model, f)
+    monkeypatch.setattr(bench, "kernel_source_hash", lambda: "a" * 16)
+    bench.run_ours(_args(no_extras=True, no_cpu_baseline=True), 0, 1, 0)
+    (line,) = _lines(capsys)
+    fm = line["step_footprint_model"]
+    assert fm["distinct_bytes"] == 7.95e9 and abs(fm["frac_of_step"] - fm["hbm_floor_ms"] / 4.8) < 1e-12 and 0.2 < fm["frac_of_step"] < 0.3
+    monkeypatch.setattr(bench, "kernel_source_hash", lambda: "b" * 16)          # other kernel sources: stale, not reported
+    bench.run_ours(_args(no_extras=True, no_cpu_baseline=True), 0, 1, 0)
+    (line,) = _lines(capsys)
+    assert "step_footprint_model" not in line
+
+
 def test_two_rank_launch_prints_one_line_and_leaves_without_exit_handlers(stubbed, capsys, tmp_path, monkeypatch):
     monkeypatch.setattr(bench, "REPO", str(tmp_path))
     monkeypatch.setattr(bench, "kernel_source_hash", lambda: "0" * 16)
