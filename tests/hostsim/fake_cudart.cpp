@@ -33,7 +33,14 @@
 
 using namespace wun;
 
+namespace cpudev {                                   // cpu_kernels.cpp: reference execution of a launch on host memory
+bool execute(const std::string& name, void** args);
+void reset();
+}
+
 namespace {
+
+bool g_execute = false;                              // fakecuda_set_execute(1): carry every launch out on the caller's (host) buffers
 
 std::mutex g_mu;
 std::vector<std::string> g_trace;
@@ -333,6 +340,7 @@ cudaError_t record_launch(const void* func, void** args, void* stream, dim3 grid
     }
     bool known = false;
     std::string acc = decode(name, args, &known);
+    if (g_execute && known && !cpudev::execute(name, args)) known = false;
     for (char& c : name) if (c == ' ') c = '_';                // one token per field in the trace line
     char head[64], geo[160];
     snprintf(head, sizeof(head), "L %llu ", (unsigned long long)(uintptr_t)stream);
@@ -348,6 +356,7 @@ cudaError_t record_launch(const void* func, void** args, void* stream, dim3 grid
 extern "C" {
 
 void fakecuda_reset() { std::lock_guard<std::mutex> lk(g_mu); g_trace.clear(); }
+void fakecuda_set_execute(int on) { g_execute = on != 0; cpudev::reset(); }
 
 long long fakecuda_trace(char* buf, long long capacity) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -399,7 +408,7 @@ cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* config, const void* fu
     return record_launch(func, args, config->stream, config->gridDim, config->blockDim, config->dynamicSmemBytes, cx);
 }
 cudaError_t cudaMemsetAsync(void* devPtr, int value, size_t count, cudaStream_t stream) {
-    (void)value;
+    if (g_execute) memset(devPtr, value, count);
     char b[160];
     snprintf(b, sizeof(b), "L %llu memset F:W:%llu:%lld", (unsigned long long)(uintptr_t)stream, (unsigned long long)(uintptr_t)devPtr, (long long)count);
     emit(b);

@@ -1,0 +1,149 @@
+"""The engine's REAL host code executed end to end on the CPU (no GPU): two training steps + an inference call, vs the oracle.
+
+tests/hostsim/ builds the engine's sources a second time with `nvcc --cudart none` against a stand-in CUDA runtime.  In execute
+mode that runtime carries every launch out on host memory with the reference routines of tests/hostsim/cpu_kernels.cpp - an
+independent statement, in plain double-precision loops, of what each kernel must compute from its by-value parameter block.
+What runs unmodified is everything the HOST does: the planner, the plane / class / group / term tables and packed-weight jobs
+built for the tcgen05 kernels (incl. pair-merged halves, output-channel splits, the fused output epilogue's frame mapping), the
+split-pass jobs that carry the bias sums, the first-layer / upsampling-backward / output-layer blocks, gradient scales,
+accumulate ranges, memsets and the device-side Adam state.  Loss, every gradient, the source estimates and the parameters after
+two TF-form Adam steps must agree with the oracle to rounding (1e-5 / 1e-4: the reference routines accumulate in double).
+
+This is NOT a CPU path of the product (libwun.so has none and fails loudly without a GPU); it is test infrastructure that lets
+the host half of the engine be checked for configurations and batch sizes no GPU test has run (e.g. the per-GPU batches of the
+8-GPU M6 split).  The device half - the kernels' own arithmetic - is what `-m gpu` tests."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "hostsim"))
+import schedule  # noqa: E402
+
+
+def _simulation_library():
+    try:
+        return schedule.build()
+    except Exception:                                        # noqa: BLE001 (tests/test_stream_schedule.py reports build failures)
+        return None
+
+
+_SIM = _simulation_library()
+needs_sim = pytest.mark.skipif(_SIM is None, reason="host simulation of the engine not built (needs nvcc and g++)")
+
+FORCED = {"WUN_PERS_MIN": "0", "WUN_FOLD": "0", "WUN_PAIR_MIN_CTAS": "1", "WUN_PAIR_DGRAD": "1"}
+
+
+def run_steps(named, overrides, batch, nf, env=None, grad_scale=1.0):
+    e = dict(os.environ)
+    for k in [k for k in e if k.startswith("WUN_")]:
+        del e[k]
+    e.update(env or {})
+    e["WUN_LIB"] = _SIM
+    e["OMP_NUM_THREADS"] = e["MKL_NUM_THREADS"] = "1"       # small nets; several of these run side by side
+    out = subprocess.run([sys.executable, os.path.join(HERE, "hostsim", "run_cpu_step.py"), str(batch), str(nf), repr(float(grad_scale)),
+                          json.dumps(overrides)] + list(named), env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def assert_matches_oracle(res):
+    assert res["unknown"] == []
+    for step in ("step1", "step2"):
+        r = res[step]
+        assert r["loss_rel"] < 1e-5, (step, r)
+        assert r["grad_worst_rel"] < 1e-4, (step, r)
+        assert r["outputs_rel"] < 1e-5, (step, r)
+        assert r["params_rel"] < 1e-5, (step, r)
+    assert res["infer_outputs_rel"] < 1e-4, res["infer_outputs_rel"]
+    assert abs(res["adam_state"][0] - 0.9 ** 3) < 1e-6 and abs(res["adam_state"][1] - 0.999 ** 3) < 1e-6 and res["adam_state"][2] == 2.0
+
+
+FAMILIES = [
+    ("m4_like", ["baseline_stereo"], dict(num_layers=3), 2, 300),
+    ("m5_like_learned", ["full"], dict(num_layers=3, num_initial_filters=16), 2, 260),
+    ("m6_like_multi_instrument", ["full_multi_instrument"], dict(num_layers=3), 2, 200),
+    ("m1_like_same_padding_mono", ["baseline"], dict(num_layers=3), 2, 256),
+    ("same_learned_stereo_difference", ["baseline_diff"], dict(num_layers=3, upsampling="learned", mono_downmix=False), 2, 128),
+]
+
+
+def run_many(cases):
+    """cases: [(label, named, overrides, batch, nf, env, grad_scale)] -> {label: result}; the subprocesses run side by side."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as pool:
+        futs = {c[0]: pool.submit(run_steps, c[1], c[2], c[3], c[4], c[5], c[6]) for c in cases}
+        return {k: f.result() for k, f in futs.items()}
+
+
+@needs_sim
+@pytest.mark.parametrize("variant", ["planner_default", "gpu_filling_variants_forced"])
+def test_two_training_steps_and_inference_on_the_cpu_device_match_the_oracle(variant):
+    forced = variant.startswith("gpu")
+    results = run_many([(name, named, ov, batch, nf, FORCED if forced else None, 0.5 if forced else 1.0) for name, named, ov, batch, nf in FAMILIES])
+    assert sorted(results) == sorted(c[0] for c in FAMILIES)
+    for name, res in results.items():
+        try:
+            assert_matches_oracle(res)
+            ks = res["kernels"]
+            assert any(k.startswith("plane_conv_umma") for k in ks) and "wgrad_umma_bulk_kernel" in ks and "umma_pack_kernel" in ks
+            if forced:
+                assert "plane_conv_umma_persistent_dg2" in ks and any(k.startswith("plane_conv_umma_persistent_out<") for k in ks), sorted(ks)
+            else:
+                assert "plane_conv_umma_fold" in ks and "output_fwd_kernel" in ks
+        except AssertionError as ex:
+            raise AssertionError("%s: %s" % (name, ex))
+
+
+SWITCHES = [
+    {"WUN_OUT_FUSE": "2"},                       # the output convs' own weight gradient inside the fused epilogue
+    {"WUN_OUT_FUSE": "0"},                       # separate output kernels next to the persistent convs
+    {"WUN_BULK_WGRAD": "0"},                     # converter-fed tcgen05 wgrad, bias sums by colsum_kernel
+    {"WUN_SPLIT_COLSUM": "0"},
+    {"WUN_FIRST_LAYER": "0"},                    # first layer through the generic plane kernels
+    {"WUN_DISABLE_UMMA": "1"},                   # the exact-fp32 CUDA-core path for everything
+    {"WUN_UMMA_DGRAD": "0"},
+    {"WUN_PAIR_FWD": "0", "WUN_PAIR_DGRAD": "0"},
+    {"WUN_NSPLIT_MAX": "4", "WUN_TEAMS": "4", "WUN_PERSISTENT": "0"},      # output-channel splits of the non-persistent kernel
+    {"WUN_SIDE_STREAM": "0"},
+]
+
+
+@needs_sim
+def test_every_structural_switch_gives_the_same_step():
+    cases = []
+    for sw in SWITCHES:
+        env = dict(FORCED)
+        env.update(sw)
+        cases.append(("+".join("%s=%s" % kv for kv in sw.items()), ["full_multi_instrument"], dict(num_layers=3, upsampling="learned"), 2, 200, env, 1.0))
+    for label, res in run_many(cases).items():
+        try:
+            assert_matches_oracle(res)
+        except AssertionError as ex:
+            raise AssertionError("%s: %s" % (label, ex))
+
+
+@needs_sim
+def test_batch_sizes_of_the_data_parallel_splits():
+    """The planner's choices depend on the batch (pair merging, splits, folded tiles): the per-GPU batches the scaling runs use."""
+    cases = [("batch %d" % b, ["full_multi_instrument"], dict(num_layers=4), b, 260, None, 1.0 / 8) for b in (1, 3, 4, 8)]
+    for label, res in run_many(cases).items():
+        try:
+            assert_matches_oracle(res)
+        except AssertionError as ex:
+            raise AssertionError("%s: %s" % (label, ex))
+
+
+@needs_sim
+def test_wider_output_filter_and_other_filter_sizes():
+    """output_filter_size > 1 (no fused epilogue: the separate output kernels with 'same' / 'valid' taps), other filter widths."""
+    cases = [("same padding, ofs 3", ["baseline"], dict(num_layers=3, output_filter_size=3, filter_size=9, merge_filter_size=3), 2, 256, FORCED, 1.0),
+             ("context, ofs 5", ["baseline_stereo"], dict(num_layers=2, output_filter_size=5, filter_size=7, input_filter_size=7), 1, 300, None, 1.0)]
+    for label, res in run_many(cases).items():
+        try:
+            assert_matches_oracle(res)
+        except AssertionError as ex:
+            raise AssertionError("%s: %s" % (label, ex))
