@@ -515,15 +515,20 @@ bool execute(const std::string& name, void** args) {
         }
         return true;
     }
-    if (has(name, "gather_windows_kernel")) {
+    if (has(name, "gather_windows_kernel")) {              // Evaluate.py:131-132
         const float* padded = *static_cast<const float* const*>(args[0]);
+        const long long n_padded = *static_cast<const long long*>(args[1]);
         const long long* starts = *static_cast<const long long* const*>(args[2]);
         const int nw = *static_cast<const int*>(args[3]), T_in = *static_cast<const int*>(args[4]), C = *static_cast<const int*>(args[5]);
         float* out = *static_cast<float* const*>(args[6]);
-        for (int w = 0; w < nw; ++w) memcpy(out + (long long)w * T_in * C, padded + starts[w] * C, sizeof(float) * (size_t)T_in * C);
+        for (int w = 0; w < nw; ++w)
+            for (long long off = 0; off < (long long)T_in * C; ++off) {
+                const long long src = starts[w] * C + off;
+                out[(long long)w * T_in * C + off] = src < n_padded * C ? padded[src] : 0.f;
+            }
         return true;
     }
-    if (has(name, "scatter_windows_kernel")) {
+    if (has(name, "scatter_windows_kernel")) {             // Evaluate.py:138-139: plain overwrite, the shifted last window wins
         const float* outs = *static_cast<const float* const*>(args[0]);
         const long long* starts = *static_cast<const long long* const*>(args[1]);
         const int nw = *static_cast<const int*>(args[2]), K = *static_cast<const int*>(args[3]), T_out = *static_cast<const int*>(args[4]),
@@ -531,8 +536,12 @@ bool execute(const std::string& name, void** args) {
         float* preds = *static_cast<float* const*>(args[6]);
         const long long n_frames = *static_cast<const long long*>(args[7]);
         for (int k = 0; k < K; ++k)
-            for (int w = 0; w < nw; ++w)           // in window order: a later (shifted last) window overwrites (Evaluate.py:138-139)
-                memcpy(preds + ((long long)k * n_frames + starts[w]) * C, outs + ((long long)k * nw + w) * T_out * C, sizeof(float) * (size_t)T_out * C);
+            for (int w = 0; w < nw; ++w)
+                for (int t = 0; t < T_out; ++t) {
+                    const long long frame = starts[w] + t;
+                    if (frame >= n_frames) continue;
+                    for (int c = 0; c < C; ++c) preds[((long long)k * n_frames + frame) * C + c] = outs[(((long long)k * nw + w) * T_out + t) * C + c];
+                }
         return true;
     }
     return false;

@@ -100,6 +100,25 @@ def main():
     want = O.forward_np(cfg, o_par, mix, False)
     res["infer_outputs_rel"] = max(rel(out_d.reshape(K, batch, t_out, C)[k], want[s]) for k, s in enumerate(names))
 
+    # window gather / scatter of predict_track (Evaluate.py:125-139): hop = T_out, the last window shifted back, plain overwrite
+    n_frames = 3 * t_out - 7
+    starts = []
+    for pos in range(0, n_frames, t_out):
+        starts.append(n_frames - t_out if pos + t_out > n_frames else pos)
+    nw = len(starts)
+    padded = rng.standard_normal((n_frames + (t_in - t_out), C)).astype(np.float32)
+    st = np.asarray(starts, np.int64)
+    win = aligned(nw * t_in * C)
+    wun.check(lib.wun_gather_windows(h, P(padded), padded.shape[0], P(st), nw, P(win), MAIN))
+    res["gather_exact"] = bool(np.array_equal(win.reshape(nw, t_in, C), np.stack([padded[s0:s0 + t_in] for s0 in starts])))
+    outs = rng.standard_normal((K, nw, t_out, C)).astype(np.float32)
+    preds = aligned(K * n_frames * C)
+    wun.check(lib.wun_scatter_windows(h, P(outs), P(st), nw, P(preds), n_frames, MAIN))
+    want_p = np.zeros((K, n_frames, C), np.float32)
+    for w, s0 in enumerate(starts):
+        want_p[:, s0:s0 + t_out] = outs[:, w]
+    res["scatter_exact"] = bool(np.array_equal(preds.reshape(K, n_frames, C), want_p))
+
     nbytes = fake.fakecuda_trace(None, 0)
     buf = ctypes.create_string_buffer(int(nbytes))
     fake.fakecuda_trace(buf, nbytes)
