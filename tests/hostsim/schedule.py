@@ -38,7 +38,15 @@ def build():
     """Returns the path of the simulated engine library, or None when there is no nvcc / g++ to build it with."""
     if not (os.path.exists(NVCC) and shutil.which("g++")):
         return None
-    os.makedirs(BUILD, exist_ok=True)
+    global BUILD
+    try:
+        os.makedirs(BUILD, exist_ok=True)
+        with open(os.path.join(BUILD, ".writable"), "w"):
+            pass
+    except OSError:                                          # read-only checkout: build under the temp directory instead
+        import tempfile
+        BUILD = os.path.join(tempfile.gettempdir(), "wun_hostsim_build")
+        os.makedirs(BUILD, exist_ok=True)
     csrc = os.path.join(PKG, "csrc")
     headers = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
     fake = os.path.join(BUILD, "libfakecudart.so")
