@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -43,6 +44,38 @@ static double plane_at(const PlaneView& P, int b, long long r, int c) {      // 
 }
 
 static inline double lrelu(double v) { return v > 0.2 * v ? v : 0.2 * v; }
+
+// ---- optional arithmetic model of the tensor-core kernels (FAKECUDA_MMA_MODEL) ----------------------------------------------------
+//   0 (default): exact products, double accumulation - the contract.
+//   3: every fp32 operand split into two bf16 (hi = rn(x), lo = rn(x - hi)), hi*hi + hi*lo + lo*hi accumulated in fp32 - the
+//      scheme of kernels_umma.cu; 1: hi*hi only (a single bf16 pass), for comparison.
+static int g_mma_model = 0;
+static inline float bf16_rn(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;                  // inf / nan
+    u += 0x7fffu + ((u >> 16) & 1u);                                 // round to nearest even
+    u &= 0xffff0000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+struct Acc {                       // one accumulator in the active arithmetic model
+    double d = 0.0;
+    float f = 0.f;
+    inline void mac(double x, double w) {
+        if (g_mma_model == 0) { d += x * w; return; }
+        const float xf = (float)x, wf = (float)w;
+        const float xh = bf16_rn(xf), wh = bf16_rn(wf);
+        f += xh * wh;                                                // (bf16 x bf16 products are exact in fp32)
+        if (g_mma_model == 3) {
+            const float xl = bf16_rn(xf - xh), wl = bf16_rn(wf - wh);
+            f += xh * wl;
+            f += xl * wh;
+        }
+    }
+    inline double value() const { return g_mma_model == 0 ? d : (double)f; }
+};
 
 // one finished accumulator value -> its place, through the epilogue of launch.h (bias + LeakyReLU | slope | plain; accumulate rows)
 static void store_out(float* base, long long bstride, int rstride, const float* saved, int acc_lo, int acc_hi, int epilogue, const float* bias,
@@ -100,10 +133,11 @@ static bool run_umma_conv(const UmmaLaunch& L, const OutputFuse* F) {
             if (it == g_packs.end()) return false;                    // a conv whose weights were never packed
             jobs.push_back(&it->second);
         }
-        std::vector<double> acc(L.N), act(L.N);
+        std::vector<Acc> acc(L.N);
+        std::vector<double> act(L.N);
         for (int b = 0; b < L.batch; ++b)
             for (int m = O.m_lo; m < O.m_hi; ++m) {
-                std::fill(acc.begin(), acc.end(), 0.0);
+                std::fill(acc.begin(), acc.end(), Acc());
                 for (int g = 0; g < K.ngroups; ++g) {
                     const UmmaGroup& G = K.groups[g];
                     const PlaneView& P = L.planes[G.plane];
@@ -116,14 +150,14 @@ static bool run_umma_conv(const UmmaLaunch& L, const OutputFuse* F) {
                                 if (wt == pj->W.end()) return false;
                                 const double* w = wt->second.data() + (size_t)k * pj->NPAD;
                                 const int nmax = (L.N - pj->n0) < pj->NPAD ? (L.N - pj->n0) : pj->NPAD;
-                                for (int n = 0; n < nmax; ++n) acc[pj->n0 + n] += x * w[n];
+                                for (int n = 0; n < nmax; ++n) acc[pj->n0 + n].mac(x, w[n]);
                             }
                         }
                 }
                 for (int nn = 0; nn < L.N; ++nn) {
                     const int h = (L.pairC > 0 && nn >= L.pairC) ? 1 : 0;
                     const int col = nn - h * L.pairC;
-                    double v = acc[nn];
+                    double v = acc[nn].value();
                     if (L.epilogue == EPI_BIAS_LRELU) act[nn] = lrelu(v + (L.bias ? L.bias[L.pairC > 0 ? col : nn] : 0.0));
                     if (L.pairC > 0) {
                         if (m < O.lo_h[h] || m >= O.hi_h[h]) continue;
@@ -243,15 +277,18 @@ static void run_conv(const ConvLaunch& L) {
 }
 
 static void wgrad_group(const PlaneView& P, const PlaneView& G, int m_lo, int m_hi, int nt, const int* d, const int* woff, float* dW,
-                        int w_sp, int w_sg, double scale, int batch) {
+                        int w_sp, int w_sg, double scale, int batch, bool tensor_core = false) {
+    const int keep = g_mma_model;
+    if (!tensor_core) g_mma_model = 0;                 // the CUDA-core kernels are exact fp32
     for (int t = 0; t < nt; ++t)
         for (int cp = 0; cp < P.C; ++cp)
             for (int cg = 0; cg < G.C; ++cg) {
-                double s = 0.0;
+                Acc s;
                 for (int b = 0; b < batch; ++b)
-                    for (int m = m_lo; m < m_hi; ++m) s += plane_at(P, b, (long long)m + d[t], cp) * plane_at(G, b, m, cg);
-                dW[(long long)woff[t] + (long long)cp * w_sp + (long long)cg * w_sg] += (float)(s * scale);
+                    for (int m = m_lo; m < m_hi; ++m) s.mac(plane_at(P, b, (long long)m + d[t], cp), plane_at(G, b, m, cg));
+                dW[(long long)woff[t] + (long long)cp * w_sp + (long long)cg * w_sg] += (float)(s.value() * scale);
             }
+    g_mma_model = keep;
 }
 
 static void run_output_fwd(const OutputLaunch& L) {
@@ -434,7 +471,7 @@ bool execute(const std::string& name, void** args) {
         const UmmaWgradLaunch& L = *static_cast<const UmmaWgradLaunch*>(args[0]);
         for (int g = 0; g < L.ngroups; ++g) {
             const WgGroup& G = L.grp[g];
-            wgrad_group(G.P, G.G, G.m_lo, G.m_hi, G.ntaps, G.d, G.woff, L.dW, L.w_sp, L.w_sg, L.scale, L.batch);
+            wgrad_group(G.P, G.G, G.m_lo, G.m_hi, G.ntaps, G.d, G.woff, L.dW, L.w_sp, L.w_sg, L.scale, L.batch, true);
         }
         return true;
     }
@@ -547,6 +584,10 @@ bool execute(const std::string& name, void** args) {
     return false;
 }
 
-void reset() { g_packs.clear(); }
+void reset() {
+    g_packs.clear();
+    const char* e = getenv("FAKECUDA_MMA_MODEL");
+    g_mma_model = e ? atoi(e) : 0;
+}
 
 }  // namespace cpudev

@@ -148,3 +148,18 @@ def test_wider_output_filter_and_other_filter_sizes():
             assert_matches_oracle(res)
         except AssertionError as ex:
             raise AssertionError("%s: %s" % (label, ex))
+
+
+@needs_sim
+def test_arithmetic_model_of_the_three_mma_scheme_meets_the_parity_bar_and_a_single_bf16_pass_does_not():
+    """every fp32 operand is split into two bf16 (hi, lo) and a product is three bf16 MMAs (hi*hi + hi*lo + lo*hi,
+    fp32 accumulation).  With the reference routines of the tensor-core launches switched to that arithmetic
+    (FAKECUDA_MMA_MODEL=3) the step stays two orders of magnitude inside the 1e-4 parity bar of BASELINE.json - the same ~5e-6 the
+    GPU measures - while a single bf16 pass (=1) misses it by a factor of 40: why the kernels issue three MMAs per product."""
+    case = (["baseline_stereo"], dict(num_layers=4), 2, 600)
+    res = run_many([("exact", *case, FORCED, 1.0), ("three_mma", *case, dict(FORCED, FAKECUDA_MMA_MODEL="3"), 1.0),
+                    ("one_mma", *case, dict(FORCED, FAKECUDA_MMA_MODEL="1"), 1.0)])
+    exact, three, one = (res[k]["step1"] for k in ("exact", "three_mma", "one_mma"))
+    assert exact["outputs_rel"] < 1e-6 and exact["grad_worst_rel"] < 1e-5
+    assert 1e-6 < three["outputs_rel"] < 3e-5 and three["grad_worst_rel"] < 1e-4 and three["loss_rel"] < 1e-5
+    assert one["outputs_rel"] > 1e-3 and one["grad_worst_rel"] > 1e-3
