@@ -99,6 +99,10 @@ def main():
     wun.check(lib.wun_forward(h, P(par), P(mix_d), batch, 0, P(out_d), P(ws_inf), ws_inf_bytes, MAIN))
     want = O.forward_np(cfg, o_par, mix, False)
     res["infer_outputs_rel"] = max(rel(out_d.reshape(K, batch, t_out, C)[k], want[s]) for k, s in enumerate(names))
+    # get_output(training=True) without a loss: no test-time clip (UnetAudioSeparator.py:131-136, Utils.py:89-92)
+    wun.check(lib.wun_forward(h, P(par), P(mix_d), batch, 1, P(out_d), P(ws_inf), ws_inf_bytes, MAIN))
+    want = O.forward_np(cfg, o_par, mix, True)
+    res["train_mode_outputs_rel"] = max(rel(out_d.reshape(K, batch, t_out, C)[k], want[s]) for k, s in enumerate(names))
 
     # window gather / scatter of predict_track (Evaluate.py:125-139): hop = T_out, the last window shifted back, plain overwrite
     n_frames = 3 * t_out - 7

@@ -59,6 +59,7 @@ def assert_matches_oracle(res):
         assert r["outputs_rel"] < 1e-5, (step, r)
         assert r["params_rel"] < 1e-5, (step, r)
     assert res["infer_outputs_rel"] < 1e-4, res["infer_outputs_rel"]
+    assert res["train_mode_outputs_rel"] < 1e-4, res["train_mode_outputs_rel"]
     assert res["gather_exact"] and res["scatter_exact"]          # predict_track's window tiling (Evaluate.py:125-139)
     assert abs(res["adam_state"][0] - 0.9 ** 3) < 1e-6 and abs(res["adam_state"][1] - 0.999 ** 3) < 1e-6 and res["adam_state"][2] == 2.0
 
