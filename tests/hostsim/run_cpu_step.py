@@ -50,6 +50,11 @@ def main():
         if k.endswith("/bias") or "interp" in k:
             params[k] = rng.uniform(-0.3, 0.3, size=params[k].shape).astype(np.float32)
     mix, targets = O.synthetic_batch(cfg, batch, t_in, t_out, seed=13)
+    shard = os.environ.get("HOSTSIM_SHARD")                 # "lo:hi": this process is one data-parallel rank holding examples [lo, hi)
+    if shard:
+        lo, hi = (int(x) for x in shard.split(":"))
+        mix, targets = mix[lo:hi], {k: v[lo:hi] for k, v in targets.items()}
+        batch = hi - lo
     names = list(cfg["source_names"])
     K, C = len(names), O.num_channels(cfg)
 
@@ -86,6 +91,8 @@ def main():
             e = rel(grads[off:off + numel], np.asarray(grads_o[pname]).reshape(-1) * grad_scale)
             if e > worst:
                 worst, which = e, pname
+        if step == 1 and os.environ.get("HOSTSIM_DUMP_GRADS"):
+            np.save(os.environ["HOSTSIM_DUMP_GRADS"], grads[:n].copy())
         res["step%d" % step] = {
             "loss": float(loss[0]), "loss_oracle": float(loss_o), "loss_rel": abs(float(loss[0]) - loss_o) / abs(loss_o),
             "grad_worst_rel": worst, "grad_worst_tensor": which,

@@ -164,3 +164,22 @@ def test_arithmetic_model_of_the_three_mma_scheme_meets_the_parity_bar_and_a_sin
     assert exact["outputs_rel"] < 1e-6 and exact["grad_worst_rel"] < 1e-5
     assert 1e-6 < three["outputs_rel"] < 3e-5 and three["grad_worst_rel"] < 1e-4 and three["loss_rel"] < 1e-5
     assert one["outputs_rel"] > 1e-3 and one["grad_worst_rel"] > 1e-3
+
+
+@needs_sim
+def test_sharded_gradients_sum_to_the_single_device_gradient(tmp_path):
+    """The data-parallel invariant (Training.py:62: the loss is a mean over the batch) at the level of the
+    engine's real host code: two ranks with half the batch each and grad_scale = local / global produce gradients whose SUM (what
+    the all-reduce computes) is the gradient one device computes for the whole batch."""
+    import numpy as np
+    case = (["full_multi_instrument"], dict(num_layers=3, upsampling="learned"), 4, 260)
+    files = {k: str(tmp_path / (k + ".npy")) for k in ("all", "r0", "r1")}
+    res = run_many([("all", *case, dict(FORCED, HOSTSIM_DUMP_GRADS=files["all"]), 1.0),
+                    ("r0", *case, dict(FORCED, HOSTSIM_DUMP_GRADS=files["r0"], HOSTSIM_SHARD="0:2"), 0.5),
+                    ("r1", *case, dict(FORCED, HOSTSIM_DUMP_GRADS=files["r1"], HOSTSIM_SHARD="2:4"), 0.5)])
+    for r in res.values():
+        assert r["step1"]["grad_worst_rel"] < 1e-4 and r["unknown"] == []
+    g = {k: np.load(f).astype(np.float64) for k, f in files.items()}
+    err = np.linalg.norm(g["r0"] + g["r1"] - g["all"]) / np.linalg.norm(g["all"])
+    assert err < 1e-6, err
+    assert np.linalg.norm(g["r0"] - g["r1"]) / np.linalg.norm(g["all"]) > 1e-2          # the shards do differ
