@@ -130,6 +130,30 @@ def main():
         want_p[:, s0:s0 + t_out] = outs[:, w]
     res["scatter_exact"] = bool(np.array_equal(preds.reshape(K, n_frames, C), want_p))
 
+    # the whole predict_track pipeline through the C-ABI (Evaluate.py:82-145 as wave-u-net_b200/Evaluate.py drives it): pad, gather
+    # the windows, batched forward at test time, scatter - against the oracle's window-by-window restatement
+    if os.environ.get("HOSTSIM_PREDICT"):
+        n_audio = 2 * t_out + t_out // 3
+        audio = (rng.uniform(-1.0, 1.0, size=(n_audio, C)) * 0.5).astype(np.float32)
+        pad = (t_in - t_out) // 2
+        padded_a = np.ascontiguousarray(np.pad(audio, [(pad, pad), (0, 0)]))
+        starts_a = []
+        for pos in range(0, n_audio, t_out):
+            starts_a.append(n_audio - t_out if pos + t_out > n_audio else pos)
+        nwa = len(starts_a)
+        sta = np.asarray(starts_a, np.int64)
+        win_a = aligned(nwa * t_in * C)
+        wun.check(lib.wun_gather_windows(h, P(padded_a), padded_a.shape[0], P(sta), nwa, P(win_a), MAIN))
+        ws_p_bytes = eng.workspace_bytes(nwa, False)
+        ws_p = aligned(ws_p_bytes // 4 + 64)
+        outs_a = aligned(K * nwa * t_out * C)
+        wun.check(lib.wun_forward(h, P(par), P(win_a), nwa, 0, P(outs_a), P(ws_p), ws_p_bytes, MAIN))
+        preds_a = aligned(K * n_audio * C)
+        wun.check(lib.wun_scatter_windows(h, P(outs_a), P(sta), nwa, P(preds_a), n_audio, MAIN))
+        want_a = O.predict_track(cfg, o_par, audio, t_in, t_out)
+        res["predict_rel"] = max(rel(preds_a.reshape(K, n_audio, C)[k], want_a[s]) for k, s in enumerate(names))
+        res["predict_windows"] = nwa
+
     nbytes = fake.fakecuda_trace(None, 0)
     buf = ctypes.create_string_buffer(int(nbytes))
     fake.fakecuda_trace(buf, nbytes)

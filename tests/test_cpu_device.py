@@ -183,3 +183,14 @@ def test_sharded_gradients_sum_to_the_single_device_gradient(tmp_path):
     err = np.linalg.norm(g["r0"] + g["r1"] - g["all"]) / np.linalg.norm(g["all"])
     assert err < 1e-6, err
     assert np.linalg.norm(g["r0"] - g["r1"]) / np.linalg.norm(g["all"]) > 1e-2          # the shards do differ
+
+
+@needs_sim
+def test_predict_track_pipeline_through_the_c_abi_matches_the_oracle():
+    """Evaluate.py:82-145 end to end on the CPU device: context padding, window gather (the last window shifted back), ONE batched
+    test-time forward over all windows, scatter with overwrite - vs the oracle's window-by-window loop; stereo context model and
+    mono 'same'-padding model."""
+    res = run_many([("context_stereo", ["baseline_stereo"], dict(num_layers=3), 1, 300, dict(FORCED, HOSTSIM_PREDICT="1"), 1.0),
+                    ("same_mono_learned", ["baseline"], dict(num_layers=3, upsampling="learned"), 1, 256, dict(HOSTSIM_PREDICT="1"), 1.0)])
+    for label, r in res.items():
+        assert r["predict_windows"] == 3 and r["predict_rel"] < 1e-4, (label, r["predict_rel"])
