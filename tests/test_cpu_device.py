@@ -24,15 +24,25 @@ sys.path.insert(0, os.path.join(HERE, "hostsim"))
 import schedule  # noqa: E402
 
 
-def _simulation_library():
+_SIM = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_once():
+    """Built when the first test of this module RUNS, not at collection (a `-m gpu` run collects this file but runs none of it)."""
+    global _SIM
     try:
-        return schedule.build()
+        _SIM = schedule.build()
     except Exception:                                        # noqa: BLE001 (tests/test_stream_schedule.py reports build failures)
-        return None
+        _SIM = None
+    yield
 
 
-_SIM = _simulation_library()
-needs_sim = pytest.mark.skipif(_SIM is None, reason="host simulation of the engine not built (needs nvcc and g++)")
+@pytest.fixture(autouse=True)
+def _need_simulation(_build_once):
+    if _SIM is None:
+        pytest.skip("host simulation of the engine not built (needs nvcc and g++)")
+
 
 FORCED = {"WUN_PERS_MIN": "0", "WUN_FOLD": "0", "WUN_PAIR_MIN_CTAS": "1", "WUN_PAIR_DGRAD": "1"}
 
@@ -81,7 +91,6 @@ def run_many(cases):
         return {k: f.result() for k, f in futs.items()}
 
 
-@needs_sim
 @pytest.mark.parametrize("variant", ["planner_default", "gpu_filling_variants_forced"])
 def test_two_training_steps_and_inference_on_the_cpu_device_match_the_oracle(variant):
     forced = variant.startswith("gpu")
@@ -114,7 +123,6 @@ SWITCHES = [
 ]
 
 
-@needs_sim
 def test_every_structural_switch_gives_the_same_step():
     cases = []
     for sw in SWITCHES:
@@ -128,7 +136,6 @@ def test_every_structural_switch_gives_the_same_step():
             raise AssertionError("%s: %s" % (label, ex))
 
 
-@needs_sim
 def test_batch_sizes_of_the_data_parallel_splits():
     """The planner's choices depend on the batch (pair merging, splits, folded tiles): the per-GPU batches the scaling runs use."""
     cases = [("batch %d" % b, ["full_multi_instrument"], dict(num_layers=4), b, 260, None, 1.0 / 8) for b in (1, 3, 4, 8)]
@@ -139,7 +146,6 @@ def test_batch_sizes_of_the_data_parallel_splits():
             raise AssertionError("%s: %s" % (label, ex))
 
 
-@needs_sim
 def test_wider_output_filter_and_other_filter_sizes():
     """output_filter_size > 1 (no fused epilogue: the separate output kernels with 'same' / 'valid' taps), other filter widths."""
     cases = [("same padding, ofs 3", ["baseline"], dict(num_layers=3, output_filter_size=3, filter_size=9, merge_filter_size=3), 2, 256, FORCED, 1.0),
@@ -151,7 +157,6 @@ def test_wider_output_filter_and_other_filter_sizes():
             raise AssertionError("%s: %s" % (label, ex))
 
 
-@needs_sim
 def test_arithmetic_model_of_the_three_mma_scheme_meets_the_parity_bar_and_a_single_bf16_pass_does_not():
     """every fp32 operand is split into two bf16 (hi, lo) and a product is three bf16 MMAs (hi*hi + hi*lo + lo*hi,
     fp32 accumulation).  With the reference routines of the tensor-core launches switched to that arithmetic
@@ -166,7 +171,6 @@ def test_arithmetic_model_of_the_three_mma_scheme_meets_the_parity_bar_and_a_sin
     assert one["outputs_rel"] > 1e-3 and one["grad_worst_rel"] > 1e-3
 
 
-@needs_sim
 def test_sharded_gradients_sum_to_the_single_device_gradient(tmp_path):
     """The data-parallel invariant (Training.py:62: the loss is a mean over the batch) at the level of the
     engine's real host code: two ranks with half the batch each and grad_scale = local / global produce gradients whose SUM (what
@@ -185,7 +189,6 @@ def test_sharded_gradients_sum_to_the_single_device_gradient(tmp_path):
     assert np.linalg.norm(g["r0"] - g["r1"]) / np.linalg.norm(g["all"]) > 1e-2          # the shards do differ
 
 
-@needs_sim
 def test_predict_track_pipeline_through_the_c_abi_matches_the_oracle():
     """Evaluate.py:82-145 end to end on the CPU device: context padding, window gather (the last window shifted back), ONE batched
     test-time forward over all windows, scatter with overwrite - vs the oracle's window-by-window loop; stereo context model and

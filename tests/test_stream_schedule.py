@@ -23,15 +23,24 @@ import schedule  # noqa: E402
 
 
 
-def _simulation_library():
+_SIM, _WHY = None, "not built yet"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_once():
+    """Built when the first test of this module RUNS, not at collection (a `-m gpu` run collects this file but runs none of it)."""
+    global _SIM, _WHY
     try:
-        return schedule.build(), ""
+        _SIM, _WHY = schedule.build(), ""
     except Exception as ex:                                  # noqa: BLE001 - a broken tool chain must not take the suite down
-        return None, "%s: %s" % (type(ex).__name__, str(ex)[:200])
+        _SIM, _WHY = None, "%s: %s" % (type(ex).__name__, str(ex)[:200])
+    yield
 
 
-_SIM, _WHY = _simulation_library()
-needs_sim = pytest.mark.skipif(_SIM is None, reason="host simulation of the engine not built (needs nvcc and g++) " + _WHY)
+@pytest.fixture(autouse=True)
+def _need_simulation(request, _build_once):
+    if _SIM is None and "simulation_library_builds" not in request.node.name:
+        pytest.skip("host simulation of the engine not built (needs nvcc and g++) " + _WHY)
 
 
 def test_the_simulation_library_builds_where_the_tool_chain_exists():
@@ -62,7 +71,6 @@ def assert_race_free(meta, ops):
     return stats
 
 
-@needs_sim
 @pytest.mark.parametrize("name,named,ov,batch,nf", FAMILIES, ids=[c[0] for c in FAMILIES])
 def test_forced_gpu_filling_variants_are_race_free_incl_bucketed_allreduce(name, named, ov, batch, nf):
     meta, ops = schedule.trace("train_dp", named, ov, batch, nf, FORCED)
@@ -77,7 +85,6 @@ def test_forced_gpu_filling_variants_are_race_free_incl_bucketed_allreduce(name,
     assert lib_launches == 2 * (meta["launches_reported"] + 4)
 
 
-@needs_sim
 @pytest.mark.parametrize("name,named,ov,batch,nf", FAMILIES[:3], ids=[c[0] for c in FAMILIES[:3]])
 def test_default_planner_choices_are_race_free(name, named, ov, batch, nf):
     meta, ops = schedule.trace("train_dp", named, ov, batch, nf)
@@ -90,7 +97,6 @@ SWITCHES = ["WUN_SPLIT_AHEAD=0", "WUN_SIDE_STREAM=0", "WUN_DGRAD_PAR=0", "WUN_FI
             "WUN_EPI2=0", "WUN_PERSISTENT=0"]
 
 
-@needs_sim
 @pytest.mark.parametrize("switch", SWITCHES)
 def test_every_switch_of_the_stream_structure_in_its_other_position(switch):
     env = dict(FORCED)
@@ -100,14 +106,12 @@ def test_every_switch_of_the_stream_structure_in_its_other_position(switch):
     assert_race_free(meta, ops)
 
 
-@needs_sim
 def test_inference_and_training_with_estimates_share_a_handle_without_races():
     for scenario in ("infer", "train_out"):
         meta, ops = schedule.trace(scenario, ["full"], dict(num_layers=4, num_initial_filters=16), 2, 1500, FORCED)
         assert assert_race_free(meta, ops)["joined_into_caller"]
 
 
-@needs_sim
 def test_an_unjoined_stream_is_noticed():
     """Drop the last wait of the caller's stream (the join of the weight-gradient stream): the trace no longer ends joined."""
     meta, ops = schedule.trace("train", ["baseline_stereo"], dict(num_layers=3), 1, 300, FORCED)
@@ -118,7 +122,6 @@ def test_an_unjoined_stream_is_noticed():
     assert not schedule.check(meta, cut, init_regions=())[1]["joined_into_caller"]
 
 
-@needs_sim
 def test_the_checker_reports_every_necessary_wait_when_it_is_dropped():
     """Teeth: remove one cudaStreamWaitEvent at a time from a race-free trace.  Most waits are the only ordering between two
     conflicting launches - the checker must name that pair; the rest are implied by other event chains.  The named pairs must
@@ -148,7 +151,6 @@ def test_the_checker_reports_every_necessary_wait_when_it_is_dropped():
     assert any(a == "split_views_kernel" and (b.startswith("plane_conv_umma") or b == "upsample_bwd_kernel") for a, b in pairs)
 
 
-@needs_sim
 def test_steady_state_steps_create_no_streams_or_events():
     """include/wun.h: "no hidden synchronisation, allocation or host<->device copy inside forward / backward / adam".  The
     internal streams and events are created by the first call (before a CUDA graph of the step would be captured); the second
@@ -167,7 +169,6 @@ BENCHMARK_SIZES = [("baseline_stereo", 16, "train"), ("full", 16, "train"), ("fu
                    ("full_multi_instrument", 4, "train"), ("baseline", 16, "train"), ("full_44KHz", 16, "infer")]
 
 
-@needs_sim
 @pytest.mark.parametrize("preset,batch,scenario", BENCHMARK_SIZES, ids=["%s_b%d" % (p, b) for p, b, _ in BENCHMARK_SIZES])
 def test_launch_geometry_at_the_benchmark_sizes_respects_the_hardware_limits(preset, batch, scenario):
     """The grid, block, dynamic shared memory and cluster width the engine REALLY passes to the runtime for every launch of the
@@ -185,7 +186,6 @@ def test_launch_geometry_at_the_benchmark_sizes_respects_the_hardware_limits(pre
         assert pers and all(g[0] <= 148 and g[1] == 1 and g[2] == 1 for g in pers), pers[:3]
 
 
-@needs_sim
 def test_the_limit_check_notices_an_oversized_launch():
     meta, ops = schedule.trace("infer", ["baseline_stereo"], dict(num_layers=3), 1, 300)
     i = next(k for k, o in enumerate(ops) if o[0] == "L" and o[4] is not None and o[4][6] > 49152)
