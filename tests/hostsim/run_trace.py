@@ -7,7 +7,8 @@ kernel runs); the caller's stream and the data-parallel communication stream are
 usage: run_trace.py <scenario> <batch> <num_frames> <json overrides> <preset> [<preset> ...]
 scenarios: train (two consecutive steps: forward_backward + device Adam), train_dp (the same with the bucketed gradient
 all-reduce of wun/parallel.py on a communication stream), infer (two forward calls), train_out (training step that also
-returns the source estimates, then an inference call on the same handle)."""
+returns the source estimates, then an inference call on the same handle), train_validate (training steps alternating with a
+validation forward at another batch size)."""
 import ctypes
 import json
 import os
@@ -47,9 +48,10 @@ def main():
     lib, h = wun.lib, eng._h
     K, C = len(cfg["source_names"]), (1 if cfg["mono_downmix"] else 2)
     ws_bytes = eng.workspace_bytes(batch, True)
-    ws_inf = eng.workspace_bytes(batch, False)
-    sizes = {"ws": ws_bytes, "params": 4 * eng.param_numel, "grads": 4 * eng.param_numel, "mix": 4 * batch * t_in * C,
-             "targets": 4 * K * batch * t_out * C, "outputs": 4 * K * batch * t_out * C, "loss": 4, "adam_m": 4 * eng.param_numel,
+    batch_inf = batch + 1 if scenario == "train_validate" else batch       # validation runs at its own batch size
+    ws_inf = eng.workspace_bytes(batch_inf, False)
+    sizes = {"ws": ws_bytes, "params": 4 * eng.param_numel, "grads": 4 * eng.param_numel, "mix": 4 * batch_inf * t_in * C,
+             "targets": 4 * K * batch * t_out * C, "outputs": 4 * K * batch_inf * t_out * C, "loss": 4, "adam_m": 4 * eng.param_numel,
              "adam_v": 4 * eng.param_numel, "adam_state": 12, "ws_infer": ws_inf}
     VP = ctypes.c_void_p
 
@@ -87,6 +89,14 @@ def main():
             user("E %d %d" % (done, COMM))
             user("S %d %d" % (MAIN, done))
             adam()
+    elif scenario == "train_validate":
+        # Training.optimise's pattern (Training.py:123-150): training steps, a validation forward at another batch size on its own
+        # workspace, training again - one handle, the internal streams and events shared by all of it
+        for _ in range(2):
+            fwd_bwd(False)
+            adam()
+            wun.check(lib.wun_forward(h, VP(addr("params")), VP(addr("mix")), batch_inf, 0, VP(addr("outputs")), VP(addr("ws_infer")),
+                                      ws_inf, VP(MAIN)))
     elif scenario == "infer":
         for _ in range(2):
             wun.check(lib.wun_forward(h, VP(addr("params")), VP(addr("mix")), batch, 0, VP(addr("outputs")), VP(addr("ws_infer")),

@@ -112,6 +112,14 @@ def test_inference_and_training_with_estimates_share_a_handle_without_races():
         assert assert_race_free(meta, ops)["joined_into_caller"]
 
 
+def test_training_alternating_with_validation_at_another_batch_size():
+    """Training.optimise (Training.py:123-150) on one handle: the workspaces differ, the internal streams and events do not."""
+    meta, ops = schedule.trace("train_validate", ["baseline_stereo"], dict(num_layers=4), 2, 1500, FORCED)
+    assert assert_race_free(meta, ops)["joined_into_caller"]
+    meta, ops = schedule.trace("train_validate", ["full"], dict(num_layers=3, num_initial_filters=16), 3, 500)
+    assert assert_race_free(meta, ops)["joined_into_caller"]
+
+
 def test_an_unjoined_stream_is_noticed():
     """Drop the last wait of the caller's stream (the join of the weight-gradient stream): the trace no longer ends joined."""
     meta, ops = schedule.trace("train", ["baseline_stereo"], dict(num_layers=3), 1, 300, FORCED)
