@@ -288,3 +288,60 @@ def test_device_prefetcher_slot_protocol(monkeypatch):
                   ("wait", free[0], "copy"), ("record", ready[0], "copy"),      # ... only behind the copy that drained it
                   ("wait", ready[1], "compute"), ("record", free[1], "compute"),
                   ("wait", ready[0], "compute"), ("record", free[0], "compute")]
+
+
+def test_predict_track_host_logic_with_a_stub_engine():
+    """Evaluate.predict_track's own work (Evaluate.py:82-145: mono mix / channel tiling, extension of short inputs, context
+    padding - zero-filled on the device -, window starts with the shifted last window, batching, scatter, removal of the
+    extension) with a stand-in engine on CPU tensors whose "network" returns (k + 1) x the centre crop of every window: the
+    separation of source k must then be exactly (k + 1) x the (down-mixed / tiled) input, frame for frame."""
+    import numpy as np
+    import torch
+    import Evaluate
+
+    class StubEngine(object):
+        def __init__(self, t_in, t_out, K):
+            self.t_in, self.t_out, self.K = t_in, t_out, K
+
+        def gather_windows(self, padded, starts, out):
+            for i, s0 in enumerate(starts.tolist()):
+                out[i] = padded[s0:s0 + self.t_in]
+
+        def forward(self, params, batch, training=False):
+            assert training is False and batch.shape[1] == self.t_in
+            crop = (self.t_in - self.t_out) // 2
+            core = batch[:, crop:crop + self.t_out, :]
+            return torch.stack([core * float(k + 1) for k in range(self.K)])
+
+        def scatter_windows(self, outs, starts, preds):
+            for w, s0 in enumerate(starts.tolist()):
+                preds[:, s0:s0 + self.t_out] = outs[:, w]
+
+    class StubSeparator(object):
+        params = None
+
+        def __init__(self, t_in, t_out, K, C):
+            self.t_in, self.t_out, self.K, self.C = t_in, t_out, K, C
+
+        def get_padding(self, shape):
+            return np.array([shape[0], self.t_in, self.C]), np.array([shape[0], self.t_out, self.C])
+
+        def engine(self, input_frames=None):
+            assert input_frames == self.t_in
+            return StubEngine(self.t_in, self.t_out, self.K)
+
+        def _ensure_params(self, eng, device, create=False):
+            pass
+
+    rng = np.random.default_rng(3)
+    for mono_downmix, in_ch, n_frames in ((False, 2, 1000), (False, 2, 333), (False, 1, 700), (True, 2, 650), (False, 2, 40), (False, 2, 297)):
+        cfg = {"mono_downmix": mono_downmix, "num_frames": 99, "source_names": ["a", "b", "c"]}
+        C = 1 if mono_downmix else 2
+        sep = StubSeparator(t_in=139, t_out=99, K=3, C=C)
+        audio = rng.standard_normal((n_frames, in_ch)).astype(np.float32)
+        got = Evaluate.predict_track(cfg, sep, audio, batch_windows=4, device="cpu")
+        want = np.mean(audio, axis=1, keepdims=True) if mono_downmix else (np.tile(audio, [1, 2]) if in_ch == 1 else audio)
+        assert list(got) == ["a", "b", "c"]
+        for k, name in enumerate(got):
+            assert got[name].shape == (n_frames, C) and got[name].dtype == np.float32
+            np.testing.assert_array_equal(got[name], want * np.float32(k + 1), err_msg="%s %s" % (name, (mono_downmix, in_ch, n_frames)))

@@ -17,6 +17,8 @@ CASES = [
     ("M5 full (learned upsampling), batch 16", "train_dp", ["full"], 16),
     ("M6 full_multi_instrument, batch 4 (global 32 over 8 GPUs)", "train_dp", ["full_multi_instrument"], 4),
     ("M6 full_multi_instrument, batch 16 (global 32 over 2 GPUs)", "train_dp", ["full_multi_instrument"], 16),
+    ("M6 full_multi_instrument, batch 8 (global 32 over 4 GPUs)", "train_dp", ["full_multi_instrument"], 8),
+    ("M6 full_multi_instrument, batch 32 (global 32 on one GPU; 4 GB workspace)", "train_dp", ["full_multi_instrument"], 32),
     ("M1 baseline (same padding, mono), batch 16", "train_dp", ["baseline"], 16),
     ("Predict: full_44KHz, 16 windows per batch, two forward calls", "infer", ["full_44KHz"], 16),
 ]

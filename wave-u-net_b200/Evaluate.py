@@ -46,8 +46,7 @@ def predict_track(model_config, separator, mix_audio, batch_windows=16, device="
         extra_pad = t_in - mix_audio.shape[0]
         mix_audio = np.pad(mix_audio, [(0, extra_pad), (0, 0)], mode="constant", constant_values=0.0)
     n_frames, C = mix_audio.shape
-    pad = (t_in - t_out) // 2
-    padded = np.pad(mix_audio, [(pad, pad), (0, 0)], mode="constant", constant_values=0.0)
+    pad = (t_in - t_out) // 2                                   # context on both sides (Evaluate.py:121-122), zero-filled ON the device
 
     eng = separator.engine(input_frames=t_in)
     names = list(model_config["source_names"])
@@ -56,7 +55,9 @@ def predict_track(model_config, separator, mix_audio, batch_windows=16, device="
     rank, ws = parallel.world()
     lo, hi = parallel.shard_range(len(starts_all), rank, ws)
 
-    padded_d = torch.from_numpy(np.ascontiguousarray(padded)).to(device)
+    padded_d = torch.zeros((n_frames + 2 * pad, C), dtype=torch.float32, device=device)
+    padded_d[pad:pad + n_frames].copy_(torch.from_numpy(np.ascontiguousarray(mix_audio)))      # (a host-side np.pad of a 3-minute
+    # track costs as much as a third of the whole separation)
     preds_local = torch.empty((K, hi - lo, t_out, C), dtype=torch.float32, device=device)
     for b0 in range(lo, hi, batch_windows):
         b1 = min(b0 + batch_windows, hi)
