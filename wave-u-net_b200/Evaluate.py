@@ -59,9 +59,10 @@ def predict_track(model_config, separator, mix_audio, batch_windows=16, device="
     padded_d[pad:pad + n_frames].copy_(torch.from_numpy(np.ascontiguousarray(mix_audio)))      # (a host-side np.pad of a 3-minute
     # track costs as much as a third of the whole separation)
     preds_local = torch.empty((K, hi - lo, t_out, C), dtype=torch.float32, device=device)
+    st_all = torch.tensor(starts_all, dtype=torch.int64, device=device)          # one upload; the batches take slices of it
     for b0 in range(lo, hi, batch_windows):
         b1 = min(b0 + batch_windows, hi)
-        st = torch.tensor(starts_all[b0:b1], dtype=torch.int64, device=device)
+        st = st_all[b0:b1]
         batch = torch.empty((b1 - b0, t_in, C), dtype=torch.float32, device=device)
         eng.gather_windows(padded_d, st, batch)
         separator._ensure_params(eng, padded_d.device, create=False)
@@ -70,7 +71,6 @@ def predict_track(model_config, separator, mix_audio, batch_windows=16, device="
     preds_all = parallel.gather_window_predictions(preds_local, len(starts_all))
     # scatter (overwrite; the shifted last window wins where it overlaps its predecessor)
     preds = torch.zeros((K, n_frames, C), dtype=torch.float32, device=device)
-    st_all = torch.tensor(starts_all, dtype=torch.int64, device=device)
     eng.scatter_windows(preds_all.contiguous(), st_all, preds)
     result = preds.cpu().numpy()
     if extra_pad > 0:
