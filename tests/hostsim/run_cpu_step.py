@@ -43,7 +43,26 @@ def main():
     fake.fakecuda_set_execute(1)
 
     cfg = Config.build_config(named, overrides, experiment_id=0)["model_config"]
-    t_in, t_out = O.get_padding(cfg, nf)
+    try:
+        t_in, t_out = O.get_padding(cfg, nf)
+        probe = O.forward_np(cfg, O.init_params(cfg, seed=1), np.zeros((1, t_in, O.num_channels(cfg)), np.float32), False)
+        real_out = int(next(iter(probe.values())).shape[1])
+        if real_out != t_out:
+            # reference quirk: get_padding's formula and the graph disagree for some filter combinations
+            # (UnetAudioSeparator.py:69-76).  The engine's plan walks the graph: its T_out must be the graph's.
+            eng_q = wun.Engine(wun.config_from_model_config(cfg), input_frames=t_in)
+            print(json.dumps({"formula_quirk": True, "formula_t_out": int(t_out), "graph_t_out": real_out, "engine_t_out": int(eng_q.T_out)}))
+            return
+    except AssertionError as ex:                              # infeasible shapes (UnetAudioSeparator.py:55, :121, Utils.py:114-117):
+        engine_error = None                                   # the engine has to refuse them too, with the same exception type
+        try:
+            wcfg = wun.config_from_model_config(cfg)
+            e_in, _ = wun.get_padding(wcfg, nf)
+            wun.Engine(wcfg, input_frames=e_in)
+        except AssertionError as ex2:
+            engine_error = "AssertionError: %s" % str(ex2)[:120]
+        print(json.dumps({"infeasible": True, "oracle_error": str(ex)[:120], "engine_error": engine_error}))
+        return
     params = O.init_params(cfg, seed=11)
     rng = np.random.default_rng(12)
     for k in params:

@@ -197,3 +197,48 @@ def test_predict_track_pipeline_through_the_c_abi_matches_the_oracle():
                     ("same_mono_learned", ["baseline"], dict(num_layers=3, upsampling="learned"), 1, 256, dict(HOSTSIM_PREDICT="1"), 1.0)])
     for label, r in res.items():
         assert r["predict_windows"] == 3 and r["predict_rel"] < 1e-4, (label, r["predict_rel"])
+
+
+def random_model_configs(n, seed):
+    """n reproducible draws from the space of shapes the reference allows (Config.py:9-39 keys the separator reads)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, 5))
+        context = bool(rng.integers(0, 2))
+        # (even filter widths only with 'same' padding: with context they make T_in - T_out odd, which the reference's callers
+        #  assert against - Test.py:25)
+        fs = int(rng.choice([3, 5, 7, 9, 15] if context else [3, 5, 7, 9, 15, 4, 6]))
+        ov = dict(num_layers=L, num_initial_filters=int(rng.choice([4, 8, 12, 16, 24, 40])), filter_size=fs, input_filter_size=fs,
+                  merge_filter_size=int(rng.choice([1, 3, 5] if context else [1, 3, 5, 2])), output_filter_size=int(rng.choice([1, 1, 1, 3])), context=context,
+                  upsampling=str(rng.choice(["linear", "learned"])), output_type=str(rng.choice(["direct", "difference"])),
+                  output_activation=str(rng.choice(["tanh", "linear"])), mono_downmix=bool(rng.integers(0, 2)),
+                  task=str(rng.choice(["voice", "multi_instrument"])))
+        nf = int(rng.integers(40, 200)) if context else int((2 ** L) * rng.integers(4, 24))
+        out.append(("draw%02d" % i, ["baseline"], ov, int(rng.integers(1, 4)), nf, None, 1.0))
+    return out
+
+
+def test_random_model_configurations_on_the_cpu_device():
+    """A seeded sweep over the configuration space (layers, filter widths incl. even ones, channel counts that are not multiples
+    of 8, both paddings, both upsamplers, both output types / activations, mono / stereo, 2 / 4 sources, batch 1-3): whatever
+    mix of tensor-core and CUDA-core launches the planner picks, the step must match the oracle; shapes the reference's asserts
+    reject (UnetAudioSeparator.py:55, :121, Utils.py:114-117) must be rejected by the engine with the same exception type."""
+    cases = random_model_configs(16, seed=2026)
+    results = run_many(cases)
+    feasible = 0
+    for label, named, ov, batch, nf, _, _ in cases:
+        res = results[label]
+        if res.get("infeasible"):
+            assert res["engine_error"] is not None and res["engine_error"].startswith("AssertionError"), (label, ov, nf, res)
+            continue
+        if res.get("formula_quirk"):          # get_padding's formula vs the graph (reference quirk): the plan follows the graph
+            assert res["engine_t_out"] == res["graph_t_out"] != res["formula_t_out"], (label, ov, nf, res)
+            continue
+        feasible += 1
+        try:
+            assert_matches_oracle(res)
+        except AssertionError as ex:
+            raise AssertionError("%s %r batch %d frames %d: %s" % (label, ov, batch, nf, ex))
+    assert feasible >= 10, feasible
