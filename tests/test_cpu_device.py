@@ -65,9 +65,10 @@ def assert_matches_oracle(res):
     for step in ("step1", "step2"):
         r = res[step]
         assert r["loss_rel"] < 1e-5, (step, r)
-        assert r["grad_worst_rel"] < 1e-4, (step, r)
+        ex = r.get("grad_explained")           # None, or the LeakyReLU-slope-flip proof for a gradient that is off (run_cpu_step.py)
+        assert r["grad_worst_rel"] < 1e-4 or (ex and ex["flips"] is not None and ex["worst_after"] < 1e-4), (step, r)
         assert r["outputs_rel"] < 1e-5, (step, r)
-        assert r["params_rel"] < 1e-5, (step, r)
+        assert r["params_rel"] < 1e-5 and r["adam_slots_rel"] < 1e-4, (step, r)
     assert res["infer_outputs_rel"] < 1e-4, res["infer_outputs_rel"]
     assert res["train_mode_outputs_rel"] < 1e-4, res["train_mode_outputs_rel"]
     assert res["gather_exact"] and res["scatter_exact"]          # predict_track's window tiling (Evaluate.py:125-139)
