@@ -243,3 +243,12 @@ def test_random_model_configurations_on_the_cpu_device():
         except AssertionError as ex:
             raise AssertionError("%s %r batch %d frames %d: %s" % (label, ov, batch, nf, ex))
     assert feasible >= 10, feasible
+
+
+def test_shapes_the_reference_asserts_against_are_refused_with_the_same_exception():
+    """'same' padding with a length that does not halve cleanly through every level (UnetAudioSeparator.py:121 asserts the skip and
+    the upsampled tensor have equal length): the oracle raises AssertionError, and so must the engine's planner (WUN_E_SHAPE)."""
+    res = run_many([("odd_length", ["baseline"], dict(num_layers=3), 1, 65, None, 1.0),
+                    ("not_divisible", ["baseline_diff"], dict(num_layers=4, upsampling="learned"), 2, 72, None, 1.0)])
+    for label, r in res.items():
+        assert r.get("infeasible") and (r["engine_error"] or "").startswith("AssertionError"), (label, r)
