@@ -202,3 +202,15 @@ def test_the_limit_check_notices_an_oversized_launch():
     g[7] = 49152                                                     # as if the cudaFuncSetAttribute call had been forgotten
     broken[i] = ops[i][:4] + (tuple(g),)
     assert len(schedule.launch_limit_violations(broken)) == 1 and schedule.launch_limit_violations(ops) == []
+
+
+def test_random_model_configurations_are_race_free_and_within_the_launch_limits():
+    """A seeded sweep over the configuration space (the draws of tests/test_cpu_device.py: layer counts, filter widths, channel
+    counts that fall back to the CUDA-core kernels, both paddings / upsamplers / output types, batch 1-3) with the bucketed
+    all-reduce: whatever mix of launches and streams the planner produces, no race, no out-of-bounds or uninitialised access,
+    every stream joined, every launch within the hardware limits.  (One-off campaigns: 96 draws, none bad.)"""
+    from test_cpu_device import random_model_configs
+    for i, (label, named, ov, batch, nf, _, _) in enumerate(random_model_configs(6, seed=77)):
+        meta, ops = schedule.trace("train_dp", named, ov, batch, nf, FORCED if i % 2 else None)
+        stats = assert_race_free(meta, ops)
+        assert stats["joined_into_caller"] and schedule.launch_limit_violations(ops) == [], (label, ov)
