@@ -48,10 +48,10 @@ def main():
     lib, h = wun.lib, eng._h
     K, C = len(cfg["source_names"]), (1 if cfg["mono_downmix"] else 2)
     ws_bytes = eng.workspace_bytes(batch, True)
-    batch_inf = batch + 1 if scenario == "train_validate" else batch       # validation runs at its own batch size
-    ws_inf = eng.workspace_bytes(batch_inf, False)
+    batch_inf = batch + 1 if scenario in ("train_validate", "train_two_batches") else batch      # validation / the other batch size
+    ws_inf = eng.workspace_bytes(batch_inf, scenario == "train_two_batches")
     sizes = {"ws": ws_bytes, "params": 4 * eng.param_numel, "grads": 4 * eng.param_numel, "mix": 4 * batch_inf * t_in * C,
-             "targets": 4 * K * batch * t_out * C, "outputs": 4 * K * batch_inf * t_out * C, "loss": 4, "adam_m": 4 * eng.param_numel,
+             "targets": 4 * K * batch_inf * t_out * C, "outputs": 4 * K * batch_inf * t_out * C, "loss": 4, "adam_m": 4 * eng.param_numel,
              "adam_v": 4 * eng.param_numel, "adam_state": 12, "ws_infer": ws_inf}
     VP = ctypes.c_void_p
 
@@ -97,6 +97,13 @@ def main():
             adam()
             wun.check(lib.wun_forward(h, VP(addr("params")), VP(addr("mix")), batch_inf, 0, VP(addr("outputs")), VP(addr("ws_infer")),
                                       ws_inf, VP(MAIN)))
+    elif scenario == "train_two_batches":
+        # an epoch whose last batch is smaller / larger: training steps at two batch sizes on one handle, each with its own
+        # workspace (the facade caches one per batch size); the planner's choices, pack arena and split arena differ per batch
+        for b, ws_name, nbytes in ((batch, "ws", ws_bytes), (batch_inf, "ws_infer", ws_inf), (batch, "ws", ws_bytes)):
+            wun.check(lib.wun_forward_backward(h, VP(addr("params")), VP(addr("mix")), VP(addr("targets")), b, None, VP(addr("loss")),
+                                               VP(addr("grads")), 1.0, VP(addr(ws_name)), nbytes, VP(MAIN)))
+            adam()
     elif scenario == "infer":
         for _ in range(2):
             wun.check(lib.wun_forward(h, VP(addr("params")), VP(addr("mix")), batch, 0, VP(addr("outputs")), VP(addr("ws_infer")),

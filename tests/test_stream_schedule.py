@@ -120,6 +120,13 @@ def test_training_alternating_with_validation_at_another_batch_size():
     assert assert_race_free(meta, ops)["joined_into_caller"]
 
 
+def test_training_steps_at_two_batch_sizes_on_one_handle():
+    """The last batch of an epoch has another size: other planner choices, other arena layouts, the same streams and events."""
+    for named, ov, batch, nf, env in ((["baseline_stereo"], dict(num_layers=4), 2, 1500, FORCED), (["full_multi_instrument"], dict(num_layers=3), 3, 300, None)):
+        meta, ops = schedule.trace("train_two_batches", named, ov, batch, nf, env)
+        assert assert_race_free(meta, ops)["joined_into_caller"]
+
+
 def test_an_unjoined_stream_is_noticed():
     """Drop the last wait of the caller's stream (the join of the weight-gradient stream): the trace no longer ends joined."""
     meta, ops = schedule.trace("train", ["baseline_stereo"], dict(num_layers=3), 1, 300, FORCED)
