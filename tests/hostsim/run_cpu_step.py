@@ -154,6 +154,23 @@ def main():
         # (the slots agree to ~1e-5 only: the kernels - like TF's ApplyAdam - form 1 - beta2 in float32, the oracle in double)
         res["step%d" % step]["adam_slots_rel"] = max(rel(m[:n], m_want), rel(v[:n], v_want))
     o_par = engine_params()
+    if os.environ.get("HOSTSIM_OTHER_BATCH") and batch > 1:
+        # the same handle at another batch size (the last batch of an epoch) and back: its own workspace, other planner choices
+        import torch
+        worst_other = 0.0
+        for nb in (batch - 1, batch):
+            wsb = eng.workspace_bytes(nb, True)
+            ws2 = aligned(wsb // 4 + 64)
+            mix2 = aligned(nb * t_in * C); mix2[:] = mix[:nb].reshape(-1)
+            tg2 = aligned(K * nb * t_out * C); tg2[:] = tg[:, :nb].reshape(-1)
+            wun.check(lib.wun_forward_backward(h, P(par), P(mix2), P(tg2), nb, None, P(loss), P(grads), 1.0, P(ws2), wsb, MAIN))
+            tp = O._as_torch(o_par, torch.float64, True)
+            outs64 = O.forward(cfg, tp, torch.as_tensor(mix[:nb]).to(torch.float64), True)
+            l64 = O.mse_loss(cfg, outs64, {k: torch.as_tensor(vv[:nb]).to(torch.float64) for k, vv in targets.items()})
+            g64 = {k: g.numpy() for k, g in zip(tp, torch.autograd.grad(l64, list(tp.values())))}
+            worst_other = max([worst_other, abs(float(loss[0]) - float(l64)) / abs(float(l64))] +
+                              [rel(grads[off:off + numel], g64[pname].reshape(-1)) for pname, shape, off, numel in eng.param_table])
+        res["other_batch_worst_rel"] = worst_other
     res["adam_state"] = [float(x) for x in state[:3]]
     # inference on the same handle (test-time clip), with the updated parameters
     wun.check(lib.wun_forward(h, P(par), P(mix_d), batch, 0, P(out_d), P(ws_inf), ws_inf_bytes, MAIN))

@@ -252,3 +252,13 @@ def test_shapes_the_reference_asserts_against_are_refused_with_the_same_exceptio
                     ("not_divisible", ["baseline_diff"], dict(num_layers=4, upsampling="learned"), 2, 72, None, 1.0)])
     for label, r in res.items():
         assert r.get("infeasible") and (r["engine_error"] or "").startswith("AssertionError"), (label, r)
+
+
+def test_one_handle_at_two_batch_sizes():
+    """After two steps at batch b: a step at b - 1 on its own workspace and one at b again - loss and gradients vs float64
+    autograd through the oracle (the planner's batch-dependent choices must not leak between calls)."""
+    res = run_many([("forced", ["full_multi_instrument"], dict(num_layers=3, upsampling="learned"), 3, 200, dict(FORCED, HOSTSIM_OTHER_BATCH="1"), 1.0),
+                    ("default", ["baseline_stereo"], dict(num_layers=4), 2, 400, dict(HOSTSIM_OTHER_BATCH="1"), 1.0)])
+    for label, r in res.items():
+        assert_matches_oracle(r)
+        assert r["other_batch_worst_rel"] < 1e-4, (label, r["other_batch_worst_rel"])
