@@ -40,7 +40,8 @@ void reset();
 
 namespace {
 
-bool g_execute = false;                              // fakecuda_set_execute(1): carry every launch out on the caller's (host) buffers
+int g_execute = 0;                                   // fakecuda_set_execute(1): carry every launch out on the caller's (host) buffers;
+                                                     // (2): the same under the footprint poison test (registered buffers)
 
 std::mutex g_mu;
 std::vector<std::string> g_trace;
@@ -64,16 +65,20 @@ void emit(const std::string& line) {
 }
 
 // ---- access formatting -------------------------------------------------------------------------------------------------
+struct AccessRec { char mode; bool is_view; uintptr_t base; long long batch, bstride, rlo, rhi, rstride, C, bytes; };
 struct Acc {
     std::string s;
+    std::vector<AccessRec> recs;
     void view(char mode, const void* base, long long batch, long long bstride, long long rlo, long long rhi, long long rstride, long long C) {
         if (!base || rhi <= rlo || C <= 0 || batch <= 0) return;
+        recs.push_back({mode, true, (uintptr_t)base, batch, bstride, rlo, rhi, rstride, C, 0});
         char b[200];
         snprintf(b, sizeof(b), " V:%c:%llu:%lld:%lld:%lld:%lld:%lld:%lld", mode, (unsigned long long)(uintptr_t)base, batch, bstride, rlo, rhi, rstride, C);
         s += b;
     }
     void flat(char mode, const void* p, long long bytes) {
         if (!p || bytes <= 0) return;
+        recs.push_back({mode, false, (uintptr_t)p, 0, 0, 0, 0, 0, 0, bytes});
         char b[120];
         snprintf(b, sizeof(b), " F:%c:%llu:%lld", mode, (unsigned long long)(uintptr_t)p, bytes);
         s += b;
@@ -129,6 +134,14 @@ void decode_umma_conv(Acc& a, const UmmaLaunch& L) {
     if (L.bias) a.flat('R', L.bias, 4LL * (L.pairC > 0 ? L.pairC : L.N));
 }
 
+// weight slice of one term: element (k, n) at W + woff + k * w_sk + n * w_sn, k < Ck, n < ncols (forward: w_sn = 1; dgrad: w_sk = 1)
+void weight_slice(Acc& a, const float* W, long long woff, int Ck, int ncols, int w_sk, int w_sn) {
+    if (w_sn == 1) a.view('R', W + woff, 1, 0, 0, Ck, w_sk, ncols);
+    else if (w_sk == 1) a.view('R', W + woff, 1, 0, 0, ncols, w_sn, Ck);
+    else
+        for (int k = 0; k < Ck; ++k) a.view('R', W + woff + (long long)k * w_sk, 1, 0, 0, ncols, w_sn, 1);
+}
+
 void decode_conv(Acc& a, const ConvLaunch& L) {
     for (int q = 0; q < L.ncls; ++q) {
         const OutView& O = L.cls[q];
@@ -138,8 +151,8 @@ void decode_conv(Acc& a, const ConvLaunch& L) {
             a.plane(L.planes[T.plane], L.batch, (long long)O.m_lo + T.d, (long long)O.m_hi + T.d);
             const PlaneView& P = L.planes[T.plane];
             const int half = L.pairC > 0 ? L.pairC : L.N;
-            if (T.woff >= 0 || L.pairC == 0) a.view('R', L.W + T.woff, 1, 0, 0, P.C, L.w_sk, L.w_sn == 1 ? half : 1);
-            if (L.pairC > 0 && T.woff2 >= 0) a.view('R', L.W + T.woff2, 1, 0, 0, P.C, L.w_sk, L.w_sn == 1 ? half : 1);
+            if (T.woff >= 0 || L.pairC == 0) weight_slice(a, L.W, T.woff, P.C, half, L.w_sk, L.w_sn);
+            if (L.pairC > 0 && T.woff2 >= 0) weight_slice(a, L.W, T.woff2, P.C, half, L.w_sk, L.w_sn);
         }
         out_class(a, O, L.epilogue, L.batch, L.N, L.pairC);
     }
@@ -203,7 +216,7 @@ bool has(const std::string& s, const char* sub) { return s.find(sub) != std::str
 
 // Decodes the global-memory footprint of one launch from its argument array.  Unknown kernels are reported as such: the
 // checker fails on them, so a kernel added to the engine has to be described here before the schedule test passes again.
-std::string decode(const std::string& name, void** args, bool* known) {
+Acc decode(const std::string& name, void** args, bool* known) {
     Acc a;
     *known = true;
     if (has(name, "plane_conv_umma_persistent_out")) {
@@ -239,8 +252,8 @@ std::string decode(const std::string& name, void** args, bool* known) {
             for (int g = 0; g < J.ngroups; ++g)
                 for (int t = J.g_term_begin[g]; t < J.g_term_begin[g] + J.g_nterm[g]; ++t) {
                     const int half = P.pairC > 0 ? P.pairC : P.N;
-                    if (P.woff[t] >= 0 || P.pairC == 0) a.view('R', P.W + P.woff[t], 1, 0, 0, J.g_C[g], P.w_sk, P.w_sn == 1 ? half : 1);
-                    if (P.pairC > 0 && P.woff2[t] >= 0) a.view('R', P.W + P.woff2[t], 1, 0, 0, J.g_C[g], P.w_sk, P.w_sn == 1 ? half : 1);
+                    if (P.woff[t] >= 0 || P.pairC == 0) weight_slice(a, P.W, P.woff[t], J.g_C[g], half, P.w_sk, P.w_sn);
+                    if (P.pairC > 0 && P.woff2[t] >= 0) weight_slice(a, P.W, P.woff2[t], J.g_C[g], half, P.w_sk, P.w_sn);
                 }
         }
     } else if (has(name, "first_fwd_kernel") || has(name, "first_wgrad_kernel")) {
@@ -325,7 +338,84 @@ std::string decode(const std::string& name, void** args, bool* known) {
     } else {
         *known = false;
     }
-    return a.s;
+    return a;
+}
+
+// ---- footprint verification (fakecuda_set_execute(2)): "poison test" ----------------------------------------------------------
+// Before a launch is carried out on the registered host buffers, every word OUTSIDE its decoded footprint is overwritten with a
+// marked NaN; afterwards (a) a word outside the decoded WRITE footprint that no longer holds what it held = a write the decoder
+// does not know about, (b) a NaN in a written word that was not NaN before = the routine read a word outside the decoded READ
+// footprint (NaN propagates through every product, also with zero).  Then the untouched words are restored.  The reference
+// routines reproduce the oracle, so their accesses are the ones the computation needs: the decoded footprints the racecheck
+// relies on are checked to CONTAIN them.
+struct HostBuf { uint8_t* p; size_t bytes; };
+std::vector<HostBuf> g_bufs;
+const uint32_t kPoison = 0x7fc0dead;
+
+void mark_range(std::vector<std::vector<uint8_t>>& mask, uintptr_t a0, long long nbytes, uint8_t bit) {
+    for (size_t i = 0; i < g_bufs.size(); ++i) {
+        const uintptr_t b0 = (uintptr_t)g_bufs[i].p, b1 = b0 + g_bufs[i].bytes;
+        uintptr_t lo = a0 < b0 ? b0 : a0, hi = (a0 + (uintptr_t)nbytes) > b1 ? b1 : (a0 + (uintptr_t)nbytes);
+        if (a0 + (uintptr_t)nbytes <= b0 || a0 >= b1 || hi <= lo) continue;
+        for (size_t w = (lo - b0) / 4; w < (hi - b0 + 3) / 4 && w < mask[i].size(); ++w) mask[i][w] |= bit;
+    }
+}
+
+void mark(std::vector<std::vector<uint8_t>>& mask, const std::vector<AccessRec>& recs) {
+    for (const AccessRec& r : recs) {
+        const uint8_t bit = r.mode == 'R' ? 1 : 2;                  // W and A both write
+        if (!r.is_view) { mark_range(mask, r.base, r.bytes, bit); continue; }
+        for (long long b = 0; b < r.batch; ++b)
+            for (long long row = r.rlo; row < r.rhi; ++row)
+                mark_range(mask, r.base + 4 * (uintptr_t)(b * r.bstride + row * r.rstride), 4 * r.C, bit);
+    }
+}
+
+std::string poison_checked_execute(const std::string& name, void** args, const Acc& acc) {
+    std::vector<std::vector<uint8_t>> mask(g_bufs.size());
+    std::vector<std::vector<uint32_t>> saved(g_bufs.size());
+    for (size_t i = 0; i < g_bufs.size(); ++i) {
+        mask[i].assign(g_bufs[i].bytes / 4, 0);
+        saved[i].assign((uint32_t*)g_bufs[i].p, (uint32_t*)g_bufs[i].p + g_bufs[i].bytes / 4);
+    }
+    mark(mask, acc.recs);
+    if (name.find("wgrad_umma_bulk_kernel") != std::string::npos) {      // the reference routine reads the groups' own views, not the
+        Acc views;                                                           // split arrays the device kernel is fed from
+        decode_wgrad_groups(views, *static_cast<const UmmaWgradLaunch*>(args[0]), nullptr);
+        mark(mask, views.recs);
+    }
+    for (size_t i = 0; i < g_bufs.size(); ++i) {
+        uint32_t* w = (uint32_t*)g_bufs[i].p;
+        for (size_t k = 0; k < mask[i].size(); ++k) if (!mask[i][k]) w[k] = kPoison;
+    }
+    const bool ok = cpudev::execute(name, args);
+    long long stray_writes = 0, stray_reads = 0;
+    for (size_t i = 0; i < g_bufs.size(); ++i) {
+        uint32_t* w = (uint32_t*)g_bufs[i].p;
+        for (size_t k = 0; k < mask[i].size(); ++k) {
+            if (!(mask[i][k] & 2)) {                                   // not in the decoded write footprint
+                const uint32_t expect = mask[i][k] ? saved[i][k] : kPoison;
+                if (w[k] != expect) ++stray_writes;
+                w[k] = saved[i][k];
+            } else {
+                float now, before;
+                memcpy(&now, &w[k], 4); memcpy(&before, &saved[i][k], 4);
+                if (now != now && before == before) {                  // a NaN appeared
+                    if (stray_reads < 3 && getenv("FAKECUDA_POISON_DEBUG"))
+                        fprintf(stderr, "poison: %s: NaN at buffer %zu word %zu (address %llu)\n", name.c_str(), i, k,
+                                (unsigned long long)((uintptr_t)g_bufs[i].p + 4 * k));
+                    ++stray_reads;
+                }
+            }
+        }
+    }
+    if (!ok) return "UNKNOWN:";
+    if (stray_writes || stray_reads) {
+        char b[160];
+        snprintf(b, sizeof(b), "FOOTPRINT-MISS(%lld_words_written_outside,%lld_NaNs_from_reads_outside):", stray_writes, stray_reads);
+        return b;
+    }
+    return "";
 }
 
 cudaError_t record_launch(const void* func, void** args, void* stream, dim3 grid, dim3 block, size_t smem, unsigned cluster_x) {
@@ -339,14 +429,17 @@ cudaError_t record_launch(const void* func, void** args, void* stream, dim3 grid
         if (at != g_max_dyn_smem.end()) attr = at->second;
     }
     bool known = false;
-    std::string acc = decode(name, args, &known);
-    if (g_execute && known && !cpudev::execute(name, args)) known = false;
+    Acc decoded = decode(name, args, &known);
+    const std::string& acc = decoded.s;
+    std::string flag;
+    if (g_execute == 2 && known) flag = poison_checked_execute(name, args, decoded);
+    else if (g_execute && known && !cpudev::execute(name, args)) known = false;
     for (char& c : name) if (c == ' ') c = '_';                // one token per field in the trace line
     char head[64], geo[160];
     snprintf(head, sizeof(head), "L %llu ", (unsigned long long)(uintptr_t)stream);
     // launch geometry: grid, block, dynamic shared memory asked for, the kernel's opted-in maximum (-1 = never set), cluster width
     snprintf(geo, sizeof(geo), " G:%u:%u:%u:%u:%u:%u:%zu:%d:%u", grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, attr, cluster_x);
-    emit(std::string(head) + (known ? "" : "UNKNOWN:") + name + geo + acc);
+    emit(std::string(head) + (known ? "" : "UNKNOWN:") + flag + name + geo + acc);
     return cudaSuccess;
 }
 
@@ -356,7 +449,8 @@ cudaError_t record_launch(const void* func, void** args, void* stream, dim3 grid
 extern "C" {
 
 void fakecuda_reset() { std::lock_guard<std::mutex> lk(g_mu); g_trace.clear(); }
-void fakecuda_set_execute(int on) { g_execute = on != 0; cpudev::reset(); }
+void fakecuda_set_execute(int on) { g_execute = on; cpudev::reset(); g_bufs.clear(); }
+void fakecuda_register_buffer(void* p, long long bytes) { g_bufs.push_back({static_cast<uint8_t*>(p), (size_t)bytes}); }
 
 long long fakecuda_trace(char* buf, long long capacity) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -40,7 +40,9 @@ def main():
     fake = ctypes.CDLL(os.path.join(os.path.dirname(wun.LIB_PATH), "libfakecudart.so"))
     fake.fakecuda_trace.restype = ctypes.c_longlong
     fake.fakecuda_trace.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
-    fake.fakecuda_set_execute(1)
+    poison = bool(os.environ.get("HOSTSIM_POISON"))          # the footprint "poison test" of fake_cudart.cpp (execute mode 2)
+    fake.fakecuda_set_execute(2 if poison else 1)
+    fake.fakecuda_register_buffer.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
 
     cfg = Config.build_config(named, overrides, experiment_id=0)["model_config"]
     try:
@@ -96,8 +98,11 @@ def main():
     VP = ctypes.c_void_p
     P = lambda a: VP(a.ctypes.data)      # noqa: E731
     MAIN = VP(0x10)
+    if poison:
+        for a in (par, grads, m, v, ws, ws_inf, mix_d, tg_d, out_d, loss, state):
+            fake.fakecuda_register_buffer(P(a), a.size * 4)
 
-    res = {"unknown": []}
+    res = {"unknown": [], "footprint_miss": []}
     lr = 1e-3
     def engine_params():
         return {pname: par[off:off + numel].reshape(np.asarray(params[pname]).shape).copy() for pname, shape, off, numel in eng.param_table}
@@ -227,12 +232,17 @@ def main():
     nbytes = fake.fakecuda_trace(None, 0)
     buf = ctypes.create_string_buffer(int(nbytes))
     fake.fakecuda_trace(buf, nbytes)
+    if os.environ.get("HOSTSIM_DUMP_TRACE"):
+        open(os.environ["HOSTSIM_DUMP_TRACE"], "w").write(buf.value.decode())
     kinds = {}
     for ln in buf.value.decode().splitlines():
         if ln.startswith("L "):
             name = ln.split(" ")[2]
             if name.startswith("UNKNOWN:"):
                 res["unknown"].append(name)
+            if name.startswith("FOOTPRINT-MISS"):
+                res["footprint_miss"].append(name[:160])
+                name = name.split(":", 1)[1]
             k = name.split("(")[0].replace("void_", "").replace("wun::", "").replace("UNKNOWN:", "")
             kinds[k] = kinds.get(k, 0) + 1
     res["kernels"] = kinds
